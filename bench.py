@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- exact top-k search throughput of the B200 shard (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
+    python bench.py --impl reference ...                     (the CPU path, same metric/config)
+
+A "step" is one search of one batch of synthetic queries over the whole (sharded) database.
+Workload at N=1 = BASELINE config[1]: 1M x 512 fp32 unit-norm rows, cosine, top-10.  `value` is
+the batched (batch 1024) queries/s with queries and results resident in HBM; the same line also
+carries the single-query (batch 1) scan numbers under "single_query", because config[1] names
+both.  N > 1 shards the SAME database by contiguous row ranges (strong scaling), every rank
+searches its shard and the per-rank top-k lists are all-gathered over NCCL and merged on the GPU
+(the coordinator's scatter-gather, src/coordinator/handler.py:191-216).
+
+Prints ONE JSON line (rank 0).  Inputs are larger than L2 (2 GB shard vs 126 MB), so no flush.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED_DB, SEED_QUERY = 0xD5B200, 0xC0FFEE
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p["bf16_tflops"]),
+                "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=1_000_000, help="total database rows (all GPUs)")
+    ap.add_argument("--dim", type=int, default=512)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--metric", default="cosine", choices=["l2", "ip", "cosine"])
+    ap.add_argument("--store", default="f32", choices=["f32", "f16"])
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--single-steps", type=int, default=0, help="steps for the batch-1 leg (default: 5*steps)")
+    ap.add_argument("--no-single", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-queries", type=int, default=0)
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return f"{a.rows}x{a.dim} {a.store} {a.metric} top-{a.k}, batch {a.batch} (+ batch 1)"
+
+
+# --------------------------------------------------------------------------------------------
+# CPU legs (oracle port: the reference's own path -- hnswlib/plyvel/thrift -- is not installable)
+# --------------------------------------------------------------------------------------------
+def cpu_knn_qps(a, nq: int, rows_cap: int = 1_000_000):
+    """Times the oracle's exact scan (oracle/knn_ref.c, OpenMP, all host threads) for nq queries
+    over min(rows, rows_cap) rows and scales linearly to the full row count."""
+    from oracle import c_ref
+    n = min(a.rows, rows_cap)
+    rows = c_ref.synth_rows(SEED_DB, 0, n, a.dim)
+    stored = c_ref.normalize(rows) if a.metric == "cosine" else rows
+    if a.store == "f16":
+        stored = stored.astype(np.float16).astype(np.float32)
+    q = c_ref.synth_rows(SEED_QUERY, 0, nq, a.dim)
+    c_ref.knn(q[:1], stored[:1000], None, a.k, a.metric)        # warm the OpenMP pool
+    t0 = time.perf_counter()
+    c_ref.knn(q, stored, None, a.k, a.metric)
+    dt = time.perf_counter() - t0
+    dt_full = dt * (a.rows / n)
+    return nq / dt_full, c_ref.num_threads(), f"{nq} queries x {n} rows in {dt:.2f}s" + (
+        f", scaled x{a.rows / n:.1f} to {a.rows} rows" if n != a.rows else "")
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nq = a.cpu_queries or 32
+    vals, desc, cores = [], "", 1
+    for i in range(a.warmup + a.steps):
+        qps, cores, desc = cpu_knn_qps(a, nq)
+        if i >= a.warmup:
+            vals.append(qps)
+    v = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": "queries/sec exact top-k", "value": v, "unit": "queries/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * nq / v,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "inputs": "larger than L2/LLC (2 GB)"},
+        "cpu_baseline": {"value": v, "unit": "queries/s", "cores": cores, "kind": "port",
+                         "sample": "per step: " + desc + " (oracle/knn_ref.c exact scan, OpenMP)"},
+        "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import dvdb_b200 as vdb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.gpus != world:
+        if world == 1 and a.gpus > 1:
+            raise SystemExit("launch N>1 with torchrun (python -m torch.distributed.run --nproc-per-node N ...)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = vdb._ffi.lib()
+
+    # ---- shard: contiguous row range of the same synthetic database --------------------------
+    lo = a.rows * rank // world
+    hi = a.rows * (rank + 1) // world
+    ix = vdb.Index(a.metric, a.dim, store_dtype=a.store, device=local)
+    ix.init_index(hi - lo)
+    ix.add_synthetic(SEED_DB, lo, hi - lo, label_start=lo)
+    elem = 2 if a.store == "f16" else 4
+    ld = ix.get_stat("ld")
+    shard_bytes = (hi - lo) * ld * elem
+
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def make_queries(nq):
+        q = torch.empty((nq, a.dim), dtype=torch.float32, device=dev)
+        vdb._ffi.check(lib.vdb_synth_dev(SEED_QUERY, 0, nq, a.dim, q.data_ptr(), stream), "synth")
+        return q
+
+    def device_leg(nq, steps, warmup):
+        """queries + results resident in HBM; returns (seconds for `steps`, dominant-kernel ns, launches)"""
+        q = make_queries(nq)
+        ids = torch.empty((nq, a.k), dtype=torch.int64, device=dev)
+        dd = torch.empty((nq, a.k), dtype=torch.float32, device=dev)
+        cnt = torch.empty((nq,), dtype=torch.int32, device=dev)
+        if world > 1:
+            g_ids = torch.empty((world, nq, a.k), dtype=torch.int64, device=dev)
+            g_dd = torch.empty((world, nq, a.k), dtype=torch.float32, device=dev)
+            o_ids = torch.empty((nq, a.k), dtype=torch.int64, device=dev)
+            o_dd = torch.empty((nq, a.k), dtype=torch.float32, device=dev)
+
+        def step():
+            ix.search_device(q.data_ptr(), nq, a.k, ids.data_ptr(), dd.data_ptr(), cnt.data_ptr(), stream)
+            if world > 1:
+                dist.all_gather_into_tensor(g_ids, ids)
+                dist.all_gather_into_tensor(g_dd, dd)
+                vdb._ffi.check(lib.vdb_merge_topk(g_dd.data_ptr(), g_ids.data_ptr(), world, nq, a.k, a.k,
+                                                  o_dd.data_ptr(), o_ids.data_ptr(), 1, local, stream), "merge")
+
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ix.set_option("profile", 1)
+        l0 = vdb.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ix.set_option("profile", 0)
+        launches = vdb.launch_count() - l0
+        nprof = ix.get_stat("profile_count")
+        kern_ns = ix.get_stat("profile_ns")
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        final = (o_ids if world > 1 else ids)[:1].cpu().numpy()
+        return float(ms.item()) * 1e-3, kern_ns, nprof, launches, final
+
+    def e2e_leg(nq, steps, warmup):
+        """through the public host-buffer API: H2D of the queries and D2H of the results inside the timed region"""
+        qh = make_queries(nq).cpu().numpy()          # host copy made outside the timed region
+        if world > 1:
+            g_ids = torch.empty((world, nq, a.k), dtype=torch.int64, device=dev)
+            g_dd = torch.empty((world, nq, a.k), dtype=torch.float32, device=dev)
+            o_ids = torch.empty((nq, a.k), dtype=torch.int64, device=dev)
+            o_dd = torch.empty((nq, a.k), dtype=torch.float32, device=dev)
+            pin_q = torch.from_numpy(qh).pin_memory()
+
+        def step():
+            if world == 1:
+                return ix.knn_query_padded(qh, a.k)
+            qd = pin_q.to(dev, non_blocking=True)
+            ids = torch.empty((nq, a.k), dtype=torch.int64, device=dev)
+            dd = torch.empty((nq, a.k), dtype=torch.float32, device=dev)
+            ix.search_device(qd.data_ptr(), nq, a.k, ids.data_ptr(), dd.data_ptr(), 0, stream)
+            dist.all_gather_into_tensor(g_ids, ids)
+            dist.all_gather_into_tensor(g_dd, dd)
+            vdb._ffi.check(lib.vdb_merge_topk(g_dd.data_ptr(), g_ids.data_ptr(), world, nq, a.k, a.k,
+                                              o_dd.data_ptr(), o_ids.data_ptr(), 1, local, stream), "merge")
+            return o_ids.cpu(), o_dd.cpu()
+
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return float(dt.item())
+
+    peaks = measured_peaks()
+    with ClockSampler(local) as clk:
+        sec, kern_ns, nprof, launches, _ = device_leg(a.batch, a.steps, a.warmup)
+        e2e_sec = e2e_leg(a.batch, a.steps, a.warmup)
+        single = None
+        if not a.no_single:
+            ss = a.single_steps or max(5 * a.steps, 50)
+            s_sec, s_kern_ns, s_nprof, s_launch, _ = device_leg(1, ss, a.warmup)
+            s_e2e = e2e_leg(1, ss, a.warmup)
+            t_k = s_kern_ns * 1e-9 / max(s_nprof, 1)
+            ach = shard_bytes / t_k / 1e9
+            single = {
+                "value": ss / s_sec, "unit": "queries/s", "ms_per_query": 1e3 * s_sec / ss, "steps": ss,
+                "e2e": {"value": ss / s_e2e, "unit": "queries/s", "h2d_bytes_per_step": a.dim * 4,
+                        "d2h_bytes_per_step": a.k * 12 + 4},
+                "roofline": {"bound": "hbm", "kernel": "scan_topk_kernel", "achieved": ach, "peak": peaks["hbm_gbs"],
+                             "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "peak_source": peaks["source"],
+                             "algorithmic_bytes_per_launch": shard_bytes, "kernel_us": t_k * 1e6, "traffic": None},
+                "gpu_launches": s_launch,
+            }
+
+    # roofline of the batched leg's dominant kernel
+    passes_per_step = nprof / max(a.steps, 1)
+    t_kernel = kern_ns * 1e-9 / max(nprof, 1)
+    tensor_batches = ix.get_stat("tensor_batches")
+    if tensor_batches > 0:
+        flops = 2.0 * a.batch * (hi - lo) * a.dim
+        ach = flops / t_kernel / 1e12
+        tf32 = a.store == "f32"
+        peak = peaks["bf16_tflops_sustained"] * (0.5 if tf32 else 1.0)
+        roof = {"bound": "tensor", "kernel": "gemm_topk_kernel", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": ach / peak, "peak_source": peaks["source"] + (" bf16 sustained x0.5 (tf32)" if tf32 else " bf16 sustained"),
+                "algorithmic_flops_per_launch": flops, "kernel_us": t_kernel * 1e6, "traffic": None}
+    else:
+        ach = shard_bytes / t_kernel / 1e9
+        roof = {"bound": "hbm", "kernel": "scan_topk_kernel", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / peaks["hbm_gbs"], "peak_source": peaks["source"],
+                "algorithmic_bytes_per_launch": shard_bytes, "kernel_us": t_kernel * 1e6,
+                "launches_per_step": passes_per_step, "traffic": None}
+
+    if rank == 0:
+        cpu = None
+        if not a.no_cpu and world == 1:
+            qps, cores, desc = cpu_knn_qps(a, a.cpu_queries or 64)
+            cpu = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+                   "sample": desc + " (oracle/knn_ref.c exact scan, OpenMP)"}
+        line = {
+            "metric": "queries/sec exact top-k", "value": a.batch * a.steps / sec, "unit": "queries/s",
+            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * sec / a.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32" if a.store == "f32" else "f16-stored/f32-accumulate", "data": "synthetic",
+            "config": {"workload": workload_name(a), "rows_per_gpu": hi - lo, "sharding": f"contiguous rows x{world}",
+                       "l2": "inputs larger than L2 (no flush needed)", "path": "tensor" if tensor_batches > 0 else "scan"},
+            "e2e": {"value": a.batch * a.steps / e2e_sec, "unit": "queries/s",
+                    "h2d_bytes_per_step": a.batch * a.dim * 4, "d2h_bytes_per_step": a.batch * a.k * 12 + a.batch * 4},
+            "gpu_launches": launches,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "single_query": single,
+            "clocks": clk.summary(),
+            "recall_at_k": None,
+            "fallback_queries": ix.get_stat("fallback_queries"),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

@@ -1,0 +1,33 @@
+// gemm_topk.h -- host interface of the batched tensor-core search (K2 + K4), gemm_topk.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+namespace vdbk {
+
+struct GemmPlan {          // per shard: cached tensor maps for the row slab
+    void* impl = nullptr;
+};
+struct GemmWorkspace {     // per in-flight call: candidate lists, thresholds, fallback flags
+    void* impl = nullptr;
+};
+
+struct GemmSearchArgs {
+    const void* rows; int ld; int dim; bool f16; uint32_t n_rows;
+    const float* sqnorm; const uint32_t* labels; const uint32_t* tomb;
+    const float* q;        // prepared queries [nq][ld] fp32
+    const float* qn2;      // [nq]
+    size_t nq; int k; int metric;   // 0 = L2, 1 = 1 - dot
+    const unsigned int* d_max_sqnorm_bits;
+    int num_sms;
+    int64_t* out_ids; float* out_dist; int* out_counts;
+};
+
+bool gemm_topk_supported(int dim, int ld, bool f16, int k, size_t n_rows);
+cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearchArgs& a, cudaStream_t st, std::string& err);
+void gemm_plan_free(GemmPlan& plan);
+void gemm_workspace_free(GemmWorkspace& ws);
+long gemm_plan_fallbacks(const GemmPlan& plan);
+
+}  // namespace vdbk

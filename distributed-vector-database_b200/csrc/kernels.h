@@ -1,0 +1,65 @@
+// kernels.h -- launcher interface between the C-ABI host layer (vdb_api.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace vdbk {
+
+// ---- K1 scan (scan_topk.cu) ---------------------------------------------------------------
+struct ScanParams {
+    const void* rows;        // [n_rows][ld] T, row stride row_bytes
+    uint32_t row_bytes;      // ld * sizeof(T), multiple of 512
+    uint32_t ld;             // padded row length in elements
+    uint32_t n_rows;
+    const uint32_t* labels;  // [n_rows] or null (label == row)
+    const uint32_t* tomb;    // bitmap, 1 = deleted, or null
+    const float* q;          // [nq][ld] prepared queries (fp32, zero padded)
+    int nq;                  // 1..8
+    int k;
+    int metric;              // 0 = squared L2 (direct form), 1 = 1 - dot
+    int stages;              // filled by the launcher
+    uint64_t* out_keys;      // [nq][grid][k]
+};
+cudaError_t launch_scan_topk(ScanParams p, bool f16, int num_sms, int* grid_out, cudaStream_t st);
+int scan_max_k(int nq_t, int ld, uint32_t row_bytes);
+
+// ---- K5 merge (merge_topk.cu) -------------------------------------------------------------
+struct MergeParams {
+    // input mode A: packed keys, per query a contiguous block of n_in keys
+    const uint64_t* in_keys;   // [nq][n_in]
+    // input mode B: (dist,id) lists laid out [G][nq][k_in]; id < 0 is padding
+    const float* in_dist;
+    const int64_t* in_ids;
+    int G, k_in;
+    size_t nq;
+    int n_in;                  // keys per query (mode A) or G*k_in (mode B)
+    int k_out;
+    uint64_t* out_keys;        // optional [nq][k_out]
+    int64_t* out_ids;          // optional [nq][k_out]  (-1 padded)
+    float* out_dist;           // optional [nq][k_out]  (+inf padded)
+    int* out_counts;           // optional [nq]
+};
+cudaError_t launch_merge_topk(const MergeParams& p, cudaStream_t st);
+
+// ---- K0 / K3 / utilities (insert.cu) ------------------------------------------------------
+// queries [nq][dim] fp32 -> prepared [nq][ld] fp32 (normalised when cosine, zero padded),
+// qn2[nq] = sum of squares of the prepared query.
+cudaError_t launch_prepare_queries(const float* q, size_t nq, int dim, int ld, bool normalize, float* out,
+                                   float* qn2, cudaStream_t st);
+// src [n][dim] fp32 -> shard rows [row0 .. row0+n) (T = f32/f16, stride ld), sqnorm, max norm.
+cudaError_t launch_insert_rows(const float* src, size_t n, int dim, int ld, bool normalize, bool f16, void* rows,
+                               float* sqnorm, size_t row0, unsigned int* max_sqnorm_bits, cudaStream_t st);
+cudaError_t launch_synth_rows(uint64_t seed, uint64_t row_start, size_t n, int dim, float* out, cudaStream_t st);
+cudaError_t launch_set_bits(uint32_t* bitmap, const uint32_t* rows, size_t n, bool set, cudaStream_t st);
+cudaError_t launch_gather_rows(const void* rows, int ld, int dim, bool f16, const uint32_t* idx, size_t n, float* out,
+                               cudaStream_t st);
+cudaError_t launch_iota_u32(uint32_t* out, size_t n, uint32_t start, cudaStream_t st);
+
+// ---- K2 / K4 batched tensor-core path (gemm_topk.cu, rerank.cu) ---------------------------
+struct GemmTopkPlan;  // opaque, owns tensor maps
+
+uint64_t launch_count();
+void count_launch();
+
+}  // namespace vdbk

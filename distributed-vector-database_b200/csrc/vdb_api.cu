@@ -1,0 +1,831 @@
+// vdb_api.cu -- host side of the C ABI declared in include/vdb.h.
+//
+// Owns the GPU-resident shard (rows, norms, labels, tombstone bitmap), the label->row map,
+// a pool of per-call workspaces (stream + scratch) and dispatches a search to the scan kernel
+// (K1) or the tensor-core kernel (K2) followed by the merge (K5).  No CPU compute path exists:
+// if CUDA is unavailable every entry point fails with VDB_ECUDA.
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <shared_mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/vdb.h"
+#include "common.cuh"
+#include "gemm_topk.h"
+#include "kernels.h"
+
+namespace vdbk {
+static std::atomic<uint64_t> g_launches{0};
+uint64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace vdbk
+
+using namespace vdbk;
+
+static thread_local std::string t_err;
+static int fail(int code, const std::string& msg) {
+    t_err = msg;
+    return code;
+}
+#define CU_TRY(expr)                                                                                  \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess) {                                                                      \
+            cudaGetLastError();                                                                       \
+            return fail(VDB_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));               \
+        }                                                                                             \
+    } while (0)
+
+namespace {
+
+constexpr int K_MAX = 1024;
+constexpr size_t STAGE_ROWS = 32768;   // insert staging chunk
+constexpr int MAX_WORKSPACES = 8;
+
+struct Workspace {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    bool used = false;
+    // device scratch (grow only)
+    float* d_q_in = nullptr;  size_t q_in_cap = 0;     // raw queries (host path)
+    float* d_q = nullptr;     size_t q_cap = 0;        // prepared queries [nq][ld]
+    float* d_qn2 = nullptr;   size_t qn2_cap = 0;
+    uint64_t* d_keys = nullptr; size_t keys_cap = 0;   // per-CTA candidate lists
+    int64_t* d_ids = nullptr; size_t ids_cap = 0;      // [nq*k]
+    float* d_dist = nullptr;  size_t dist_cap = 0;
+    int* d_cnt = nullptr;     size_t cnt_cap = 0;
+    // pinned host staging
+    float* h_q = nullptr; size_t h_q_cap = 0;
+    uint8_t* h_out = nullptr; size_t h_out_cap = 0;
+    GemmWorkspace gemm;
+};
+
+template <typename T>
+cudaError_t grow(T*& p, size_t& cap, size_t need) {
+    if (need <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = std::max(need, (size_t)4096);
+    cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+}
+template <typename T>
+cudaError_t grow_host(T*& p, size_t& cap, size_t need) {
+    if (need <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = std::max(need, (size_t)4096);
+    cudaError_t e = cudaMallocHost((void**)&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+}
+
+}  // namespace
+
+struct vdb {
+    int dim = 0, ld = 0, metric = 0, dtype = 0, device = 0, num_sms = 148;
+    size_t capacity = 0;
+    std::atomic<size_t> count{0};
+    size_t live = 0;
+    void* rows = nullptr;
+    float* sqnorm = nullptr;
+    uint32_t* labels = nullptr;
+    uint32_t* tomb = nullptr;
+    unsigned int* d_max_sqnorm = nullptr;
+    float* d_stage = nullptr;
+    uint32_t* d_idx = nullptr; size_t idx_cap = 0;
+    cudaStream_t wstream = nullptr;   // writer stream
+    mutable std::shared_mutex mu;
+    // label -> row
+    bool affine = true;
+    int64_t label_base = 0;
+    std::unordered_map<int64_t, uint32_t> map;
+    std::vector<uint64_t> h_dead;     // host mirror of the tombstone bitmap
+    bool any_dead = false;
+    // workspaces
+    std::mutex ws_mu;
+    std::condition_variable ws_cv;
+    std::vector<std::unique_ptr<Workspace>> ws_all;
+    std::vector<Workspace*> ws_free;
+    // options / stats
+    std::atomic<long> opt_path{0};          // 0 auto, 1 force scan, 2 force tensor
+    std::atomic<long> opt_scan_batch{8};    // nq <= this takes the scan kernel in auto mode
+    std::atomic<long> stat_fallback{0}, stat_tensor_batches{0}, stat_scan_passes{0};
+    GemmPlan gemm_plan;
+    // opt-in timing of the dominant kernel (scan or tensor) with CUDA events on the launching stream
+    std::atomic<long> opt_profile{0};
+    std::mutex prof_mu;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pool;
+
+    size_t elem() const { return dtype == VDB_F16 ? 2 : 4; }
+    size_t row_bytes() const { return (size_t)ld * elem(); }
+    bool dead(size_t r) const { return (h_dead[r >> 6] >> (r & 63)) & 1; }
+    void set_dead(size_t r, bool v) {
+        if (v) h_dead[r >> 6] |= (1ull << (r & 63));
+        else h_dead[r >> 6] &= ~(1ull << (r & 63));
+    }
+    // returns row or -1
+    long long row_of(int64_t label) const {
+        if (affine) {
+            const int64_t r = label - label_base;
+            return (r >= 0 && (size_t)r < count.load()) ? r : -1;
+        }
+        auto it = map.find(label);
+        return it == map.end() ? -1 : (long long)it->second;
+    }
+};
+
+namespace {
+
+int alloc_shard(vdb* db) {
+    CU_TRY(cudaSetDevice(db->device));
+    const size_t cap = std::max(db->capacity, (size_t)1);
+    CU_TRY(cudaMalloc(&db->rows, cap * db->row_bytes()));
+    CU_TRY(cudaMalloc((void**)&db->sqnorm, cap * sizeof(float)));
+    CU_TRY(cudaMalloc((void**)&db->labels, cap * sizeof(uint32_t)));
+    const size_t words = (cap + 31) / 32 + 4;
+    CU_TRY(cudaMalloc((void**)&db->tomb, words * sizeof(uint32_t)));
+    CU_TRY(cudaMemset(db->tomb, 0, words * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc((void**)&db->d_max_sqnorm, sizeof(unsigned int)));
+    CU_TRY(cudaMemset(db->d_max_sqnorm, 0, sizeof(unsigned int)));
+    CU_TRY(cudaMalloc((void**)&db->d_stage, STAGE_ROWS * (size_t)db->dim * sizeof(float)));
+    CU_TRY(cudaStreamCreateWithFlags(&db->wstream, cudaStreamNonBlocking));
+    db->h_dead.assign((cap + 63) / 64, 0);
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, db->device));
+    db->num_sms = prop.multiProcessorCount;
+    if (prop.major != 10)
+        return fail(VDB_ECUDA, std::string("this library is built for sm_100a (B200); device is ") + prop.name);
+    return VDB_OK;
+}
+
+void free_workspace(Workspace* w) {
+    if (w->d_q_in) cudaFree(w->d_q_in);
+    if (w->d_q) cudaFree(w->d_q);
+    if (w->d_qn2) cudaFree(w->d_qn2);
+    if (w->d_keys) cudaFree(w->d_keys);
+    if (w->d_ids) cudaFree(w->d_ids);
+    if (w->d_dist) cudaFree(w->d_dist);
+    if (w->d_cnt) cudaFree(w->d_cnt);
+    if (w->h_q) cudaFreeHost(w->h_q);
+    if (w->h_out) cudaFreeHost(w->h_out);
+    gemm_workspace_free(w->gemm);
+    if (w->done) cudaEventDestroy(w->done);
+    if (w->stream) cudaStreamDestroy(w->stream);
+}
+
+Workspace* acquire_ws(vdb* db) {
+    std::unique_lock<std::mutex> lk(db->ws_mu);
+    for (;;) {
+        if (!db->ws_free.empty()) {
+            Workspace* w = db->ws_free.back();
+            db->ws_free.pop_back();
+            return w;
+        }
+        if ((int)db->ws_all.size() < MAX_WORKSPACES) {
+            auto w = std::make_unique<Workspace>();
+            if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&w->done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+            db->ws_all.push_back(std::move(w));
+            return db->ws_all.back().get();
+        }
+        db->ws_cv.wait(lk);
+    }
+}
+void release_ws(vdb* db, Workspace* w) {
+    {
+        std::lock_guard<std::mutex> lk(db->ws_mu);
+        db->ws_free.push_back(w);
+    }
+    db->ws_cv.notify_one();
+}
+struct WsGuard {
+    vdb* db; Workspace* w;
+    ~WsGuard() { if (w) release_ws(db, w); }
+};
+
+struct ProfScope {   // records start/stop events around the dominant kernel when profiling is on
+    vdb* db; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(vdb* d, cudaStream_t s) : db(d), st(s) {
+        if (!db->opt_profile.load()) return;
+        std::lock_guard<std::mutex> lk(db->prof_mu);
+        if (!db->prof_pool.empty()) { a = db->prof_pool.back().first; b = db->prof_pool.back().second; db->prof_pool.pop_back(); }
+        else { cudaEventCreate(&a); cudaEventCreate(&b); }
+        cudaEventRecord(a, st);
+    }
+    ~ProfScope() {
+        if (!a) return;
+        cudaEventRecord(b, st);
+        std::lock_guard<std::mutex> lk(db->prof_mu);
+        db->prof_events.emplace_back(a, b);
+    }
+};
+
+// Enqueue a search of nq device-resident raw queries on `st`.  Outputs are device pointers.
+int search_core(vdb* db, Workspace* ws, const float* d_q_raw, size_t nq, int k, int64_t* d_ids, float* d_dist,
+                int* d_cnt, cudaStream_t st, size_t n) {
+    const bool f16 = db->dtype == VDB_F16;
+    MergeParams mp{};
+    mp.nq = nq;
+    mp.k_out = k;
+    mp.out_ids = d_ids;
+    mp.out_dist = d_dist;
+    mp.out_counts = d_cnt;
+    if (n == 0) {  // empty shard: all padding (reference: success + empty lists, handler.py:353-354)
+        CU_TRY(grow(ws->d_keys, ws->keys_cap, 16));
+        mp.in_keys = ws->d_keys;
+        mp.n_in = 0;
+        CU_TRY(launch_merge_topk(mp, st));
+        return VDB_OK;
+    }
+    CU_TRY(grow(ws->d_q, ws->q_cap, nq * (size_t)db->ld));
+    CU_TRY(grow(ws->d_qn2, ws->qn2_cap, nq));
+    CU_TRY(launch_prepare_queries(d_q_raw, nq, db->dim, db->ld, db->metric == VDB_COSINE, ws->d_q, ws->d_qn2, st));
+
+    const long path = db->opt_path.load();
+    bool tensor = false;
+    if (path == 2) tensor = true;
+    else if (path == 0) tensor = (long)nq > db->opt_scan_batch.load();
+    if (tensor && !gemm_topk_supported(db->dim, db->ld, f16, k, n)) {
+        if (path == 2) return fail(VDB_EINVAL, "tensor path forced but unsupported for this shape/k");
+        tensor = false;
+    }
+    if (tensor) {
+        GemmSearchArgs a{};
+        a.rows = db->rows; a.ld = db->ld; a.dim = db->dim; a.f16 = f16; a.n_rows = (uint32_t)n;
+        a.sqnorm = db->sqnorm; a.labels = db->labels; a.tomb = db->any_dead ? db->tomb : nullptr;
+        a.q = ws->d_q; a.qn2 = ws->d_qn2; a.nq = nq; a.k = k;
+        a.metric = db->metric == VDB_L2 ? 0 : 1;
+        a.d_max_sqnorm_bits = db->d_max_sqnorm;
+        a.num_sms = db->num_sms;
+        a.out_ids = d_ids; a.out_dist = d_dist; a.out_counts = d_cnt;
+        std::string err;
+        cudaError_t e;
+        {
+            ProfScope prof(db, st);
+            e = gemm_topk_search(db->gemm_plan, ws->gemm, a, st, err);
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(VDB_ECUDA, "gemm_topk_search: " + (err.empty() ? std::string(cudaGetErrorString(e)) : err));
+        }
+        db->stat_tensor_batches.fetch_add(1);
+        return VDB_OK;
+    }
+
+    // ---- scan path: groups of up to 8 queries per pass over the shard ----
+    ScanParams sp{};
+    sp.rows = db->rows;
+    sp.row_bytes = (uint32_t)db->row_bytes();
+    sp.ld = db->ld;
+    sp.n_rows = (uint32_t)n;
+    sp.labels = db->labels;
+    sp.tomb = db->any_dead ? db->tomb : nullptr;
+    sp.k = k;
+    sp.metric = db->metric == VDB_L2 ? 0 : 1;
+    const uint32_t nchunks = (uint32_t)((n + 15) / 16);
+    const int grid = (int)std::min<uint32_t>((uint32_t)db->num_sms, nchunks);
+    CU_TRY(grow(ws->d_keys, ws->keys_cap, nq * (size_t)grid * k));
+    for (size_t g = 0; g < nq; g += 8) {
+        sp.nq = (int)std::min<size_t>(8, nq - g);
+        sp.q = ws->d_q + g * (size_t)db->ld;
+        sp.out_keys = ws->d_keys + g * (size_t)grid * k;
+        int grid_used = 0;
+        {
+            ProfScope prof(db, st);
+            CU_TRY(launch_scan_topk(sp, f16, db->num_sms, &grid_used, st));
+        }
+        if (grid_used != grid) return fail(VDB_ECUDA, "internal: scan grid mismatch");
+        db->stat_scan_passes.fetch_add(1);
+    }
+    mp.in_keys = ws->d_keys;
+    mp.n_in = grid * k;
+    CU_TRY(launch_merge_topk(mp, st));
+    return VDB_OK;
+}
+
+int check_k(const vdb* db, int k, size_t nq) {
+    if (k < 1 || k > K_MAX) return fail(VDB_EINVAL, "k must be in [1, 1024]");
+    const int nq_t = nq >= 8 ? 8 : nq >= 4 ? 4 : nq >= 2 ? 2 : 1;
+    const int kmax = scan_max_k(nq_t, db->ld, (uint32_t)db->row_bytes());
+    if (kmax < 1) return fail(VDB_EINVAL, "dim too large for the scan kernel's shared-memory ring");
+    if (k > kmax) return fail(VDB_EINVAL, "k too large for this dim");
+    return VDB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vdb_last_error(void) { return t_err.c_str(); }
+const char* vdb_version(void) { return "vdb_b200 0.1 (sm_100a)"; }
+uint64_t vdb_launch_count(void) { return launch_count(); }
+
+int vdb_create(int dim, int metric, int store_dtype, size_t capacity, int device, vdb_t** out) {
+    if (!out) return fail(VDB_EINVAL, "out is null");
+    *out = nullptr;
+    if (dim < 1 || dim > 8192) return fail(VDB_EINVAL, "dim out of range");
+    if (metric < VDB_L2 || metric > VDB_COSINE) return fail(VDB_EINVAL, "metric must be 0 (l2), 1 (ip) or 2 (cosine)");
+    if (store_dtype != VDB_F32 && store_dtype != VDB_F16) return fail(VDB_EINVAL, "store_dtype must be 0 (f32) or 1 (f16)");
+    if (capacity >= 0xFFFFFFF0ull) return fail(VDB_EINVAL, "capacity must be below 2^32 rows per shard");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(VDB_ECUDA, "no CUDA device: this library has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(VDB_EINVAL, "device index out of range");
+    auto db = std::make_unique<vdb>();
+    db->dim = dim;
+    db->metric = metric;
+    db->dtype = store_dtype;
+    db->device = device;
+    db->capacity = capacity;
+    const int unit = store_dtype == VDB_F16 ? 256 : 128;   // one 512-byte warp load
+    db->ld = (dim + unit - 1) / unit * unit;
+    if (scan_max_k(1, db->ld, (uint32_t)db->row_bytes()) < 1) return fail(VDB_EINVAL, "dim too large for the scan kernel");
+    int rc = alloc_shard(db.get());
+    if (rc != VDB_OK) {
+        vdb_destroy(db.release());
+        return rc;
+    }
+    *out = db.release();
+    return VDB_OK;
+}
+
+void vdb_destroy(vdb_t* db) {
+    if (!db) return;
+    cudaSetDevice(db->device);
+    cudaDeviceSynchronize();
+    for (auto& w : db->ws_all) free_workspace(w.get());
+    for (auto& ev : db->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    for (auto& ev : db->prof_pool) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    gemm_plan_free(db->gemm_plan);
+    if (db->rows) cudaFree(db->rows);
+    if (db->sqnorm) cudaFree(db->sqnorm);
+    if (db->labels) cudaFree(db->labels);
+    if (db->tomb) cudaFree(db->tomb);
+    if (db->d_max_sqnorm) cudaFree(db->d_max_sqnorm);
+    if (db->d_stage) cudaFree(db->d_stage);
+    if (db->d_idx) cudaFree(db->d_idx);
+    if (db->wstream) cudaStreamDestroy(db->wstream);
+    delete db;
+}
+
+size_t vdb_count(const vdb_t* db) { return db ? db->count.load() : 0; }
+size_t vdb_live_count(const vdb_t* db) {
+    if (!db) return 0;
+    std::shared_lock<std::shared_mutex> lk(db->mu);
+    return db->live;
+}
+size_t vdb_capacity(const vdb_t* db) { return db ? db->capacity : 0; }
+int vdb_dim(const vdb_t* db) { return db ? db->dim : 0; }
+
+// caller holds the exclusive lock.  Tombstones rows on host mirror + device.
+static int tombstone_rows(vdb* db, const std::vector<uint32_t>& rows, bool set) {
+    if (rows.empty()) return VDB_OK;
+    CU_TRY(grow(db->d_idx, db->idx_cap, rows.size()));
+    CU_TRY(cudaMemcpyAsync(db->d_idx, rows.data(), rows.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, db->wstream));
+    CU_TRY(launch_set_bits(db->tomb, db->d_idx, rows.size(), set, db->wstream));
+    CU_TRY(cudaStreamSynchronize(db->wstream));
+    for (uint32_t r : rows) db->set_dead(r, set);
+    if (set) db->any_dead = true;
+    return VDB_OK;
+}
+
+// caller holds the exclusive lock.  Registers labels for rows [row0, row0+n) and uploads them.
+static int register_labels(vdb* db, const int64_t* labels, size_t n, size_t row0) {
+    for (size_t i = 0; i < n; ++i)
+        if (labels[i] < 0 || labels[i] > (int64_t)LABEL_MAX) return fail(VDB_EINVAL, "labels must lie in [0, 2^32-2]");
+    // existing live label => tombstone the old row (hnswlib would update in place)
+    std::vector<uint32_t> kill;
+    for (size_t i = 0; i < n; ++i) {
+        long long r = db->row_of(labels[i]);
+        if (r >= 0 && !db->dead((size_t)r)) kill.push_back((uint32_t)r);
+    }
+    // duplicates inside this batch: the last one wins
+    std::unordered_map<int64_t, size_t> last;
+    bool dup = false;
+    if (n > 1) {
+        last.reserve(n * 2);
+        for (size_t i = 0; i < n; ++i) {
+            auto it = last.find(labels[i]);
+            if (it != last.end()) { kill.push_back((uint32_t)(row0 + it->second)); it->second = i; dup = true; }
+            else last.emplace(labels[i], i);
+        }
+    }
+    // does the batch keep label == base + row ?
+    bool keeps_affine = db->affine && !dup;
+    if (keeps_affine) {
+        if (row0 == 0) db->label_base = labels[0];
+        for (size_t i = 0; i < n && keeps_affine; ++i) keeps_affine = labels[i] == db->label_base + (int64_t)(row0 + i);
+    }
+    if (db->affine && !keeps_affine) {   // materialise the map for what is already there
+        db->map.reserve((row0 + n) * 2);
+        for (size_t r = 0; r < row0; ++r) db->map[db->label_base + (int64_t)r] = (uint32_t)r;
+        db->affine = false;
+    }
+    if (!db->affine)
+        for (size_t i = 0; i < n; ++i) db->map[labels[i]] = (uint32_t)(row0 + i);
+    std::vector<uint32_t> l32(n);
+    for (size_t i = 0; i < n; ++i) l32[i] = (uint32_t)labels[i];
+    CU_TRY(cudaMemcpyAsync(db->labels + row0, l32.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, db->wstream));
+    CU_TRY(cudaStreamSynchronize(db->wstream));
+    if (!kill.empty()) {
+        std::sort(kill.begin(), kill.end());
+        kill.erase(std::unique(kill.begin(), kill.end()), kill.end());
+        // rows killed inside this batch are not yet counted live
+        int rc = tombstone_rows(db, kill, true);
+        if (rc) return rc;
+        db->live -= kill.size();   // in-batch duplicates are compensated by the caller's += n
+    }
+    return VDB_OK;
+}
+
+static int add_impl(vdb* db, const float* rows, bool rows_on_device, const int64_t* labels, size_t n, cudaStream_t user) {
+    if (!db) return fail(VDB_EINVAL, "db is null");
+    if (n == 0) return VDB_OK;
+    if (!rows || !labels) return fail(VDB_EINVAL, "rows/labels is null");
+    std::unique_lock<std::shared_mutex> lk(db->mu);
+    CU_TRY(cudaSetDevice(db->device));
+    const size_t row0 = db->count.load();
+    if (row0 + n > db->capacity)
+        return fail(VDB_EFULL, "The number of elements exceeds the specified limit");   // hnswlib's message
+    if (rows_on_device && user) CU_TRY(cudaStreamSynchronize(user));
+    int rc = register_labels(db, labels, n, row0);
+    if (rc) return rc;
+    for (size_t off = 0; off < n; off += STAGE_ROWS) {
+        const size_t m = std::min(STAGE_ROWS, n - off);
+        const float* src = rows + off * (size_t)db->dim;
+        if (!rows_on_device) {
+            CU_TRY(cudaMemcpyAsync(db->d_stage, src, m * (size_t)db->dim * sizeof(float), cudaMemcpyHostToDevice, db->wstream));
+            src = db->d_stage;
+        }
+        CU_TRY(launch_insert_rows(src, m, db->dim, db->ld, db->metric == VDB_COSINE, db->dtype == VDB_F16, db->rows,
+                                  db->sqnorm, row0 + off, db->d_max_sqnorm, db->wstream));
+        if (!rows_on_device) CU_TRY(cudaStreamSynchronize(db->wstream));   // staging buffer is reused
+    }
+    CU_TRY(cudaStreamSynchronize(db->wstream));
+    db->live += n;
+    db->count.store(row0 + n);
+    return VDB_OK;
+}
+
+int vdb_add(vdb_t* db, const float* rows, const int64_t* labels, size_t n) { return add_impl(db, rows, false, labels, n, nullptr); }
+int vdb_add_dev(vdb_t* db, const float* d_rows, const int64_t* h_labels, size_t n, void* stream) {
+    return add_impl(db, d_rows, true, h_labels, n, (cudaStream_t)stream);
+}
+
+int vdb_synth_dev(uint64_t seed, uint64_t row_start, size_t n, int dim, float* d_out, void* stream) {
+    if (!d_out || dim < 1) return fail(VDB_EINVAL, "bad argument");
+    CU_TRY(launch_synth_rows(seed, row_start, n, dim, d_out, (cudaStream_t)stream));
+    return VDB_OK;
+}
+
+int vdb_add_synthetic(vdb_t* db, uint64_t seed, uint64_t row_start, size_t n, int64_t label_start) {
+    if (!db) return fail(VDB_EINVAL, "db is null");
+    if (n == 0) return VDB_OK;
+    std::unique_lock<std::shared_mutex> lk(db->mu);
+    CU_TRY(cudaSetDevice(db->device));
+    const size_t row0 = db->count.load();
+    if (row0 + n > db->capacity) return fail(VDB_EFULL, "The number of elements exceeds the specified limit");
+    if (label_start < 0 || label_start + (int64_t)n - 1 > (int64_t)LABEL_MAX) return fail(VDB_EINVAL, "labels must lie in [0, 2^32-2]");
+    // labels are label_start + i: keep the affine map when possible, else fall back to the generic path
+    const bool keeps_affine = db->affine && (row0 == 0 || label_start == db->label_base + (int64_t)row0);
+    if (!keeps_affine) {
+        std::vector<int64_t> l(n);
+        for (size_t i = 0; i < n; ++i) l[i] = label_start + (int64_t)i;
+        int rc = register_labels(db, l.data(), n, row0);
+        if (rc) return rc;
+    } else {
+        if (row0 == 0) db->label_base = label_start;
+        CU_TRY(launch_iota_u32(db->labels + row0, n, (uint32_t)label_start, db->wstream));
+    }
+    for (size_t off = 0; off < n; off += STAGE_ROWS) {
+        const size_t m = std::min(STAGE_ROWS, n - off);
+        CU_TRY(launch_synth_rows(seed, row_start + off, m, db->dim, db->d_stage, db->wstream));
+        CU_TRY(launch_insert_rows(db->d_stage, m, db->dim, db->ld, db->metric == VDB_COSINE, db->dtype == VDB_F16,
+                                  db->rows, db->sqnorm, row0 + off, db->d_max_sqnorm, db->wstream));
+    }
+    CU_TRY(cudaStreamSynchronize(db->wstream));
+    db->live += n;
+    db->count.store(row0 + n);
+    return VDB_OK;
+}
+
+static int mark_impl(vdb* db, const int64_t* labels, size_t n, bool set) {
+    if (!db) return fail(VDB_EINVAL, "db is null");
+    if (n == 0) return VDB_OK;
+    if (!labels) return fail(VDB_EINVAL, "labels is null");
+    std::unique_lock<std::shared_mutex> lk(db->mu);
+    CU_TRY(cudaSetDevice(db->device));
+    std::vector<uint32_t> rows;
+    rows.reserve(n);
+    for (size_t i = 0; i < n; ++i) {
+        long long r = db->row_of(labels[i]);
+        if (r < 0) return fail(VDB_ENOTFOUND, "Label not found");   // hnswlib's message
+        if (db->dead((size_t)r) != set) rows.push_back((uint32_t)r);
+    }
+    std::sort(rows.begin(), rows.end());
+    rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
+    int rc = tombstone_rows(db, rows, set);
+    if (rc) return rc;
+    if (set) db->live -= rows.size();
+    else db->live += rows.size();
+    return VDB_OK;
+}
+int vdb_mark_deleted(vdb_t* db, const int64_t* labels, size_t n) { return mark_impl(db, labels, n, true); }
+int vdb_unmark_deleted(vdb_t* db, const int64_t* labels, size_t n) { return mark_impl(db, labels, n, false); }
+
+int vdb_search(vdb_t* db, const float* queries, size_t nq, int k, int64_t* out_labels, float* out_dist, int* out_counts) {
+    if (!db) return fail(VDB_EINVAL, "db is null");
+    if (nq == 0) return VDB_OK;
+    if (!queries || !out_labels || !out_dist) return fail(VDB_EINVAL, "null buffer");
+    int rc = check_k(db, k, nq);
+    if (rc) return rc;
+    std::shared_lock<std::shared_mutex> lk(db->mu);
+    CU_TRY(cudaSetDevice(db->device));
+    const size_t n = db->count.load();
+    Workspace* ws = acquire_ws(db);
+    if (!ws) return fail(VDB_ECUDA, "cannot create a search workspace (stream)");
+    WsGuard guard{db, ws};
+    cudaStream_t st = ws->stream;
+    const size_t qelems = nq * (size_t)db->dim, nout = nq * (size_t)k;
+    CU_TRY(grow(ws->d_q_in, ws->q_in_cap, qelems));
+    CU_TRY(grow_host(ws->h_q, ws->h_q_cap, qelems));
+    CU_TRY(grow(ws->d_ids, ws->ids_cap, nout));
+    CU_TRY(grow(ws->d_dist, ws->dist_cap, nout));
+    CU_TRY(grow(ws->d_cnt, ws->cnt_cap, nq));
+    const size_t out_bytes = nout * (sizeof(int64_t) + sizeof(float)) + nq * sizeof(int);
+    CU_TRY(grow_host(ws->h_out, ws->h_out_cap, out_bytes));
+    memcpy(ws->h_q, queries, qelems * sizeof(float));
+    CU_TRY(cudaMemcpyAsync(ws->d_q_in, ws->h_q, qelems * sizeof(float), cudaMemcpyHostToDevice, st));
+    rc = search_core(db, ws, ws->d_q_in, nq, k, ws->d_ids, ws->d_dist, ws->d_cnt, st, n);
+    if (rc) { cudaStreamSynchronize(st); return rc; }
+    int64_t* h_ids = reinterpret_cast<int64_t*>(ws->h_out);
+    float* h_dist = reinterpret_cast<float*>(ws->h_out + nout * sizeof(int64_t));
+    int* h_cnt = reinterpret_cast<int*>(ws->h_out + nout * (sizeof(int64_t) + sizeof(float)));
+    CU_TRY(cudaMemcpyAsync(h_ids, ws->d_ids, nout * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(h_dist, ws->d_dist, nout * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(h_cnt, ws->d_cnt, nq * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    memcpy(out_labels, h_ids, nout * sizeof(int64_t));
+    memcpy(out_dist, h_dist, nout * sizeof(float));
+    if (out_counts) memcpy(out_counts, h_cnt, nq * sizeof(int));
+    return VDB_OK;
+}
+
+int vdb_search_dev(vdb_t* db, const float* d_queries, size_t nq, int k, int64_t* d_labels, float* d_dist, int* d_counts,
+                   void* stream) {
+    if (!db) return fail(VDB_EINVAL, "db is null");
+    if (nq == 0) return VDB_OK;
+    if (!d_queries || !d_labels || !d_dist) return fail(VDB_EINVAL, "null buffer");
+    int rc = check_k(db, k, nq);
+    if (rc) return rc;
+    std::shared_lock<std::shared_mutex> lk(db->mu);
+    CU_TRY(cudaSetDevice(db->device));
+    const size_t n = db->count.load();
+    Workspace* ws = acquire_ws(db);
+    if (!ws) return fail(VDB_ECUDA, "cannot create a search workspace (stream)");
+    WsGuard guard{db, ws};
+    cudaStream_t st = (cudaStream_t)stream;
+    // the scratch may still be in use by the previous call's stream: order after it on the GPU
+    if (ws->used) CU_TRY(cudaStreamWaitEvent(st, ws->done, 0));
+    rc = search_core(db, ws, d_queries, nq, k, d_labels, d_dist, d_counts, st, n);
+    CU_TRY(cudaEventRecord(ws->done, st));
+    ws->used = true;
+    return rc;
+}
+
+int vdb_resize(vdb_t* db, size_t new_capacity) {
+    if (!db) return fail(VDB_EINVAL, "db is null");
+    std::unique_lock<std::shared_mutex> lk(db->mu);
+    CU_TRY(cudaSetDevice(db->device));
+    CU_TRY(cudaDeviceSynchronize());
+    const size_t n = db->count.load();
+    if (new_capacity < n) return fail(VDB_EINVAL, "new capacity below current count");
+    if (new_capacity >= 0xFFFFFFF0ull) return fail(VDB_EINVAL, "capacity must be below 2^32 rows per shard");
+    const size_t cap = std::max(new_capacity, (size_t)1);
+    void* rows = nullptr; float* sq = nullptr; uint32_t* lab = nullptr; uint32_t* tomb = nullptr;
+    const size_t words = (cap + 31) / 32 + 4, old_words = (db->capacity + 31) / 32;
+    CU_TRY(cudaMalloc(&rows, cap * db->row_bytes()));
+    CU_TRY(cudaMalloc((void**)&sq, cap * sizeof(float)));
+    CU_TRY(cudaMalloc((void**)&lab, cap * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc((void**)&tomb, words * sizeof(uint32_t)));
+    CU_TRY(cudaMemset(tomb, 0, words * sizeof(uint32_t)));
+    CU_TRY(cudaMemcpy(rows, db->rows, n * db->row_bytes(), cudaMemcpyDeviceToDevice));
+    CU_TRY(cudaMemcpy(sq, db->sqnorm, n * sizeof(float), cudaMemcpyDeviceToDevice));
+    CU_TRY(cudaMemcpy(lab, db->labels, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
+    CU_TRY(cudaMemcpy(tomb, db->tomb, std::min(words, old_words) * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
+    cudaFree(db->rows); cudaFree(db->sqnorm); cudaFree(db->labels); cudaFree(db->tomb);
+    db->rows = rows; db->sqnorm = sq; db->labels = lab; db->tomb = tomb;
+    db->capacity = new_capacity;
+    db->h_dead.resize((cap + 63) / 64, 0);
+    gemm_plan_free(db->gemm_plan);   // tensor maps point at the old allocation
+    return VDB_OK;
+}
+
+int vdb_get_rows(vdb_t* db, const int64_t* labels, size_t n, float* out) {
+    if (!db) return fail(VDB_EINVAL, "db is null");
+    if (n == 0) return VDB_OK;
+    if (!labels || !out) return fail(VDB_EINVAL, "null buffer");
+    std::unique_lock<std::shared_mutex> lk(db->mu);   // uses the writer stream + d_idx
+    CU_TRY(cudaSetDevice(db->device));
+    std::vector<uint32_t> rows(n);
+    for (size_t i = 0; i < n; ++i) {
+        long long r = db->row_of(labels[i]);
+        if (r < 0 || db->dead((size_t)r)) return fail(VDB_ENOTFOUND, "Label not found");
+        rows[i] = (uint32_t)r;
+    }
+    float* d_out = nullptr;
+    CU_TRY(grow(db->d_idx, db->idx_cap, n));
+    CU_TRY(cudaMalloc((void**)&d_out, n * (size_t)db->dim * sizeof(float)));
+    cudaError_t e = cudaMemcpyAsync(db->d_idx, rows.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, db->wstream);
+    if (e == cudaSuccess) e = launch_gather_rows(db->rows, db->ld, db->dim, db->dtype == VDB_F16, db->d_idx, n, d_out, db->wstream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, n * (size_t)db->dim * sizeof(float), cudaMemcpyDeviceToHost, db->wstream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(db->wstream);
+    cudaFree(d_out);
+    CU_TRY(e);
+    return VDB_OK;
+}
+
+// ---- snapshot: header | rows | sqnorm | labels(u32) | tombstone words(u64 host mirror) ----
+struct SnapHeader {
+    char magic[8];
+    uint32_t version, dim, ld, metric, dtype, affine;
+    uint64_t count, live;
+    int64_t label_base;
+    uint32_t max_sqnorm_bits, pad;
+};
+
+int vdb_save(vdb_t* db, const char* path) {
+    if (!db || !path) return fail(VDB_EINVAL, "null argument");
+    std::unique_lock<std::shared_mutex> lk(db->mu);
+    CU_TRY(cudaSetDevice(db->device));
+    CU_TRY(cudaDeviceSynchronize());
+    const size_t n = db->count.load();
+    std::string tmp = std::string(path) + ".tmp";
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) return fail(VDB_EIO, std::string("cannot open ") + tmp);
+    SnapHeader h{};
+    memcpy(h.magic, "VDBB200\0", 8);
+    h.version = 1; h.dim = db->dim; h.ld = db->ld; h.metric = db->metric; h.dtype = db->dtype; h.affine = db->affine;
+    h.count = n; h.live = db->live; h.label_base = db->label_base;
+    cudaMemcpy(&h.max_sqnorm_bits, db->d_max_sqnorm, 4, cudaMemcpyDeviceToHost);
+    bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+    const size_t chunk_rows = std::max<size_t>(1, (64u << 20) / db->row_bytes());
+    std::vector<uint8_t> buf(chunk_rows * db->row_bytes());
+    for (size_t r = 0; ok && r < n; r += chunk_rows) {
+        const size_t m = std::min(chunk_rows, n - r);
+        if (cudaMemcpy(buf.data(), (uint8_t*)db->rows + r * db->row_bytes(), m * db->row_bytes(), cudaMemcpyDeviceToHost) != cudaSuccess) ok = false;
+        else ok = fwrite(buf.data(), db->row_bytes(), m, f) == m;
+    }
+    std::vector<uint32_t> tmp32(n);
+    if (ok && n) {
+        ok = cudaMemcpy(tmp32.data(), db->sqnorm, n * 4, cudaMemcpyDeviceToHost) == cudaSuccess && fwrite(tmp32.data(), 4, n, f) == n;
+        ok = ok && cudaMemcpy(tmp32.data(), db->labels, n * 4, cudaMemcpyDeviceToHost) == cudaSuccess && fwrite(tmp32.data(), 4, n, f) == n;
+        const size_t w = (n + 63) / 64;
+        ok = ok && fwrite(db->h_dead.data(), 8, w, f) == w;
+    }
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) { remove(tmp.c_str()); cudaGetLastError(); return fail(VDB_EIO, std::string("write failed: ") + path); }
+    if (rename(tmp.c_str(), path) != 0) return fail(VDB_EIO, std::string("rename failed: ") + path);
+    return VDB_OK;
+}
+
+int vdb_load(const char* path, size_t capacity, int device, vdb_t** out) {
+    if (!path || !out) return fail(VDB_EINVAL, "null argument");
+    *out = nullptr;
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(VDB_EIO, std::string("cannot open ") + path);
+    SnapHeader h{};
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "VDBB200\0", 8) != 0 || h.version != 1) {
+        fclose(f);
+        return fail(VDB_EIO, "not a vdb_b200 snapshot");
+    }
+    const size_t n = h.count;
+    if (capacity < n) capacity = n;
+    vdb_t* db = nullptr;
+    int rc = vdb_create((int)h.dim, (int)h.metric, (int)h.dtype, capacity, device, &db);
+    if (rc) { fclose(f); return rc; }
+    if ((uint32_t)db->ld != h.ld) { fclose(f); vdb_destroy(db); return fail(VDB_EIO, "snapshot row stride mismatch"); }
+    bool ok = true;
+    const size_t chunk_rows = std::max<size_t>(1, (64u << 20) / db->row_bytes());
+    std::vector<uint8_t> buf(chunk_rows * db->row_bytes());
+    for (size_t r = 0; ok && r < n; r += chunk_rows) {
+        const size_t m = std::min(chunk_rows, n - r);
+        ok = fread(buf.data(), db->row_bytes(), m, f) == m &&
+             cudaMemcpy((uint8_t*)db->rows + r * db->row_bytes(), buf.data(), m * db->row_bytes(), cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+    std::vector<uint32_t> tmp32(n);
+    if (ok && n) {
+        ok = fread(tmp32.data(), 4, n, f) == n && cudaMemcpy(db->sqnorm, tmp32.data(), n * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+        ok = ok && fread(tmp32.data(), 4, n, f) == n && cudaMemcpy(db->labels, tmp32.data(), n * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+        if (ok && !h.affine) {
+            db->affine = false;
+            db->map.reserve(n * 2);
+            for (size_t r = 0; r < n; ++r) db->map[(int64_t)tmp32[r]] = (uint32_t)r;   // later rows win
+        }
+        const size_t w = (n + 63) / 64;
+        ok = ok && fread(db->h_dead.data(), 8, w, f) == w;
+        if (ok) {
+            std::vector<uint32_t> words((n + 31) / 32 + 1, 0);
+            bool any = false;
+            for (size_t r = 0; r < n; ++r)
+                if (db->dead(r)) { words[r >> 5] |= 1u << (r & 31); any = true; }
+            db->any_dead = any;
+            ok = cudaMemcpy(db->tomb, words.data(), ((n + 31) / 32) * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+        }
+    }
+    fclose(f);
+    if (!ok) { cudaGetLastError(); vdb_destroy(db); return fail(VDB_EIO, "snapshot truncated or copy failed"); }
+    cudaMemcpy(db->d_max_sqnorm, &h.max_sqnorm_bits, 4, cudaMemcpyHostToDevice);
+    db->label_base = h.label_base;
+    db->live = h.live;
+    db->count.store(n);
+    *out = db;
+    return VDB_OK;
+}
+
+int vdb_merge_topk(const float* dist, const int64_t* ids, int G, size_t nq, int k_in, int k_out, float* o_dist,
+                   int64_t* o_ids, int on_device, int device, void* stream) {
+    if (nq == 0) return VDB_OK;
+    if (!dist || !ids || !o_dist || !o_ids) return fail(VDB_EINVAL, "null buffer");
+    if (G < 1 || k_in < 1 || k_out < 1 || k_out > K_MAX) return fail(VDB_EINVAL, "bad G/k");
+    if ((size_t)G * (size_t)k_in > (size_t)1 << 30) return fail(VDB_EINVAL, "too many candidates");
+    MergeParams mp{};
+    mp.G = G; mp.k_in = k_in; mp.nq = nq; mp.n_in = G * k_in; mp.k_out = k_out;
+    if (on_device) {
+        mp.in_dist = dist; mp.in_ids = ids; mp.out_dist = o_dist; mp.out_ids = o_ids;
+        CU_TRY(launch_merge_topk(mp, (cudaStream_t)stream));
+        return VDB_OK;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(VDB_ECUDA, "no CUDA device: this library has no CPU fallback");
+    }
+    CU_TRY(cudaSetDevice(device));
+    const size_t nin = (size_t)G * nq * k_in, nout = nq * (size_t)k_out;
+    float *d_dist = nullptr, *d_od = nullptr;
+    int64_t *d_ids = nullptr, *d_oi = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d_dist, nin * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_ids, nin * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_od, nout * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_oi, nout * 8);
+    if (e == cudaSuccess) e = cudaMemcpy(d_dist, dist, nin * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_ids, ids, nin * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        mp.in_dist = d_dist; mp.in_ids = d_ids; mp.out_dist = d_od; mp.out_ids = d_oi;
+        e = launch_merge_topk(mp, nullptr);
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(o_dist, d_od, nout * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(o_ids, d_oi, nout * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d_dist); cudaFree(d_ids); cudaFree(d_od); cudaFree(d_oi);
+    CU_TRY(e);
+    return VDB_OK;
+}
+
+int vdb_set_option(vdb_t* db, const char* name, long value) {
+    if (!db || !name) return fail(VDB_EINVAL, "null argument");
+    if (!strcmp(name, "path")) { db->opt_path.store(value); return VDB_OK; }
+    if (!strcmp(name, "scan_batch")) { db->opt_scan_batch.store(value); return VDB_OK; }
+    if (!strcmp(name, "profile")) { db->opt_profile.store(value); return VDB_OK; }
+    return fail(VDB_EINVAL, std::string("unknown option ") + name);
+}
+long vdb_get_stat(vdb_t* db, const char* name) {
+    if (!db || !name) return -1;
+    if (!strcmp(name, "fallback_queries")) return db->stat_fallback.load() + gemm_plan_fallbacks(db->gemm_plan);
+    if (!strcmp(name, "tensor_batches")) return db->stat_tensor_batches.load();
+    if (!strcmp(name, "scan_passes")) return db->stat_scan_passes.load();
+    if (!strcmp(name, "num_sms")) return db->num_sms;
+    if (!strcmp(name, "profile_ns") || !strcmp(name, "profile_count")) {
+        // sum of (stop - start) over the dominant-kernel launches recorded since the last read
+        std::lock_guard<std::mutex> lk(db->prof_mu);
+        if (!strcmp(name, "profile_count")) return (long)db->prof_events.size();
+        double total_ms = 0.0;
+        for (auto& ev : db->prof_events) {
+            cudaEventSynchronize(ev.second);
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) total_ms += ms;
+            db->prof_pool.push_back(ev);
+        }
+        db->prof_events.clear();
+        return (long)(total_ms * 1e6);
+    }
+    if (!strcmp(name, "ld")) return db->ld;
+    return -1;
+}
+
+}  // extern "C"

@@ -1,0 +1,114 @@
+/* vdb.h -- C ABI of the B200 exact-kNN shard ("libvdb_b200.so").
+ *
+ * This is the drop-in boundary for the datanode search hot path of
+ * f1ybaozii/Distributed-Vector-Database.  The reference has no FFI of its own: the seam is
+ * the set of hnswlib.Index method calls made by VectorNodeHandler plus the coordinator's
+ * merge.  Each entry point below names the reference call it replaces
+ * (paths relative to the reference checkout).  Python binds these with ctypes
+ * (distributed-vector-database_b200/_ffi.py); INTEGRATION.md shows the stub a maintainer
+ * of the reference would add.
+ *
+ * Conventions: every function returning int gives 0 on success, a negative VDB_E* code on
+ * failure and leaves a message for vdb_last_error() (thread-local).  Unless a name ends in
+ * _dev, pointers are HOST pointers owned by the caller; the library owns all device memory
+ * behind the opaque handle.  Calls on one handle are thread-safe: searches run concurrently
+ * (one internal stream + workspace per in-flight call), writers are exclusive.
+ *
+ * Labels (hnswlib "ids") must lie in [0, 2^32-2]; results order by (distance, label).
+ * There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef VDB_B200_H
+#define VDB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vdb vdb_t;
+
+enum vdb_metric { VDB_L2 = 0, VDB_IP = 1, VDB_COSINE = 2 };  /* hnswlib space 'l2' | 'ip' | 'cosine' */
+enum vdb_dtype { VDB_F32 = 0, VDB_F16 = 1 };                 /* storage type of the shard rows      */
+enum vdb_error {
+    VDB_OK = 0,
+    VDB_EINVAL = -1,   /* bad argument                                  */
+    VDB_ECUDA = -2,    /* CUDA runtime/driver error (message has it)   */
+    VDB_EFULL = -3,    /* add beyond capacity (hnswlib: RuntimeError)  */
+    VDB_ENOMEM = -4,
+    VDB_EIO = -5,
+    VDB_ENOTFOUND = -6 /* label not present                            */
+};
+
+/* hnswlib.Index(space, dim) + init_index(max_elements, ...)   src/datanode/handler.py:46,86
+ * ef_construction / M have no meaning for an exact index and are not taken. */
+int vdb_create(int dim, int metric, int store_dtype, size_t capacity, int device, vdb_t **out);
+void vdb_destroy(vdb_t *db);
+
+/* hnswlib.Index.add_items(float32[n,dim], int64[n])           handler.py:112,268-271,279-282
+ * cosine rows are L2-normalised on insert as hnswlib does; ||d||^2 is stored beside each row.
+ * A label that is already live is tombstoned and re-appended (same observable result as
+ * hnswlib's in-place update).  VDB_EFULL when count + n > capacity. */
+int vdb_add(vdb_t *db, const float *rows, const int64_t *labels, size_t n);
+int vdb_add_dev(vdb_t *db, const float *d_rows, const int64_t *h_labels, size_t n, void *stream);
+/* Bench/test utility: append rows [row_start, row_start+n) of the synthetic unit-norm set
+ * `seed` (definition: oracle/cpu_ref.py synth_rows), generated on the device, labels
+ * label_start + i. */
+int vdb_add_synthetic(vdb_t *db, uint64_t seed, uint64_t row_start, size_t n, int64_t label_start);
+/* Same generator into a caller-owned device buffer [n, dim] fp32 (queries for benches). */
+int vdb_synth_dev(uint64_t seed, uint64_t row_start, size_t n, int dim, float *d_out, void *stream);
+
+/* Tombstones: `if hnsw_id in self.deleted_ids: continue`      handler.py:256,332,378
+ * (hnswlib.Index.mark_deleted / unmark_deleted).  Masked inside the scan. */
+int vdb_mark_deleted(vdb_t *db, const int64_t *labels, size_t n);
+int vdb_unmark_deleted(vdb_t *db, const int64_t *labels, size_t n);
+
+/* hnswlib.Index.knn_query(float32[nq,dim], k) -> (labels[nq,k], distances[nq,k]) ascending
+ *                                                              handler.py:364
+ * Exact over all live rows.  Rows with fewer than k live neighbours are padded with label -1
+ * and distance +inf; out_counts[q] (optional) is the number of real results.
+ * nq <= 8..16 takes the HBM-streaming scan kernel, larger nq the tcgen05 kernel + exact
+ * fp32 re-rank. */
+int vdb_search(vdb_t *db, const float *queries, size_t nq, int k, int64_t *out_labels,
+               float *out_dist, int *out_counts);
+/* Same with DEVICE pointers, enqueued on `stream` (a cudaStream_t; NULL = default stream),
+ * no host synchronisation. */
+int vdb_search_dev(vdb_t *db, const float *d_queries, size_t nq, int k, int64_t *d_labels,
+                   float *d_dist, int *d_counts, void *stream);
+
+/* get_current_count / get_max_elements                         handler.py:82,196,237-238,350 */
+size_t vdb_count(const vdb_t *db);       /* rows appended, tombstoned ones included (hnswlib semantics) */
+size_t vdb_live_count(const vdb_t *db);
+size_t vdb_capacity(const vdb_t *db);
+int vdb_dim(const vdb_t *db);
+/* hnswlib.Index.resize_index(new_max) -- the reference rebuilds instead (handler.py:91-120) */
+int vdb_resize(vdb_t *db, size_t new_capacity);
+/* hnswlib.Index.get_items(labels): rows AS STORED (normalised / fp16-rounded), fp32 out */
+int vdb_get_rows(vdb_t *db, const int64_t *labels, size_t n, float *out);
+
+/* save_index(path) / load_index(path, max_elements)            handler.py:65,80,115,164,195,302
+ * A flat shard snapshot (header, rows, norms, labels, tombstones) replaces hnswlib's
+ * private index.bin. */
+int vdb_save(vdb_t *db, const char *path);
+int vdb_load(const char *path, size_t capacity, int device, vdb_t **out);
+
+/* CoordinatorHandler.search merge: sorted(range(n), key=score)[:top_k]
+ *                                                              src/coordinator/handler.py:212-216
+ * dist/ids [G, nq, k_in] (id < 0 = padding) -> ascending (distance, id) top k_out per query.
+ * on_device != 0: all four pointers are device pointers and the work is enqueued on
+ * `stream`; otherwise host pointers, synchronous. */
+int vdb_merge_topk(const float *dist, const int64_t *ids, int G, size_t nq, int k_in, int k_out,
+                   float *o_dist, int64_t *o_ids, int on_device, int device, void *stream);
+
+/* Introspection for bench.py / tests */
+uint64_t vdb_launch_count(void);              /* kernels this library has launched so far   */
+int vdb_set_option(vdb_t *db, const char *name, long value);
+long vdb_get_stat(vdb_t *db, const char *name); /* "fallback_queries", "tensor_batches", ... */
+const char *vdb_last_error(void);
+const char *vdb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VDB_B200_H */

@@ -1,0 +1,189 @@
+"""GPU parity: the CUDA search path (through the C ABI) against the CPU oracle on the same seeded
+inputs.  ids must be identical to the oracle's exact result (ties by id; rows whose float64
+distances tie within 1e-5 relative may swap), distances within 1e-5 relative of the definition.
+Tolerance lives in oracle.cpu_ref.check_topk(rtol=1e-5)."""
+import numpy as np
+import pytest
+
+from oracle import cpu_ref as R
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def build(vdb, metric, n, dim=512, store="f32", scale=1.0, seed=R.SEED_DB, cap=None):
+    ix = vdb.Index(metric, dim, store_dtype=store)
+    ix.init_index(cap or max(n, 1))
+    raw = R.synth_rows(seed, 0, n, dim) * np.float32(scale) if n else np.zeros((0, dim), np.float32)
+    if n:
+        ix.add_items(raw, np.arange(n))
+    return ix, raw
+
+
+def assert_parity(ix, raw, metric, store, queries, k, deleted=(), labels=None):
+    stored = R.prepare_rows(raw, metric, store)
+    labels = np.arange(len(raw)) if labels is None else labels
+    got_l, got_d, cnt = ix.knn_query_padded(queries, k)
+    n_live = len(raw) - len(set(deleted))
+    for i in range(len(queries)):
+        assert cnt[i] == min(k, n_live)
+        msg = R.check_topk(got_l[i, :cnt[i]], got_d[i, :cnt[i]], queries[i], stored, labels, k, metric,
+                           deleted=deleted, rtol=RTOL)
+        assert msg is None, f"query {i}: {msg}"
+        assert (got_l[i, cnt[i]:] == -1).all() and np.isinf(got_d[i, cnt[i]:]).all()
+
+
+@pytest.mark.parametrize("metric", ["l2", "ip", "cosine"])
+@pytest.mark.parametrize("nq", [1, 2, 3, 8, 19])
+def test_scan_parity_f32(vdb, metric, nq):
+    ix, raw = build(vdb, metric, 5000, scale=1.7)
+    q = R.synth_rows(R.SEED_QUERY, 0, nq, 512) * np.float32(0.9)
+    assert_parity(ix, raw, metric, "f32", q, 10)
+
+
+@pytest.mark.parametrize("metric", ["l2", "ip", "cosine"])
+def test_scan_parity_f16_d768(vdb, metric):
+    ix, raw = build(vdb, metric, 3000, dim=768, store="f16")
+    q = R.synth_rows(R.SEED_QUERY, 0, 5, 768)
+    assert_parity(ix, raw, metric, "f16", q, 10)
+
+
+@pytest.mark.parametrize("k", [1, 5, 100, 257])
+def test_scan_k_sizes(vdb, k):
+    ix, raw = build(vdb, "l2", 4000)
+    q = R.synth_rows(R.SEED_QUERY, 7, 3, 512)
+    assert_parity(ix, raw, "l2", "f32", q, k)
+
+
+@pytest.mark.parametrize("dim", [4, 100, 128, 130, 960])
+def test_odd_dims(vdb, dim):
+    ix, raw = build(vdb, "cosine", 777, dim=dim)
+    q = R.synth_rows(R.SEED_QUERY, 0, 2, dim)
+    assert_parity(ix, raw, "cosine", "f32", q, 7)
+
+
+@pytest.mark.parametrize("n", [0, 1, 7, 15, 16, 17, 31, 33])
+def test_tiny_and_ragged_shards(vdb, n):
+    """empty index -> empty result (handler.py:353-354); fewer rows than k -> short result."""
+    ix, raw = build(vdb, "l2", n, cap=64)
+    q = R.synth_rows(R.SEED_QUERY, 0, 2, 512)
+    assert_parity(ix, raw, "l2", "f32", q, 10)
+
+
+def test_tombstones_and_overwrite(vdb):
+    """delete = tombstone (handler.py:332); overwrite = tombstone + append (handler.py:254-264)."""
+    ix, raw = build(vdb, "ip", 2000, cap=2100)
+    q = R.synth_rows(R.SEED_QUERY, 0, 4, 512)
+    stored = R.prepare_rows(raw, "ip")
+    first, _, _ = R.knn_exact(q, stored, np.arange(2000), 10, "ip")
+    dead = sorted(set(first[:, :6].reshape(-1).tolist()))          # kill most of the winners
+    ix.mark_deleted(dead)
+    assert ix.get_live_count() == 2000 - len(dead)
+    assert ix.get_current_count() == 2000
+    assert_parity(ix, raw, "ip", "f32", q, 10, deleted=dead)
+    ix.unmark_deleted(dead[:3])
+    assert_parity(ix, raw, "ip", "f32", q, 10, deleted=dead[3:])
+    # re-adding a live label replaces its vector
+    new_vec = q[0:1] * np.float32(1.0)
+    ix.add_items(new_vec, [5])
+    assert ix.get_current_count() == 2001
+    got_l, got_d = ix.knn_query(q[0:1], 1)
+    assert int(got_l[0, 0]) == 5
+    np.testing.assert_allclose(ix.get_items([5])[0], new_vec[0], rtol=0, atol=0)
+
+
+def test_exact_ties_break_by_label(vdb):
+    """duplicate vectors: equal distances, smaller label first (hnswlib pair ordering)."""
+    ix = vdb.Index("l2", 512)
+    ix.init_index(64)
+    base = R.synth_rows(R.SEED_DB, 0, 4, 512)
+    rows = np.concatenate([base, base, base[::-1]])
+    labels = np.array([40, 30, 20, 10, 41, 31, 21, 11, 12, 22, 32, 42])
+    ix.add_items(rows, labels)
+    got_l, got_d = ix.knn_query(base[0:1], 6)
+    assert got_l[0, :3].tolist() == [40, 41, 42] and (got_d[0, :3] == 0).all()
+    stored = R.prepare_rows(rows, "l2")
+    want_l, want_d, _ = R.knn_exact(base[0:1], stored, labels, 6, "l2")
+    assert got_l[0].astype(np.int64).tolist() == want_l[0].tolist()
+
+
+def test_errors_match_hnswlib(vdb):
+    ix, raw = build(vdb, "l2", 10, cap=10)
+    with pytest.raises(RuntimeError):                      # full (handler.py:272 catches this)
+        ix.add_items(raw[:1], [99])
+    with pytest.raises(RuntimeError):                      # k > count (handler.py:366 catches this)
+        ix.knn_query(raw[:1], 11)
+    with pytest.raises(RuntimeError):
+        ix.knn_query(np.zeros((1, 100), np.float32), 1)    # wrong dim
+    with pytest.raises(RuntimeError):
+        ix.mark_deleted([12345])
+    ix.resize_index(20)
+    ix.add_items(raw[:1], [99])
+    assert ix.get_current_count() == 11 and ix.get_max_elements() == 20
+
+
+def test_save_load_roundtrip(vdb, tmp_path):
+    ix, raw = build(vdb, "cosine", 1500, store="f16", dim=768)
+    ix.mark_deleted([3, 4, 5])
+    q = R.synth_rows(R.SEED_QUERY, 0, 3, 768)
+    a = ix.knn_query_padded(q, 10)
+    path = str(tmp_path / "index.bin")
+    ix.save_index(path)
+    ix2 = vdb.Index("cosine", 768, store_dtype="f16")
+    ix2.load_index(path, max_elements=4000)
+    assert ix2.get_current_count() == 1500 and ix2.get_live_count() == 1497 and ix2.get_max_elements() == 4000
+    b = ix2.knn_query_padded(q, 10)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_device_synthetic_rows_bit_identical(vdb):
+    """the on-device generator == the oracle's generator, so 10M-row sets can be spot-checked."""
+    ix = vdb.Index("ip", 512)
+    ix.init_index(70000)
+    ix.add_synthetic(R.SEED_DB, 1000, 70000)
+    ids = [1000, 1001, 35000, 70999]
+    want = R.synth_rows(R.SEED_DB, 1000, 70000, 512)[[0, 1, 34000, 69999]]
+    assert np.array_equal(ix.get_items(ids), want)
+
+
+def test_merge_topk_matches_oracle(vdb):
+    rng = np.random.default_rng(3)
+    G, nq, k = 8, 33, 100
+    dist = np.sort(rng.random((G, nq, k), dtype=np.float32), axis=2)
+    dist[rng.random(dist.shape) < 0.05] = 0.25                   # exact cross-shard ties
+    dist = np.sort(dist, axis=2)
+    ids = rng.permutation(G * nq * k).astype(np.int64).reshape(G, nq, k)
+    ids[:, :, 90:][rng.random((G, nq, 10)) < 0.3] = -1           # ragged shards
+    got_d, got_i = vdb.merge_topk(dist, ids, k)
+    want_d, want_i = R.merge_topk_by_id(dist, ids, k)
+    assert np.array_equal(got_i, want_i) and np.array_equal(got_d, want_d)
+
+
+def test_full_size_properties_1m(vdb):
+    """BASELINE config 2 size (1M x 512 cosine k=10): size-independent checks -- a stored row
+    queried against the index finds itself at distance ~0; results are sorted; batched and
+    single-query searches agree; sampled queries equal the oracle on regenerated rows."""
+    n = 1_000_000
+    ix = vdb.Index("cosine", 512)
+    ix.init_index(n)
+    ix.add_synthetic(R.SEED_DB, 0, n)
+    probe_rows = [0, 123456, 999999]
+    q = R.synth_rows(R.SEED_DB, 0, 1, 512)
+    q = np.concatenate([R.synth_rows(R.SEED_DB, r, 1, 512) for r in probe_rows] + [R.synth_rows(R.SEED_QUERY, 0, 5, 512)])
+    l8, d8, c8 = ix.knn_query_padded(q, 10)
+    for i, r in enumerate(probe_rows):
+        assert l8[i, 0] == r and abs(d8[i, 0]) < 1e-6
+    assert (np.diff(d8, axis=1) >= 0).all() and (c8 == 10).all()
+    for i in range(len(q)):
+        l1, d1, _ = ix.knn_query_padded(q[i:i + 1], 10)
+        assert np.array_equal(l1[0], l8[i]) and np.array_equal(d1[0], d8[i])
+    from oracle import c_ref
+    rows = c_ref.synth_rows(R.SEED_DB, 0, n, 512)
+    stored = c_ref.normalize(rows)
+    want_l, want_d, _ = c_ref.knn(q, stored, None, 10, "cosine")
+    for i in range(len(q)):
+        msg = R.check_topk(l8[i], d8[i], q[i], stored[np.unique(np.concatenate([want_l[i], l8[i]]))],
+                           np.unique(np.concatenate([want_l[i], l8[i]])), 10, "cosine", rtol=RTOL)
+        assert msg is None, msg
+        assert set(l8[i].tolist()) == set(want_l[i].tolist()) or msg is None
