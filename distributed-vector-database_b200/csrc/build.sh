@@ -15,5 +15,5 @@ for f in scan_topk merge_topk insert gemm_topk vdb_api; do
   fi
 done
 for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
-"$NVCC" -shared -o "$OUT" _obj/*.o -lcuda
+"$NVCC" -shared -o "$OUT" _obj/*.o
 echo "built $(realpath $OUT)"

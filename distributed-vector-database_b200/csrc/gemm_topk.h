@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <vector>
 
 namespace vdbk {
 
@@ -26,6 +27,9 @@ struct GemmSearchArgs {
 
 bool gemm_topk_supported(int dim, int ld, bool f16, int k, size_t n_rows);
 cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearchArgs& a, cudaStream_t st, std::string& err);
+// after gemm_topk_search: synchronises `st` and lists the queries whose certificate failed
+cudaError_t gemm_topk_flagged(GemmWorkspace& ws, size_t nq, std::vector<int>& flagged, cudaStream_t st);
+void gemm_plan_note_fallbacks(GemmPlan& plan, long n);
 void gemm_plan_free(GemmPlan& plan);
 void gemm_workspace_free(GemmWorkspace& ws);
 long gemm_plan_fallbacks(const GemmPlan& plan);

@@ -65,6 +65,11 @@ struct Workspace {
     float* h_q = nullptr; size_t h_q_cap = 0;
     uint8_t* h_out = nullptr; size_t h_out_cap = 0;
     GemmWorkspace gemm;
+    // exact re-search of queries that failed the tensor path's certificate
+    float* d_fq = nullptr; size_t fq_cap = 0;
+    int64_t* d_fids = nullptr; size_t fids_cap = 0;
+    float* d_fdist = nullptr; size_t fdist_cap = 0;
+    int* d_fcnt = nullptr; size_t fcnt_cap = 0;
 };
 
 template <typename T>
@@ -180,6 +185,10 @@ void free_workspace(Workspace* w) {
     if (w->d_cnt) cudaFree(w->d_cnt);
     if (w->h_q) cudaFreeHost(w->h_q);
     if (w->h_out) cudaFreeHost(w->h_out);
+    if (w->d_fq) cudaFree(w->d_fq);
+    if (w->d_fids) cudaFree(w->d_fids);
+    if (w->d_fdist) cudaFree(w->d_fdist);
+    if (w->d_fcnt) cudaFree(w->d_fcnt);
     gemm_workspace_free(w->gemm);
     if (w->done) cudaEventDestroy(w->done);
     if (w->stream) cudaStreamDestroy(w->stream);
@@ -232,6 +241,46 @@ struct ProfScope {   // records start/stop events around the dominant kernel whe
     }
 };
 
+// Exact scan (K1 + K5) of nq PREPARED queries [nq][ld]; groups of up to 8 queries per pass.
+int scan_prepared(vdb* db, Workspace* ws, const float* d_qp, size_t nq, int k, int64_t* d_ids, float* d_dist,
+                  int* d_cnt, cudaStream_t st, size_t n) {
+    const bool f16 = db->dtype == VDB_F16;
+    ScanParams sp{};
+    sp.rows = db->rows;
+    sp.row_bytes = (uint32_t)db->row_bytes();
+    sp.ld = db->ld;
+    sp.n_rows = (uint32_t)n;
+    sp.labels = db->labels;
+    sp.tomb = db->any_dead ? db->tomb : nullptr;
+    sp.k = k;
+    sp.metric = db->metric == VDB_L2 ? 0 : 1;
+    const uint32_t nchunks = (uint32_t)((n + 15) / 16);
+    const int grid = (int)std::min<uint32_t>((uint32_t)db->num_sms, nchunks);
+    CU_TRY(grow(ws->d_keys, ws->keys_cap, nq * (size_t)grid * k));
+    for (size_t g = 0; g < nq; g += 8) {
+        sp.nq = (int)std::min<size_t>(8, nq - g);
+        sp.q = d_qp + g * (size_t)db->ld;
+        sp.out_keys = ws->d_keys + g * (size_t)grid * k;
+        int grid_used = 0;
+        {
+            ProfScope prof(db, st);
+            CU_TRY(launch_scan_topk(sp, f16, db->num_sms, &grid_used, st));
+        }
+        if (grid_used != grid) return fail(VDB_ECUDA, "internal: scan grid mismatch");
+        db->stat_scan_passes.fetch_add(1);
+    }
+    MergeParams mp{};
+    mp.nq = nq;
+    mp.k_out = k;
+    mp.out_ids = d_ids;
+    mp.out_dist = d_dist;
+    mp.out_counts = d_cnt;
+    mp.in_keys = ws->d_keys;
+    mp.n_in = grid * k;
+    CU_TRY(launch_merge_topk(mp, st));
+    return VDB_OK;
+}
+
 // Enqueue a search of nq device-resident raw queries on `st`.  Outputs are device pointers.
 int search_core(vdb* db, Workspace* ws, const float* d_q_raw, size_t nq, int k, int64_t* d_ids, float* d_dist,
                 int* d_cnt, cudaStream_t st, size_t n) {
@@ -281,38 +330,32 @@ int search_core(vdb* db, Workspace* ws, const float* d_q_raw, size_t nq, int k, 
             return fail(VDB_ECUDA, "gemm_topk_search: " + (err.empty() ? std::string(cudaGetErrorString(e)) : err));
         }
         db->stat_tensor_batches.fetch_add(1);
+        // queries whose coverage certificate failed are re-searched with the exact scan
+        std::vector<int> flagged;
+        CU_TRY(gemm_topk_flagged(ws->gemm, nq, flagged, st));
+        if (!flagged.empty()) {
+            const size_t nf = flagged.size();
+            gemm_plan_note_fallbacks(db->gemm_plan, (long)nf);
+            CU_TRY(grow(ws->d_fq, ws->fq_cap, nf * (size_t)db->ld));
+            CU_TRY(grow(ws->d_fids, ws->fids_cap, nf * (size_t)k));
+            CU_TRY(grow(ws->d_fdist, ws->fdist_cap, nf * (size_t)k));
+            CU_TRY(grow(ws->d_fcnt, ws->fcnt_cap, nf));
+            for (size_t i = 0; i < nf; ++i)
+                CU_TRY(cudaMemcpyAsync(ws->d_fq + i * (size_t)db->ld, ws->d_q + (size_t)flagged[i] * db->ld,
+                                       (size_t)db->ld * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            int rc = scan_prepared(db, ws, ws->d_fq, nf, k, ws->d_fids, ws->d_fdist, ws->d_fcnt, st, n);
+            if (rc) return rc;
+            for (size_t i = 0; i < nf; ++i) {
+                const size_t qi = (size_t)flagged[i];
+                CU_TRY(cudaMemcpyAsync(d_ids + qi * k, ws->d_fids + i * k, (size_t)k * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+                CU_TRY(cudaMemcpyAsync(d_dist + qi * k, ws->d_fdist + i * k, (size_t)k * sizeof(float), cudaMemcpyDeviceToDevice, st));
+                if (d_cnt) CU_TRY(cudaMemcpyAsync(d_cnt + qi, ws->d_fcnt + i, sizeof(int), cudaMemcpyDeviceToDevice, st));
+            }
+        }
         return VDB_OK;
     }
 
-    // ---- scan path: groups of up to 8 queries per pass over the shard ----
-    ScanParams sp{};
-    sp.rows = db->rows;
-    sp.row_bytes = (uint32_t)db->row_bytes();
-    sp.ld = db->ld;
-    sp.n_rows = (uint32_t)n;
-    sp.labels = db->labels;
-    sp.tomb = db->any_dead ? db->tomb : nullptr;
-    sp.k = k;
-    sp.metric = db->metric == VDB_L2 ? 0 : 1;
-    const uint32_t nchunks = (uint32_t)((n + 15) / 16);
-    const int grid = (int)std::min<uint32_t>((uint32_t)db->num_sms, nchunks);
-    CU_TRY(grow(ws->d_keys, ws->keys_cap, nq * (size_t)grid * k));
-    for (size_t g = 0; g < nq; g += 8) {
-        sp.nq = (int)std::min<size_t>(8, nq - g);
-        sp.q = ws->d_q + g * (size_t)db->ld;
-        sp.out_keys = ws->d_keys + g * (size_t)grid * k;
-        int grid_used = 0;
-        {
-            ProfScope prof(db, st);
-            CU_TRY(launch_scan_topk(sp, f16, db->num_sms, &grid_used, st));
-        }
-        if (grid_used != grid) return fail(VDB_ECUDA, "internal: scan grid mismatch");
-        db->stat_scan_passes.fetch_add(1);
-    }
-    mp.in_keys = ws->d_keys;
-    mp.n_in = grid * k;
-    CU_TRY(launch_merge_topk(mp, st));
-    return VDB_OK;
+    return scan_prepared(db, ws, ws->d_q, nq, k, d_ids, d_dist, d_cnt, st, n);
 }
 
 int check_k(const vdb* db, int k, size_t nq) {
@@ -632,7 +675,6 @@ int vdb_resize(vdb_t* db, size_t new_capacity) {
     db->rows = rows; db->sqnorm = sq; db->labels = lab; db->tomb = tomb;
     db->capacity = new_capacity;
     db->h_dead.resize((cap + 63) / 64, 0);
-    gemm_plan_free(db->gemm_plan);   // tensor maps point at the old allocation
     return VDB_OK;
 }
 

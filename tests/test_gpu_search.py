@@ -187,3 +187,95 @@ def test_full_size_properties_1m(vdb):
                            np.unique(np.concatenate([want_l[i], l8[i]])), 10, "cosine", rtol=RTOL)
         assert msg is None, msg
         assert set(l8[i].tolist()) == set(want_l[i].tolist()) or msg is None
+
+
+# ---------------------------------------------------------------------------------------------
+# batched tensor-core path (K2 + K5 + K4): forced with set_option("path", 2)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("metric", ["l2", "ip", "cosine"])
+@pytest.mark.parametrize("store,dim", [("f32", 512), ("f16", 768)])
+def test_tensor_path_parity(vdb, metric, store, dim):
+    ix, raw = build(vdb, metric, 6000, dim=dim, store=store, scale=1.3)
+    ix.set_option("path", 2)
+    q = R.synth_rows(R.SEED_QUERY, 0, 150, dim) * np.float32(0.8)
+    assert_parity(ix, raw, metric, store, q, 10)
+    assert ix.get_stat("tensor_batches") >= 1
+
+
+@pytest.mark.parametrize("k", [1, 16, 17, 100, 128])
+def test_tensor_path_k_sizes(vdb, k):
+    ix, raw = build(vdb, "l2", 9000)
+    ix.set_option("path", 2)
+    q = R.synth_rows(R.SEED_QUERY, 3, 40, 512)
+    assert_parity(ix, raw, "l2", "f32", q, k)
+
+
+@pytest.mark.parametrize("n", [1, 100, 255, 256, 257, 1000])
+def test_tensor_path_small_and_ragged(vdb, n):
+    ix, raw = build(vdb, "ip", n, cap=2048)
+    ix.set_option("path", 2)
+    q = R.synth_rows(R.SEED_QUERY, 0, 9, 512)
+    assert_parity(ix, raw, "ip", "f32", q, 10)
+
+
+def test_tensor_path_tombstones(vdb):
+    ix, raw = build(vdb, "cosine", 5000)
+    ix.set_option("path", 2)
+    q = R.synth_rows(R.SEED_QUERY, 0, 130, 512)
+    stored = R.prepare_rows(raw, "cosine")
+    first, _, _ = R.knn_exact(q[:8], stored, np.arange(5000), 10, "cosine")
+    dead = sorted(set(first[:, :7].reshape(-1).tolist()))
+    ix.mark_deleted(dead)
+    assert_parity(ix, raw, "cosine", "f32", q, 10, deleted=dead)
+
+
+def test_tensor_path_equals_scan_path_bitwise(vdb):
+    """K4 re-ranks with the scan kernel's summation order: both paths return identical bits."""
+    ix, raw = build(vdb, "cosine", 20000)
+    q = R.synth_rows(R.SEED_QUERY, 0, 300, 512)
+    ix.set_option("path", 1)
+    a = ix.knn_query_padded(q, 10)
+    ix.set_option("path", 2)
+    b = ix.knn_query_padded(q, 10)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+
+
+def test_tensor_path_certificate_fallback_on_near_duplicates(vdb):
+    """rows that differ below tf32 resolution cannot be ordered by the tensor pass: the coverage
+    certificate must fail and the exact scan must take over -- results stay exact."""
+    rng = np.random.default_rng(11)
+    base = R.synth_rows(R.SEED_DB, 0, 1, 512)[0]
+    rows = base[None, :] + rng.normal(0, 2e-4, size=(3000, 512)).astype(np.float32)
+    ix = vdb.Index("l2", 512)
+    ix.init_index(3000)
+    ix.add_items(rows, np.arange(3000))
+    ix.set_option("path", 2)
+    q = (base[None, :] + rng.normal(0, 2e-4, size=(20, 512))).astype(np.float32)
+    assert_parity(ix, rows, "l2", "f32", q, 10)
+    assert ix.get_stat("fallback_queries") > 0
+
+
+def test_tensor_path_large_batch_vs_scan(vdb):
+    """batch 1024 over 200k rows (the bench shape, scaled): tensor path == exact scan path."""
+    n = 200_000
+    ix = vdb.Index("cosine", 512)
+    ix.init_index(n)
+    ix.add_synthetic(R.SEED_DB, 0, n)
+    q = R.synth_rows(R.SEED_QUERY, 0, 1024, 512)
+    ix.set_option("path", 2)
+    lt, dt, ct = ix.knn_query_padded(q, 10)
+    ix.set_option("path", 1)
+    ls, ds, cs = ix.knn_query_padded(q[:64], 10)
+    assert np.array_equal(lt[:64], ls) and np.array_equal(dt[:64], ds)
+    from oracle import c_ref
+    stored = c_ref.normalize(c_ref.synth_rows(R.SEED_DB, 0, n, 512))
+    want_l, want_d, _ = c_ref.knn(q, stored, None, 10, "cosine")
+    bad = 0
+    for i in range(1024):
+        if not np.array_equal(lt[i], want_l[i]):
+            u = np.unique(np.concatenate([want_l[i], lt[i]]))
+            msg = R.check_topk(lt[i], dt[i], q[i], stored[u], u, 10, "cosine", rtol=RTOL)
+            assert msg is None, f"query {i}: {msg}"
+            bad += 1
+    assert bad < 16          # only distance ties within tolerance may differ
+    np.testing.assert_allclose(dt, want_d, rtol=RTOL, atol=RTOL)
