@@ -19,9 +19,10 @@
 //            network in registers) into the query's sorted k'-list in global memory.
 //   The [nq, n_rows] distance matrix never exists in memory.
 //
-// Work = items (slice of the shard x 128-query block); a CTA walks its items and leaves, per
-// item and query, the k' best APPROXIMATE (tf32 / fp16-rounded-query) candidates.  K5 merges
-// the slices; K4 recomputes those k' candidates exactly (same summation order as the scan
+// Work = items (slice of the shard x 128-query block); a CTA walks its items.  Every CTA that
+// works on a query merges into that query's ONE shared sorted list of the k' best APPROXIMATE
+// (tf32 / fp16-rounded-query) candidates (global memory, L2-resident, per-query spin lock), so
+// the pruning threshold is that of the union of all rows seen so far.  K4 recomputes those k' candidates exactly (same summation order as the scan
 // kernel, so batched and single-query searches return bit-identical distances) and proves the
 // result: every row that is not a candidate has approximate distance >= tau (the k'-th
 // approximate distance), hence exact distance >= tau - eps with eps a rigorous bound on the
@@ -31,6 +32,7 @@
 #include <cudaTypedefs.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -49,12 +51,13 @@ constexpr int GT_STAGE_BYTES = GT_A_BYTES + GT_B_BYTES;
 constexpr int GT_STAGES = 3;
 constexpr int GT_THREADS = 256;
 constexpr int GT_PEND_CAP = 64;                      // pending keys per query (flush at >= 32)
+constexpr int GT_PEND_STRIDE = 65;                   // padded row: same-slot appends of a warp spread over banks
 constexpr int GT_EPI_THREADS = 128;
 constexpr int GT_TMEM_COLS = 512;
 
 // dynamic shared memory map (base aligned to 1024)
 constexpr int GT_OFF_PEND = GT_STAGES * GT_STAGE_BYTES;                       // 147456
-constexpr int GT_OFF_NORM = GT_OFF_PEND + GT_EPI_THREADS * GT_PEND_CAP * 8;   // + 65536
+constexpr int GT_OFF_NORM = GT_OFF_PEND + GT_EPI_THREADS * GT_PEND_STRIDE * 8; // + 66560
 constexpr int GT_OFF_BAR = GT_OFF_NORM + 2 * GT_BN * 4;                       // + 2048
 constexpr int GT_SMEM_BYTES = GT_OFF_BAR + 128 + 1024;                        // barriers + align slack
 
@@ -63,9 +66,12 @@ struct GemmParams {
     int num_kb;              // k-blocks per row (row bytes / 128)
     int kb_elems;            // elements per k-block (32 fp32 / 64 fp16)
     int MB, S, n_tiles, n_items;
+    int dbg;                 // experiments only: 1 = epilogue reads TMEM but selects nothing, 2 = releases at once
     const float* sqnorm;     // [n_rows] (L2 only)
     const uint32_t* tomb;    // bitmap or null
-    uint64_t* cand;          // [nq][S][KP]
+    uint64_t* cand;          // [nq][KP]  ONE sorted candidate list per query, shared by every CTA (L2-resident)
+    int* locks;              // [nq] spin lock guarding a query's list during a merge
+    uint32_t* thr_g;         // [nq] ordered bits of the list's k'-th approximate value (0xFFFFFFFF until full)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -121,6 +127,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void st_shared_u64(uint32_t addr, uint64_t v) {
+    asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
@@ -167,15 +176,22 @@ __device__ __forceinline__ uint64_t warp_bitonic_merge32(uint64_t key, int lane)
     return key;
 }
 
-// Merge `n_pend` pending keys of one query into its sorted k'-list.  Executed by a converged warp.
-// m[r] holds list element r*32 + lane.  Returns the list's new last key.
+// Merge `n_pend` pending keys of one query into the query's shared sorted k'-list (global memory, L2).
+// Executed by a converged warp under the query's spin lock: every CTA that scans a slice of the shard
+// for this query merges into the same list, so the running threshold is the k'-th best of the UNION of
+// all rows seen so far by anyone.  m[r] holds list element r*32 + lane.  Returns the list's new last key.
 template <int KP>
-__device__ __forceinline__ uint64_t flush_query(uint64_t* __restrict__ list, const uint64_t* pend, int n_pend,
-                                                const uint32_t* __restrict__ tomb, uint32_t n_rows, int lane) {
+__device__ __forceinline__ uint64_t flush_query(uint64_t* list, int* lock, uint32_t* thr_slot, const uint64_t* pend,
+                                                int n_pend, const uint32_t* __restrict__ tomb, uint32_t n_rows, int lane) {
     constexpr int R = KP / 32;
     uint64_t m[R];
+    if (lane == 0) {
+        while (atomicCAS(lock, 0, 1) != 0) __nanosleep(64);
+    }
+    __syncwarp();
+    __threadfence();
 #pragma unroll
-    for (int r = 0; r < R; ++r) m[r] = list[r * 32 + lane];
+    for (int r = 0; r < R; ++r) m[r] = __ldcg(reinterpret_cast<const unsigned long long*>(list) + r * 32 + lane);
     for (int base = 0; base < n_pend; base += 32) {
         uint64_t p = (base + lane < n_pend) ? pend[base + lane] : KEY_SENTINEL;
         if (p != KEY_SENTINEL) {   // drop padding rows of the last tile and tombstoned rows here (rare path)
@@ -208,8 +224,16 @@ __device__ __forceinline__ uint64_t flush_query(uint64_t* __restrict__ list, con
         }
     }
 #pragma unroll
-    for (int r = 0; r < R; ++r) list[r * 32 + lane] = m[r];
-    return __shfl_sync(0xffffffffu, m[R - 1], 31);
+    for (int r = 0; r < R; ++r) __stcg(reinterpret_cast<unsigned long long*>(list) + r * 32 + lane, m[r]);
+    const uint64_t last = __shfl_sync(0xffffffffu, m[R - 1], 31);
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) {
+        if (last != KEY_SENTINEL) atomicMin(thr_slot, (uint32_t)(last >> 32));
+        __threadfence();
+        atomicExch(lock, 0);
+    }
+    return last;
 }
 
 __device__ __forceinline__ float thr_from_key(uint64_t last) {
@@ -254,8 +278,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            const uint64_t pol_stream = l2_policy_evict_first();   // shard rows: streamed
-            const uint64_t pol_keep = l2_policy_evict_last();      // queries: reused by every tile
+            // shard tiles are re-read from L2 by the CTAs that hold the other query blocks of the same
+            // slice, so they keep the default policy; the query block is reused by every tile: keep it
+            uint64_t pol_stream;
+            asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_stream));
+            const uint64_t pol_keep = l2_policy_evict_last();
             uint32_t it = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 const int slice = item / p.MB, mb = item - slice * p.MB;
@@ -306,30 +333,23 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ================= epilogue: streaming top-k' =================
         const int et = threadIdx.x - 128;                  // 0..127 == TMEM lane == query within block
         const int ew = et >> 5;                            // == warp % 4 : TMEM lane quadrant
-        uint64_t* my_pend = pend_all + (size_t)et * GT_PEND_CAP;
+        const uint32_t my_pend_s = smem_u32(pend_all + (size_t)et * GT_PEND_STRIDE);
         uint32_t tcount = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             const int slice = item / p.MB, mb = item - slice * p.MB;
             const int t0 = (int)((long long)slice * p.n_tiles / p.S), t1 = (int)((long long)(slice + 1) * p.n_tiles / p.S);
             const uint32_t q = (uint32_t)mb * GT_BM + et;
             const bool q_ok = q < p.nq;
-            // this warp's 32 lists start empty
-            for (int j = 0; j < 32; ++j) {
-                const uint32_t qj = (uint32_t)mb * GT_BM + ew * 32 + j;
-                if (qj < p.nq) {
-                    uint64_t* l = p.cand + ((size_t)qj * p.S + slice) * KP;
-#pragma unroll
-                    for (int r = 0; r < KP / 32; ++r) l[r * 32 + lane] = KEY_SENTINEL;
-                }
-            }
-            __syncwarp();
-            uint64_t* my_list = p.cand + ((size_t)(q_ok ? q : 0) * p.S + slice) * KP;
             float thr = q_ok ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);   // +inf / -inf (never passes)
             int cnt = 0;
 
             for (int tile = t0; tile < t1; ++tile, ++tcount) {
                 const uint32_t acc = tcount & 1;
                 const uint32_t row0 = (uint32_t)tile * GT_BN;
+                // the query's shared list is tightened by every CTA working on it: a row that is not below its
+                // current k'-th approximate value cannot be in the global top-k'
+                uint32_t tg = 0xFFFFFFFFu;
+                if (q_ok) tg = __ldcg(p.thr_g + q);
                 if constexpr (L2) {
                     // stage ||d||^2 of this tile's rows (buffer `acc` was last read two tiles ago, and every
                     // epilogue thread has passed the previous tile's barrier since)
@@ -339,12 +359,14 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     ns[et + 128] = r_b < p.n_rows ? p.sqnorm[r_b] : 0.0f;
                     asm volatile("bar.sync 1, 128;" ::: "memory");
                 }
+                if (tg != 0xFFFFFFFFu) thr = fminf(thr, ordered_to_float(tg));
                 mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * GT_BN;
                 const float* ns = norm_s + acc * GT_BN;
 #pragma unroll 1
                 for (int c = 0; c < GT_BN / 32; ++c) {
+                    if (p.dbg == 2) break;
                     uint32_t v[32];
                     tmem_ld32(taddr + c * 32, v);
                     tmem_ld_wait();
@@ -354,8 +376,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         float a;
                         if constexpr (L2) a = fmaf(-2.0f, dot, ns[c * 32 + j]);
                         else a = -dot;
-                        if (a < thr) {
-                            my_pend[cnt] = make_key(a, row0 + c * 32 + j);
+                        if (a < thr && p.dbg == 0) {
+                            st_shared_u64(my_pend_s + cnt * 8, make_key(a, row0 + c * 32 + j));
                             ++cnt;
                         }
                     }
@@ -366,11 +388,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         fl &= fl - 1;
                         const int n_p = __shfl_sync(0xffffffffu, cnt, src);
                         const uint32_t qs = (uint32_t)mb * GT_BM + ew * 32 + src;
-                        uint64_t* l = p.cand + ((size_t)qs * p.S + slice) * KP;
-                        const uint64_t last = flush_query<KP>(l, pend_all + (size_t)(ew * 32 + src) * GT_PEND_CAP, n_p,
+                        const uint64_t last = flush_query<KP>(p.cand + (size_t)qs * KP, p.locks + qs, p.thr_g + qs,
+                                                              pend_all + (size_t)(ew * 32 + src) * GT_PEND_STRIDE, n_p,
                                                               p.tomb, p.n_rows, lane);
                         if (lane == src) {
-                            thr = thr_from_key(last);
+                            if (last != KEY_SENTINEL) thr = fminf(thr, key_dist(last));
                             cnt = 0;
                         }
                         __syncwarp();
@@ -388,11 +410,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 fl &= fl - 1;
                 const int n_p = __shfl_sync(0xffffffffu, cnt, src);
                 const uint32_t qs = (uint32_t)mb * GT_BM + ew * 32 + src;
-                uint64_t* l = p.cand + ((size_t)qs * p.S + slice) * KP;
-                flush_query<KP>(l, pend_all + (size_t)(ew * 32 + src) * GT_PEND_CAP, n_p, p.tomb, p.n_rows, lane);
+                flush_query<KP>(p.cand + (size_t)qs * KP, p.locks + qs, p.thr_g + qs,
+                                pend_all + (size_t)(ew * 32 + src) * GT_PEND_STRIDE, n_p, p.tomb, p.n_rows, lane);
                 __syncwarp();
             }
-            (void)my_list;
         }
     }
     tc_fence_before();
@@ -521,9 +542,10 @@ __global__ void f32_to_f16_kernel(const float* __restrict__ in, __half* __restri
 // ------------------------------------------------------------------------------------------
 struct GemmWsImpl {
     uint64_t* cand = nullptr; size_t cand_cap = 0;
-    uint64_t* approx = nullptr; size_t approx_cap = 0;
+    int* locks = nullptr; size_t locks_cap = 0;
     __half* q16 = nullptr; size_t q16_cap = 0;
     int* flags = nullptr; size_t flags_cap = 0;
+    uint32_t* thr_g = nullptr; size_t thr_cap = 0;
     int* n_flagged = nullptr;
     int* h_n_flagged = nullptr;   // pinned
 };
@@ -652,9 +674,13 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
     const int S = choose_slices(MB, n_tiles, a.num_sms);
     const size_t esz = a.f16 ? 2 : 4;
     cudaError_t e;
-    if ((e = grow_dev(w->cand, w->cand_cap, a.nq * (size_t)S * kp)) != cudaSuccess) return e;
-    if ((e = grow_dev(w->approx, w->approx_cap, a.nq * (size_t)kp)) != cudaSuccess) return e;
+    if ((e = grow_dev(w->cand, w->cand_cap, a.nq * (size_t)kp)) != cudaSuccess) return e;
+    if ((e = grow_dev(w->locks, w->locks_cap, a.nq)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(w->cand, 0xFF, a.nq * (size_t)kp * sizeof(uint64_t), st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(w->locks, 0, a.nq * sizeof(int), st)) != cudaSuccess) return e;
     if ((e = grow_dev(w->flags, w->flags_cap, a.nq)) != cudaSuccess) return e;
+    if ((e = grow_dev(w->thr_g, w->thr_cap, a.nq)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(w->thr_g, 0xFF, a.nq * sizeof(uint32_t), st)) != cudaSuccess) return e;
     const void* qa = a.q;
     if (a.f16) {
         if ((e = grow_dev(w->q16, w->q16_cap, a.nq * (size_t)a.ld)) != cudaSuccess) return e;
@@ -672,22 +698,18 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
     gp.n_rows = a.n_rows; gp.nq = (uint32_t)a.nq;
     gp.num_kb = (int)((size_t)a.ld * esz / GT_KB_BYTES);
     gp.kb_elems = (int)(GT_KB_BYTES / esz);
+    { const char* d = getenv("VDB_GEMM_DBG"); gp.dbg = d ? atoi(d) : 0; }
     gp.MB = MB; gp.S = S; gp.n_tiles = n_tiles; gp.n_items = MB * S;
-    gp.sqnorm = a.sqnorm; gp.tomb = a.tomb; gp.cand = w->cand;
+    gp.sqnorm = a.sqnorm; gp.tomb = a.tomb; gp.cand = w->cand; gp.locks = w->locks; gp.thr_g = w->thr_g;
     const int grid = std::min(gp.n_items, a.num_sms);
     const bool l2 = a.metric == 0;
     if (a.f16) e = l2 ? launch_gemm_kp<true, true>(kp, tmA, tmB, gp, grid, st) : launch_gemm_kp<true, false>(kp, tmA, tmB, gp, grid, st);
     else       e = l2 ? launch_gemm_kp<false, true>(kp, tmA, tmB, gp, grid, st) : launch_gemm_kp<false, false>(kp, tmA, tmB, gp, grid, st);
     if (e != cudaSuccess) return e;
 
-    // slices -> one ascending approximate list of k' per query
-    MergeParams mp{};
-    mp.in_keys = w->cand; mp.nq = a.nq; mp.n_in = S * kp; mp.k_out = kp; mp.out_keys = w->approx;
-    if ((e = launch_merge_topk(mp, st)) != cudaSuccess) return e;
-
     if ((e = cudaMemsetAsync(w->n_flagged, 0, sizeof(int), st)) != cudaSuccess) return e;
     RerankParams rp{};
-    rp.approx = w->approx; rp.rows = a.rows; rp.row_bytes = (uint32_t)((size_t)a.ld * esz); rp.ld = a.ld;
+    rp.approx = w->cand; rp.rows = a.rows; rp.row_bytes = (uint32_t)((size_t)a.ld * esz); rp.ld = a.ld;
     rp.labels = a.labels; rp.q = a.q; rp.qn2 = a.qn2; rp.max_sqnorm_bits = a.d_max_sqnorm_bits;
     rp.k = a.k; rp.metric = a.metric;
     rp.eps_rel = a.f16 ? 6.5e-4f : 2.5e-3f;
@@ -729,9 +751,10 @@ void gemm_workspace_free(GemmWorkspace& ws) {
     auto* w = static_cast<GemmWsImpl*>(ws.impl);
     if (!w) return;
     if (w->cand) cudaFree(w->cand);
-    if (w->approx) cudaFree(w->approx);
+    if (w->locks) cudaFree(w->locks);
     if (w->q16) cudaFree(w->q16);
     if (w->flags) cudaFree(w->flags);
+    if (w->thr_g) cudaFree(w->thr_g);
     if (w->n_flagged) cudaFree(w->n_flagged);
     if (w->h_n_flagged) cudaFreeHost(w->h_n_flagged);
     delete w;
