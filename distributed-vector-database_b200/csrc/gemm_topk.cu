@@ -32,6 +32,7 @@
 #include <cudaTypedefs.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 #include <vector>
@@ -42,13 +43,14 @@
 
 namespace vdbk {
 
-constexpr int GT_BM = 128;
-constexpr int GT_BN = 256;
+constexpr int GT_BM = 128;                           // queries per CTA (TMEM lanes); a CTA PAIR covers 256
+constexpr int GT_BN = 256;                           // shard rows per tile (TMEM columns)
+constexpr int GT_BN_HALF = GT_BN / 2;                // rows of the B tile each CTA of the pair stages
 constexpr int GT_KB_BYTES = 128;                     // one 128B swizzle atom per row per k-block
 constexpr int GT_A_BYTES = GT_BM * GT_KB_BYTES;      // 16 KB
-constexpr int GT_B_BYTES = GT_BN * GT_KB_BYTES;      // 32 KB
+constexpr int GT_B_BYTES = GT_BN_HALF * GT_KB_BYTES; // 16 KB (this CTA's half of the 256-row tile)
 constexpr int GT_STAGE_BYTES = GT_A_BYTES + GT_B_BYTES;
-constexpr int GT_STAGES = 3;
+constexpr int GT_STAGES = 4;
 constexpr int GT_THREADS = 256;
 constexpr int GT_PEND_CAP = 64;                      // pending keys per query (flush at >= 32)
 constexpr int GT_PEND_STRIDE = 65;                   // padded row: same-slot appends of a warp spread over banks
@@ -56,47 +58,74 @@ constexpr int GT_EPI_THREADS = 128;
 constexpr int GT_TMEM_COLS = 512;
 
 // dynamic shared memory map (base aligned to 1024)
-constexpr int GT_OFF_PEND = GT_STAGES * GT_STAGE_BYTES;                       // 147456
+constexpr int GT_OFF_PEND = GT_STAGES * GT_STAGE_BYTES;                       // 131072
 constexpr int GT_OFF_NORM = GT_OFF_PEND + GT_EPI_THREADS * GT_PEND_STRIDE * 8; // + 66560
 constexpr int GT_OFF_BAR = GT_OFF_NORM + 2 * GT_BN * 4;                       // + 2048
-constexpr int GT_SMEM_BYTES = GT_OFF_BAR + 128 + 1024;                        // barriers + align slack
+constexpr int GT_OFF_CTL = GT_OFF_BAR + 128;                                  // EpiCtl
+constexpr int GT_SMEM_BYTES = GT_OFF_CTL + 1600 + 1024;                       // control block + align slack
 
 struct GemmParams {
     uint32_t n_rows, nq;
     int num_kb;              // k-blocks per row (row bytes / 128)
     int kb_elems;            // elements per k-block (32 fp32 / 64 fp16)
     int MB, S, n_tiles, n_items;
+    unsigned long long* stats;   // optional debug counters (null = off)
     int dbg;                 // experiments only: 1 = epilogue reads TMEM but selects nothing, 2 = releases at once
     const float* sqnorm;     // [n_rows] (L2 only)
     const uint32_t* tomb;    // bitmap or null
     uint64_t* cand;          // [nq][KP]  ONE sorted candidate list per query, shared by every CTA (L2-resident)
-    int* locks;              // [nq] spin lock guarding a query's list during a merge
+    uint64_t* gpend;         // [nq][KP]  keys accepted since the last merge (unsorted)
+    int* gcnt;               // [nq]      how many
+    int* locks;              // [nq] spin lock guarding a query's shared state
     uint32_t* thr_g;         // [nq] ordered bits of the list's k'-th approximate value (0xFFFFFFFF until full)
 };
 
 // ------------------------------------------------------------------------------------------
-// PTX wrappers (tcgen05 / TMA); cta_group::1
+// PTX wrappers (tcgen05 / TMA); cta_group::2 (CTA pair)
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int x, int y, uint64_t* bar,
+// cluster helpers -------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_addr` (a shared::cta address) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// 2-D tensor copy into THIS CTA's shared memory; completion bytes are counted on the mbarrier at
+// shared::cluster address `bar_cluster` (the pair leader's barrier: its MMA consumes both halves)
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int x, int y, uint32_t bar_cluster,
                                             uint64_t policy) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
         " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
-        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(x), "r"(y), "l"(policy)
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster), "r"(x), "r"(y), "l"(policy)
         : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
                  : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+// arrives (once the MMAs issued so far have retired) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t)3)
                  : "memory");
 }
 template <bool F16>
@@ -104,13 +133,13 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
     if constexpr (F16) {
         asm volatile(
             "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
             "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
             : "memory");
     } else {
         asm volatile(
             "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
             "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
             : "memory");
     }
@@ -176,75 +205,144 @@ __device__ __forceinline__ uint64_t warp_bitonic_merge32(uint64_t key, int lane)
     return key;
 }
 
-// Merge `n_pend` pending keys of one query into the query's shared sorted k'-list (global memory, L2).
-// Executed by a converged warp under the query's spin lock: every CTA that scans a slice of the shard
-// for this query merges into the same list, so the running threshold is the k'-th best of the UNION of
-// all rows seen so far by anyone.  m[r] holds list element r*32 + lane.  Returns the list's new last key.
-template <int KP>
-__device__ __forceinline__ uint64_t flush_query(uint64_t* list, int* lock, uint32_t* thr_slot, const uint64_t* pend,
-                                                int n_pend, const uint32_t* __restrict__ tomb, uint32_t n_rows, int lane) {
-    constexpr int R = KP / 32;
-    uint64_t m[R];
-    if (lane == 0) {
-        while (atomicCAS(lock, 0, 1) != 0) __nanosleep(64);
-    }
-    __syncwarp();
-    __threadfence();
+// Full bitonic sort of KP = R*32 keys held R per lane, element index e = r*32 + lane, ascending in e.
+template <int R>
+__device__ __forceinline__ void warp_sort_striped(uint64_t (&v)[R], int lane) {
+    constexpr int KP = R * 32;
 #pragma unroll
-    for (int r = 0; r < R; ++r) m[r] = __ldcg(reinterpret_cast<const unsigned long long*>(list) + r * 32 + lane);
-    for (int base = 0; base < n_pend; base += 32) {
-        uint64_t p = (base + lane < n_pend) ? pend[base + lane] : KEY_SENTINEL;
-        if (p != KEY_SENTINEL) {   // drop padding rows of the last tile and tombstoned rows here (rare path)
-            const uint32_t row = (uint32_t)p;
-            if (row >= n_rows || (tomb && ((tomb[row >> 5] >> (row & 31)) & 1u))) p = KEY_SENTINEL;
-        }
-        p = warp_sort32(p, lane);
-        // half-cleaner against the list's top 32: keeps the 32 smallest of (top 32 U pending), bitonic
-        const uint64_t prev = __shfl_sync(0xffffffffu, p, 31 - lane);
-        m[R - 1] = umin64(m[R - 1], prev);
-        if constexpr (R == 1) {
-            m[0] = warp_bitonic_merge32<true>(m[0], lane);
-        } else {
-            // sort the top block DESCENDING so that m[0..R-2] (ascending) ++ m[R-1] is bitonic
-            m[R - 1] = warp_bitonic_merge32<false>(m[R - 1], lane);
-            // bitonic merge of KP elements: register strides first, then lane strides
+    for (int size = 2; size <= KP; size <<= 1) {
 #pragma unroll
-            for (int rs = R / 2; rs > 0; rs >>= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= 32) {
+                const int rs = stride >> 5;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     if ((r & rs) == 0) {
-                        const uint64_t lo = umin64(m[r], m[r + rs]), hi = umax64(m[r], m[r + rs]);
-                        m[r] = lo;
-                        m[r + rs] = hi;
+                        const bool asc = (((r * 32) & size) == 0) || size == KP;
+                        const uint64_t lo = umin64(v[r], v[r + rs]), hi = umax64(v[r], v[r + rs]);
+                        v[r] = asc ? lo : hi;
+                        v[r + rs] = asc ? hi : lo;
                     }
                 }
-            }
+            } else {
 #pragma unroll
-            for (int r = 0; r < R; ++r) m[r] = warp_bitonic_merge32<true>(m[r], lane);
+                for (int r = 0; r < R; ++r) {
+                    const uint64_t other = shfl_xor64(v[r], stride);
+                    const bool asc = ((((r * 32) | lane) & size) == 0) || size == KP;
+                    const bool lower = (lane & stride) == 0;
+                    v[r] = (lower == asc) ? umin64(v[r], other) : umax64(v[r], other);
+                }
+            }
+        }
+    }
+}
+// Bitonic merge (ascending) of a bitonic sequence of KP = R*32 keys, striped layout.
+template <int R>
+__device__ __forceinline__ void warp_merge_striped(uint64_t (&v)[R], int lane) {
+#pragma unroll
+    for (int rs = R / 2; rs > 0; rs >>= 1) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if ((r & rs) == 0) {
+                const uint64_t lo = umin64(v[r], v[r + rs]), hi = umax64(v[r], v[r + rs]);
+                v[r] = lo;
+                v[r + rs] = hi;
+            }
         }
     }
 #pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = warp_bitonic_merge32<true>(v[r], lane);
+}
+
+// Per-query shared candidate state in global memory (L2-resident), guarded by locks[q]:
+//   cand[q][KP]   sorted ascending: the KP best approximate keys merged so far
+//   gpend[q][KP]  unsorted keys accepted since the last merge, gcnt[q] of them
+//   thr_g[q]      ordered bits of cand[q][KP-1] (0xFFFFFFFF until the list is full): the pruning threshold
+// Appending is cheap; the sort + merge runs once per KP accepted keys.
+template <int KP>
+__device__ __forceinline__ uint64_t heavy_merge(uint64_t* list, const uint64_t* gpend, int n_new, int lane) {
+    constexpr int R = KP / 32;
+    uint64_t pn[R], m[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int e = r * 32 + lane;
+        pn[r] = e < n_new ? __ldcg(reinterpret_cast<const unsigned long long*>(gpend) + e) : KEY_SENTINEL;
+        m[r] = __ldcg(reinterpret_cast<const unsigned long long*>(list) + e);
+    }
+    warp_sort_striped<R>(pn, lane);
+    // half-cleaner against the reversed new keys: keeps the KP smallest of the union as a bitonic sequence
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint64_t rev = __shfl_sync(0xffffffffu, pn[R - 1 - r], 31 - lane);
+        m[r] = umin64(m[r], rev);
+    }
+    warp_merge_striped<R>(m, lane);
+#pragma unroll
     for (int r = 0; r < R; ++r) __stcg(reinterpret_cast<unsigned long long*>(list) + r * 32 + lane, m[r]);
-    const uint64_t last = __shfl_sync(0xffffffffu, m[R - 1], 31);
-    __threadfence();
+    return __shfl_sync(0xffffffffu, m[R - 1], 31);
+}
+
+struct QueryShared {
+    uint64_t* cand; uint64_t* gpend; int* gcnt; int* locks; uint32_t* thr_g;
+};
+
+// Hand `key` (one per lane, `valid` lanes only) of query q to the shared state.  Whole converged warp.
+// Returns the query's current threshold bits.
+template <int KP>
+__device__ __forceinline__ uint32_t share_keys(const QueryShared& g, uint32_t q, uint64_t key, bool valid, int lane) {
+    const uint32_t mask = __ballot_sync(0xffffffffu, valid);
+    const int ns = __popc(mask);
+    if (ns == 0) return __ldcg(g.thr_g + q);
+    int* lock = g.locks + q;
+    if (lane == 0) {
+        while (atomicCAS(lock, 0, 1) != 0) __nanosleep(40);
+        __threadfence();
+    }
+    __syncwarp();
+    uint64_t* gp = g.gpend + (size_t)q * KP;
+    uint64_t* list = g.cand + (size_t)q * KP;
+    int gc = __ldcg(g.gcnt + q);
+    const int idx = __popc(mask & ((1u << lane) - 1u));
+    const int room = KP - gc;
+    if (valid && idx < room) __stcg(reinterpret_cast<unsigned long long*>(gp) + gc + idx, key);
+    uint32_t thr_bits = 0xFFFFFFFFu;
+    if (ns >= room) {   // buffer full: sort it and merge it into the sorted list
+        __threadfence();
+        __syncwarp();
+        const uint64_t last = heavy_merge<KP>(list, gp, KP, lane);
+        if (last != KEY_SENTINEL) thr_bits = (uint32_t)(last >> 32);
+        __syncwarp();
+        if (valid && idx >= room) __stcg(reinterpret_cast<unsigned long long*>(gp) + (idx - room), key);
+        gc = ns - room;
+        if (lane == 0 && thr_bits != 0xFFFFFFFFu) atomicMin(g.thr_g + q, thr_bits);
+    } else {
+        gc += ns;
+        thr_bits = __ldcg(g.thr_g + q);
+    }
     __syncwarp();
     if (lane == 0) {
-        if (last != KEY_SENTINEL) atomicMin(thr_slot, (uint32_t)(last >> 32));
+        __stcg(g.gcnt + q, gc);
         __threadfence();
         atomicExch(lock, 0);
     }
-    return last;
+    return thr_bits;
 }
 
-__device__ __forceinline__ float thr_from_key(uint64_t last) {
-    return last == KEY_SENTINEL ? __int_as_float(0x7f800000) : key_dist(last);
-}
+// shared-memory control block between the epilogue threads (producers of candidate keys) and the
+// merger warps (consumers): one ring of GT_PEND_CAP keys per query
+struct EpiCtl {
+    uint32_t head_pub[GT_EPI_THREADS];   // keys appended so far (published by the epilogue thread)
+    uint32_t tail[GT_EPI_THREADS];       // keys consumed so far (merger)
+    float thr_s[GT_EPI_THREADS];         // latest threshold the merger has seen for the query
+    uint32_t qbase[4];                   // first query of each epilogue warp's current item
+    uint32_t done;                       // epilogue warps that have finished all items
+};
 
 // ------------------------------------------------------------------------------------------
 // K2
 // ------------------------------------------------------------------------------------------
 template <bool F16, int KP, bool L2>
-__global__ void __launch_bounds__(GT_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GT_THREADS, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -255,57 +353,72 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* tmem_full = empty + GT_STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    EpiCtl* ctl = reinterpret_cast<EpiCtl*>(smem + GT_OFF_CTL);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta_rank = cluster_ctarank();     // 0 = pair leader (issues the MMAs), 1 = peer
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < GT_STAGES; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&full[s], 1);      // leader's arrive.expect_tx; bytes of BOTH CTAs' copies land on the leader's barrier
+            mbar_init(&empty[s], 1);     // one multicast tcgen05.commit per use
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], GT_EPI_THREADS);
+            mbar_init(&tmem_empty[a], 8);   // 4 epilogue warps x 2 CTAs arrive on the LEADER's barrier
         }
         fence_barrier_init();
+    }
+    if (threadIdx.x < GT_EPI_THREADS) {
+        ctl->head_pub[threadIdx.x] = 0;
+        ctl->tail[threadIdx.x] = 0;
+        ctl->thr_s[threadIdx.x] = __int_as_float(0x7f800000);
+        if (threadIdx.x < 4) ctl->qbase[threadIdx.x] = 0;
+        if (threadIdx.x == 0) ctl->done = 0;
     }
     if (warp == 2) tmem_alloc(tmem_ptr, GT_TMEM_COLS);
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                  // barriers of both CTAs are initialised before any remote arrive / copy
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    const QueryShared gsh{p.cand, p.gpend, p.gcnt, p.locks, p.thr_g};
 
     if (warp == 0) {
-        // ================= TMA producer =================
+        // ================= TMA producer (both CTAs: own query rows, own half of the shard tile) =================
         if (lane == 0) {
-            // shard tiles are re-read from L2 by the CTAs that hold the other query blocks of the same
+            // shard tiles are re-read from L2 by the pairs that hold the other query blocks of the same
             // slice, so they keep the default policy; the query block is reused by every tile: keep it
             uint64_t pol_stream;
             asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_stream));
             const uint64_t pol_keep = l2_policy_evict_last();
             uint32_t it = 0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            for (int item = pair; item < p.n_items; item += num_pairs) {
                 const int slice = item / p.MB, mb = item - slice * p.MB;
                 const int t0 = (int)((long long)slice * p.n_tiles / p.S), t1 = (int)((long long)(slice + 1) * p.n_tiles / p.S);
+                const int arow = mb * (2 * GT_BM) + (int)cta_rank * GT_BM;
                 for (int tile = t0; tile < t1; ++tile) {
+                    const int brow = tile * GT_BN + (int)cta_rank * GT_BN_HALF;
                     for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
                         const int s = it % GT_STAGES;
                         const uint32_t ph = (it / GT_STAGES) & 1;
                         mbar_wait(&empty[s], ph ^ 1);
-                        mbar_arrive_expect_tx(&full[s], GT_STAGE_BYTES);
+                        if (cta_rank == 0) mbar_arrive_expect_tx(&full[s], 2 * GT_STAGE_BYTES);
+                        const uint32_t bar = map_to_cta(smem_u32(&full[s]), 0);
                         uint8_t* sa = smem + s * GT_STAGE_BYTES;
-                        tma_load_2d(sa, &tmA, kb * p.kb_elems, mb * GT_BM, &full[s], pol_keep);
-                        tma_load_2d(sa + GT_A_BYTES, &tmB, kb * p.kb_elems, tile * GT_BN, &full[s], pol_stream);
+                        tma_load_2d(sa, &tmA, kb * p.kb_elems, arow, bar, pol_keep);
+                        tma_load_2d(sa + GT_A_BYTES, &tmB, kb * p.kb_elems, brow, bar, pol_stream);
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(F16 ? 0u : 2u, GT_BM, GT_BN);
+        // ================= MMA issuer (pair leader only): M = 256 (2 x 128 queries) x N = 256 =================
+        if (lane == 0 && cta_rank == 0) {
+            constexpr uint32_t idesc = make_idesc(F16 ? 0u : 2u, 2 * GT_BM, GT_BN);
             uint32_t it = 0, tcount = 0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            for (int item = pair; item < p.n_items; item += num_pairs) {
                 const int slice = item / p.MB;
                 const int t0 = (int)((long long)slice * p.n_tiles / p.S), t1 = (int)((long long)(slice + 1) * p.n_tiles / p.S);
                 for (int tile = t0; tile < t1; ++tile, ++tcount) {
@@ -323,25 +436,101 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4)   // 4 x 32 bytes of K per 128-byte swizzle atom
                             umma<F16>(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
-                        umma_commit(&empty[s]);            // smem stage reusable once these MMAs retire
+                        umma_commit_pair(&empty[s]);           // both CTAs may refill this stage once the MMAs retire
                     }
-                    umma_commit(&tmem_full[acc]);          // accumulator ready for the epilogue
+                    umma_commit_pair(&tmem_full[acc]);         // accumulators ready in both CTAs' TMEM
                 }
             }
         }
-    } else if (warp >= 4) {
-        // ================= epilogue: streaming top-k' =================
-        const int et = threadIdx.x - 128;                  // 0..127 == TMEM lane == query within block
+    } else if (warp == 2 || warp == 3) {
+        // ================= mergers: drain the per-query rings into the shared lists =================
+        // Global-memory latency (lock, list) stays off the TMEM-drain path of the epilogue warps.
+        const int base = (warp - 2) * 64;    // warp 2 serves epilogue warps 4,5; warp 3 serves 6,7
+        volatile uint32_t* v_head = ctl->head_pub;
+        volatile uint32_t* v_tail = ctl->tail;
+        volatile float* v_thr = ctl->thr_s;
+        long long mg_busy = 0, mg_hand = 0, mg_kept = 0, mg_t0 = clock64();
+        for (;;) {
+            const bool fin = *reinterpret_cast<volatile uint32_t*>(&ctl->done) == 4;
+            __threadfence_block();
+            const uint32_t av0 = v_head[base + lane] - v_tail[base + lane];
+            const uint32_t av1 = v_head[base + 32 + lane] - v_tail[base + 32 + lane];
+            const uint32_t big0 = __ballot_sync(0xffffffffu, av0 >= 16), big1 = __ballot_sync(0xffffffffu, av1 >= 16);
+            const uint32_t any0 = __ballot_sync(0xffffffffu, av0 > 0), any1 = __ballot_sync(0xffffffffu, av1 > 0);
+            if ((any0 | any1) == 0) {
+                if (fin) {
+                    if (p.stats && lane == 0) {
+                        atomicAdd(p.stats + 5, (unsigned long long)mg_busy);   // merger warp-cycles in hand-offs
+                        atomicAdd(p.stats + 6, (unsigned long long)mg_hand);   // hand-offs
+                        atomicAdd(p.stats + 7, (unsigned long long)mg_kept);   // keys surviving the pre-filter
+                        atomicAdd(p.stats + 8, (unsigned long long)(clock64() - mg_t0));
+                    }
+                    break;
+                }
+                __nanosleep(200);
+                continue;
+            }
+            const bool take_big = (big0 | big1) != 0;
+            for (int half = 0; half < 2; ++half) {
+                uint32_t m = half == 0 ? (take_big ? big0 : any0) : (take_big ? big1 : any1);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int qi = base + half * 32 + src;
+                    const long long c0 = clock64();
+                    const uint32_t t = v_tail[qi];
+                    const uint32_t n = min(v_head[qi] - t, 32u);
+                    __threadfence_block();
+                    const uint64_t* ring = pend_all + (size_t)qi * GT_PEND_STRIDE;
+                    uint64_t key = KEY_SENTINEL;
+                    if ((uint32_t)lane < n) key = *reinterpret_cast<const volatile uint64_t*>(ring + ((t + lane) & (GT_PEND_CAP - 1)));
+                    const uint32_t q = *reinterpret_cast<volatile uint32_t*>(&ctl->qbase[qi >> 5]) + (qi & 31);
+                    // pre-filter: keys accepted under a threshold that has since tightened, padding rows of the
+                    // last tile, tombstoned rows
+                    const uint32_t tb = __ldcg(p.thr_g + q);
+                    bool valid = key != KEY_SENTINEL;
+                    if (valid) {
+                        const uint32_t row = (uint32_t)key;
+                        valid = (uint32_t)(key >> 32) < tb && row < p.n_rows &&
+                                !(p.tomb && ((p.tomb[row >> 5] >> (row & 31)) & 1u));
+                    }
+                    mg_kept += __popc(__ballot_sync(0xffffffffu, valid));
+                    const uint32_t nb = share_keys<KP>(gsh, q, key, valid, lane);
+                    if (lane == 0) {
+                        if (nb != 0xFFFFFFFFu) v_thr[qi] = fminf(v_thr[qi], ordered_to_float(nb));
+                        __threadfence_block();
+                        v_tail[qi] = t + n;
+                    }
+                    __syncwarp();
+                    mg_busy += clock64() - c0;
+                    ++mg_hand;
+                }
+            }
+        }
+    } else {
+        // ================= epilogue: streaming top-k' (each CTA: its own 128 queries) =================
+        const int et = threadIdx.x - 128;                  // 0..127 == TMEM lane == query within this CTA's block
         const int ew = et >> 5;                            // == warp % 4 : TMEM lane quadrant
-        const uint32_t my_pend_s = smem_u32(pend_all + (size_t)et * GT_PEND_STRIDE);
+        const uint32_t my_ring_s = smem_u32(pend_all + (size_t)et * GT_PEND_STRIDE);
+        volatile uint32_t* my_tail = &ctl->tail[et];
+        volatile float* my_thr_s = &ctl->thr_s[et];
+        uint32_t head = 0, pub = 0;
         uint32_t tcount = 0;
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        long long st_wait_full = 0, st_wait_ring = 0, st_wait_item = 0, st_busy = 0, st_t0 = clock64();
+        for (int item = pair; item < p.n_items; item += num_pairs) {
             const int slice = item / p.MB, mb = item - slice * p.MB;
             const int t0 = (int)((long long)slice * p.n_tiles / p.S), t1 = (int)((long long)(slice + 1) * p.n_tiles / p.S);
-            const uint32_t q = (uint32_t)mb * GT_BM + et;
+            const uint32_t qbase = (uint32_t)mb * (2 * GT_BM) + cta_rank * GT_BM;
+            const uint32_t q = qbase + et;
             const bool q_ok = q < p.nq;
+            // the ring still holds keys of the previous item's query until the merger has drained it
+            { const long long c0 = clock64(); while (*my_tail != head) __nanosleep(64); st_wait_item += clock64() - c0; }
+            __syncwarp();
+            *my_thr_s = q_ok ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);
+            if (lane == 0) ctl->qbase[ew] = qbase + ew * 32;
+            __threadfence_block();
             float thr = q_ok ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);   // +inf / -inf (never passes)
-            int cnt = 0;
+            float n_next0 = 0.0f, n_next1 = 0.0f;
 
             for (int tile = t0; tile < t1; ++tile, ++tcount) {
                 const uint32_t acc = tcount & 1;
@@ -351,16 +540,25 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 uint32_t tg = 0xFFFFFFFFu;
                 if (q_ok) tg = __ldcg(p.thr_g + q);
                 if constexpr (L2) {
-                    // stage ||d||^2 of this tile's rows (buffer `acc` was last read two tiles ago, and every
-                    // epilogue thread has passed the previous tile's barrier since)
+                    // ||d||^2 of this tile's rows: prefetched into registers one tile ahead (first tile of an
+                    // item: loaded here), published to the buffer the previous-but-one tile used
                     float* ns = norm_s + acc * GT_BN;
-                    const uint32_t r_a = row0 + et, r_b = row0 + 128 + et;
-                    ns[et] = r_a < p.n_rows ? p.sqnorm[r_a] : 0.0f;
-                    ns[et + 128] = r_b < p.n_rows ? p.sqnorm[r_b] : 0.0f;
+                    if (tile == t0) {
+                        const uint32_t r_a = row0 + et, r_b = row0 + 128 + et;
+                        n_next0 = r_a < p.n_rows ? p.sqnorm[r_a] : 0.0f;
+                        n_next1 = r_b < p.n_rows ? p.sqnorm[r_b] : 0.0f;
+                    }
+                    ns[et] = n_next0;
+                    ns[et + 128] = n_next1;
                     asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (tile + 1 < t1) {
+                        const uint32_t r_a = row0 + GT_BN + et, r_b = row0 + GT_BN + 128 + et;
+                        n_next0 = r_a < p.n_rows ? p.sqnorm[r_a] : 0.0f;
+                        n_next1 = r_b < p.n_rows ? p.sqnorm[r_b] : 0.0f;
+                    }
                 }
                 if (tg != 0xFFFFFFFFu) thr = fminf(thr, ordered_to_float(tg));
-                mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
+                { const long long c0 = clock64(); mbar_wait(&tmem_full[acc], (tcount >> 1) & 1); st_wait_full += clock64() - c0; }
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * GT_BN;
                 const float* ns = norm_s + acc * GT_BN;
@@ -369,6 +567,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (p.dbg == 2) break;
                     uint32_t v[32];
                     tmem_ld32(taddr + c * 32, v);
+                    thr = fminf(thr, *my_thr_s);
+                    // a chunk may append up to 32 keys: wait (rare) until the merger has left that much room
+                    if (head - *my_tail > (uint32_t)(GT_PEND_CAP - 32)) { const long long c0 = clock64(); while (head - *my_tail > (uint32_t)(GT_PEND_CAP - 32)) __nanosleep(32); st_wait_ring += clock64() - c0; }
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
@@ -377,48 +578,53 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         if constexpr (L2) a = fmaf(-2.0f, dot, ns[c * 32 + j]);
                         else a = -dot;
                         if (a < thr && p.dbg == 0) {
-                            st_shared_u64(my_pend_s + cnt * 8, make_key(a, row0 + c * 32 + j));
-                            ++cnt;
+                            st_shared_u64(my_ring_s + (head & (GT_PEND_CAP - 1)) * 8, make_key(a, row0 + c * 32 + j));
+                            ++head;
                         }
+                    }
+                    if (head != pub) {
+                        __threadfence_block();
+                        ctl->head_pub[et] = head;
+                        pub = head;
                     }
                     __syncwarp();
-                    uint32_t fl = __ballot_sync(0xffffffffu, cnt >= 32);
-                    while (fl) {
-                        const int src = __ffs(fl) - 1;
-                        fl &= fl - 1;
-                        const int n_p = __shfl_sync(0xffffffffu, cnt, src);
-                        const uint32_t qs = (uint32_t)mb * GT_BM + ew * 32 + src;
-                        const uint64_t last = flush_query<KP>(p.cand + (size_t)qs * KP, p.locks + qs, p.thr_g + qs,
-                                                              pend_all + (size_t)(ew * 32 + src) * GT_PEND_STRIDE, n_p,
-                                                              p.tomb, p.n_rows, lane);
-                        if (lane == src) {
-                            if (last != KEY_SENTINEL) thr = fminf(thr, key_dist(last));
-                            cnt = 0;
-                        }
-                        __syncwarp();
-                    }
                 }
-                // all TMEM reads of this accumulator are done
+                // all TMEM reads of this accumulator are done: one arrive per warp on the LEADER's barrier
                 tc_fence_before();
-                mbar_arrive(&tmem_empty[acc]);
-            }
-            // drain what is still pending
-            __syncwarp();
-            uint32_t fl = __ballot_sync(0xffffffffu, cnt > 0);
-            while (fl) {
-                const int src = __ffs(fl) - 1;
-                fl &= fl - 1;
-                const int n_p = __shfl_sync(0xffffffffu, cnt, src);
-                const uint32_t qs = (uint32_t)mb * GT_BM + ew * 32 + src;
-                flush_query<KP>(p.cand + (size_t)qs * KP, p.locks + qs, p.thr_g + qs,
-                                pend_all + (size_t)(ew * 32 + src) * GT_PEND_STRIDE, n_p, p.tomb, p.n_rows, lane);
                 __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[acc]), 0));
             }
+        }
+        __syncwarp();
+        if (p.stats) {
+            st_busy = clock64() - st_t0;
+            atomicAdd(p.stats + 0, (unsigned long long)head);            // keys appended
+            if (lane == 0) {
+                atomicAdd(p.stats + 1, (unsigned long long)st_wait_full);   // epilogue warp-cycles waiting for MMA
+                atomicAdd(p.stats + 4, (unsigned long long)st_busy);        // epilogue warp-cycles total
+            }
+            atomicAdd(p.stats + 2, (unsigned long long)st_wait_ring);    // thread-cycles waiting for ring space
+            atomicAdd(p.stats + 3, (unsigned long long)st_wait_item);    // thread-cycles waiting for drain at item switch
+        }
+        if (lane == 0) {
+            __threadfence_block();
+            atomicAdd(&ctl->done, 1u);
         }
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                  // the peer may still be arriving on / copying against this CTA's barriers
     if (warp == 2) tmem_dealloc(tmem_base, GT_TMEM_COLS);
+}
+
+// Merges what is still waiting in gpend[q] into cand[q]: one warp per query.
+template <int KP>
+__global__ void finalize_lists_kernel(uint64_t* cand, const uint64_t* gpend, const int* gcnt, size_t nq) {
+    const size_t w = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= nq) return;
+    const int n = gcnt[w];
+    if (n > 0) heavy_merge<KP>(cand + w * KP, gpend + w * KP, n, lane);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -543,11 +749,14 @@ __global__ void f32_to_f16_kernel(const float* __restrict__ in, __half* __restri
 struct GemmWsImpl {
     uint64_t* cand = nullptr; size_t cand_cap = 0;
     int* locks = nullptr; size_t locks_cap = 0;
+    uint64_t* gpend = nullptr; size_t gpend_cap = 0;
+    int* gcnt = nullptr; size_t gcnt_cap = 0;
     __half* q16 = nullptr; size_t q16_cap = 0;
     int* flags = nullptr; size_t flags_cap = 0;
     uint32_t* thr_g = nullptr; size_t thr_cap = 0;
     int* n_flagged = nullptr;
     int* h_n_flagged = nullptr;   // pinned
+    unsigned long long* stats = nullptr;
 };
 struct GemmPlanImpl {
     long fallbacks = 0;
@@ -669,15 +878,19 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
     }
     auto* w = static_cast<GemmWsImpl*>(ws.impl);
     const int kp = kp_for_k(a.k);
-    const int MB = (int)((a.nq + GT_BM - 1) / GT_BM);
+    const int MB = (int)((a.nq + 2 * GT_BM - 1) / (2 * GT_BM));   // 256-query blocks, one per CTA pair
     const int n_tiles = (int)((a.n_rows + GT_BN - 1) / GT_BN);
-    const int S = choose_slices(MB, n_tiles, a.num_sms);
+    const int num_pairs_max = a.num_sms / 2;
+    const int S = choose_slices(MB, n_tiles, num_pairs_max);
     const size_t esz = a.f16 ? 2 : 4;
     cudaError_t e;
     if ((e = grow_dev(w->cand, w->cand_cap, a.nq * (size_t)kp)) != cudaSuccess) return e;
     if ((e = grow_dev(w->locks, w->locks_cap, a.nq)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(w->cand, 0xFF, a.nq * (size_t)kp * sizeof(uint64_t), st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(w->locks, 0, a.nq * sizeof(int), st)) != cudaSuccess) return e;
+    if ((e = grow_dev(w->gpend, w->gpend_cap, a.nq * (size_t)kp)) != cudaSuccess) return e;
+    if ((e = grow_dev(w->gcnt, w->gcnt_cap, a.nq)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(w->gcnt, 0, a.nq * sizeof(int), st)) != cudaSuccess) return e;
     if ((e = grow_dev(w->flags, w->flags_cap, a.nq)) != cudaSuccess) return e;
     if ((e = grow_dev(w->thr_g, w->thr_cap, a.nq)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(w->thr_g, 0xFF, a.nq * sizeof(uint32_t), st)) != cudaSuccess) return e;
@@ -690,7 +903,7 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
         qa = w->q16;
     }
     CUtensorMap tmA, tmB;
-    if (!make_tmap(&tmA, qa, a.f16, a.nq, (uint64_t)a.ld, GT_BM) || !make_tmap(&tmB, a.rows, a.f16, a.n_rows, (uint64_t)a.ld, GT_BN)) {
+    if (!make_tmap(&tmA, qa, a.f16, a.nq, (uint64_t)a.ld, GT_BM) || !make_tmap(&tmB, a.rows, a.f16, a.n_rows, (uint64_t)a.ld, GT_BN_HALF)) {
         err = "cuTensorMapEncodeTiled failed";
         return cudaErrorUnknown;
     }
@@ -699,14 +912,38 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
     gp.num_kb = (int)((size_t)a.ld * esz / GT_KB_BYTES);
     gp.kb_elems = (int)(GT_KB_BYTES / esz);
     { const char* d = getenv("VDB_GEMM_DBG"); gp.dbg = d ? atoi(d) : 0; }
+    if (getenv("VDB_GEMM_STATS")) {
+        if (!w->stats) cudaMalloc((void**)&w->stats, 16 * sizeof(unsigned long long));
+        cudaMemsetAsync(w->stats, 0, 16 * sizeof(unsigned long long), st);
+        gp.stats = w->stats;
+    }
     gp.MB = MB; gp.S = S; gp.n_tiles = n_tiles; gp.n_items = MB * S;
-    gp.sqnorm = a.sqnorm; gp.tomb = a.tomb; gp.cand = w->cand; gp.locks = w->locks; gp.thr_g = w->thr_g;
-    const int grid = std::min(gp.n_items, a.num_sms);
+    gp.sqnorm = a.sqnorm; gp.tomb = a.tomb; gp.cand = w->cand; gp.gpend = w->gpend; gp.gcnt = w->gcnt; gp.locks = w->locks; gp.thr_g = w->thr_g;
+    const int grid = 2 * std::min(gp.n_items, num_pairs_max);   // whole CTA pairs
     const bool l2 = a.metric == 0;
     if (a.f16) e = l2 ? launch_gemm_kp<true, true>(kp, tmA, tmB, gp, grid, st) : launch_gemm_kp<true, false>(kp, tmA, tmB, gp, grid, st);
     else       e = l2 ? launch_gemm_kp<false, true>(kp, tmA, tmB, gp, grid, st) : launch_gemm_kp<false, false>(kp, tmA, tmB, gp, grid, st);
     if (e != cudaSuccess) return e;
 
+    {   // keys still waiting in the per-query pending buffers
+        const unsigned blocks = (unsigned)((a.nq * 32 + 255) / 256);
+        switch (kp) {
+            case 32: finalize_lists_kernel<32><<<blocks, 256, 0, st>>>(w->cand, w->gpend, w->gcnt, a.nq); break;
+            case 64: finalize_lists_kernel<64><<<blocks, 256, 0, st>>>(w->cand, w->gpend, w->gcnt, a.nq); break;
+            case 128: finalize_lists_kernel<128><<<blocks, 256, 0, st>>>(w->cand, w->gpend, w->gcnt, a.nq); break;
+            default: finalize_lists_kernel<256><<<blocks, 256, 0, st>>>(w->cand, w->gpend, w->gcnt, a.nq); break;
+        }
+        count_launch();
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    if (gp.stats) {
+        unsigned long long hs[16];
+        cudaMemcpyAsync(hs, w->stats, sizeof(hs), cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        fprintf(stderr, "[gemm stats] S=%d items=%d grid=%d | appended=%llu kept=%llu handoffs=%llu | epi wait_full=%.1f%% ring=%.2f%% item=%.2f%% | merger busy=%.1f%%\n",
+                S, gp.n_items, grid, hs[0], hs[7], hs[6], 100.0 * hs[1] / (double)(hs[4] + 1),
+                100.0 * hs[2] / 32.0 / (double)(hs[4] + 1), 100.0 * hs[3] / 32.0 / (double)(hs[4] + 1), 100.0 * hs[5] / (double)(hs[8] + 1));
+    }
     if ((e = cudaMemsetAsync(w->n_flagged, 0, sizeof(int), st)) != cudaSuccess) return e;
     RerankParams rp{};
     rp.approx = w->cand; rp.rows = a.rows; rp.row_bytes = (uint32_t)((size_t)a.ld * esz); rp.ld = a.ld;
@@ -752,6 +989,8 @@ void gemm_workspace_free(GemmWorkspace& ws) {
     if (!w) return;
     if (w->cand) cudaFree(w->cand);
     if (w->locks) cudaFree(w->locks);
+    if (w->gpend) cudaFree(w->gpend);
+    if (w->gcnt) cudaFree(w->gcnt);
     if (w->q16) cudaFree(w->q16);
     if (w->flags) cudaFree(w->flags);
     if (w->thr_g) cudaFree(w->thr_g);
