@@ -1,33 +1,38 @@
 // gemm_topk.cu -- K2: batched search as a dense contraction on the 5th-gen tensor cores, fused
-// with a streaming top-k' select, + K4: exact fp32 re-rank with a coverage certificate.
+// with threshold filtering of the scores, + K2s (select) and K4 (exact fp32 re-rank + coverage
+// certificate).
 //
 // Replaces hnswlib.Index.knn_query for nq > 8 (reference call site src/datanode/handler.py:364;
 // hnswlib accepts [nq, dim], the reference only ever passes one row).
 //
-// K2 (gemm_topk_kernel), one persistent CTA per SM, 256 threads, warp-specialised:
-//   warp 0   TMA producer: per k-block (128 bytes of every row) one 2-D tensor copy of the
-//            128-query tile (A) and one of the 256-row shard tile (B), SWIZZLE_128B, into a
-//            ring of shared-memory stages (cp.async.bulk.tensor, mbarrier complete_tx)
-//   warp 1   MMA issuer: one elected lane issues tcgen05.mma (kind::tf32 for fp32 rows,
-//            kind::f16 for fp16 rows), M=128 x N=256, fp32 accumulators in TMEM (two 256-column
-//            buffers, ping-pong), tcgen05.commit frees smem stages / publishes accumulators
-//   warp 2   TMEM allocator
+// K2 (gemm_filter_kernel): persistent CTA PAIRS (cluster of 2, tcgen05 cta_group::2), 256 threads:
+//   warp 0   TMA producer: per k-block (128 bytes of every row) one 2-D tensor copy of this CTA's
+//            128 query rows (A) and of its half (128 rows) of the 256-row shard tile (B),
+//            SWIZZLE_128B, into a 4-stage shared-memory ring; completion bytes of both CTAs are
+//            counted on the pair leader's mbarrier
+//   warp 1   MMA issuer (leader CTA): tcgen05.mma.cta_group::2, kind::tf32 for fp32 rows /
+//            kind::f16 for fp16 rows, M=256 (2 x 128 queries) x N=256, fp32 accumulators in TMEM
+//            (two 256-column buffers, ping-pong); tcgen05.commit (multicast to both CTAs) frees
+//            smem stages / publishes accumulators
+//   warps 2-3 movers: drain the per-query key rings into the per-query candidate buffers in
+//            global memory (one atomicAdd reservation per query and round, lane-parallel)
 //   warps 4-7 epilogue: each thread owns one query (one TMEM lane): tcgen05.ld 32 columns at a
-//            time, turn the dot product into an approximate distance, compare with the query's
-//            running threshold (k'-th best so far), append survivors to a per-query pending
-//            buffer in shared memory; full buffers are merged warp-cooperatively (bitonic
-//            network in registers) into the query's sorted k'-list in global memory.
+//            time, turn the dot product into an approximate distance, keep the rows that beat the
+//            query's threshold (a key ring in shared memory; nothing else leaves the SM).
 //   The [nq, n_rows] distance matrix never exists in memory.
 //
-// Work = items (slice of the shard x 128-query block); a CTA walks its items.  Every CTA that
-// works on a query merges into that query's ONE shared sorted list of the k' best APPROXIMATE
-// (tf32 / fp16-rounded-query) candidates (global memory, L2-resident, per-query spin lock), so
-// the pruning threshold is that of the union of all rows seen so far.  K4 recomputes those k' candidates exactly (same summation order as the scan
-// kernel, so batched and single-query searches return bit-identical distances) and proves the
-// result: every row that is not a candidate has approximate distance >= tau (the k'-th
-// approximate distance), hence exact distance >= tau - eps with eps a rigorous bound on the
-// reduced-precision error; if the k-th exact distance is < tau - eps the exact top-k is inside
-// the candidate set.  Queries that fail the certificate are re-searched with the exact scan.
+// Thresholds come from LEVELS: the shard's 256-row tiles are visited in bit-reversed order, so
+// every prefix of the order is an evenly spread sample.  Level 0 (a few tiles) keeps everything;
+// K2s then selects each query's k' best approximate keys and their k'-th value becomes the
+// threshold of level 1, which is 8x larger, and so on (expected survivors per level: 8 k').  A row
+// that fails a threshold is provably not among the k' best approximate rows of the union.
+//
+// K4 recomputes the final k' candidates exactly (same summation order as the scan kernel, so
+// batched and single-query searches return bit-identical distances) and proves the result: every
+// non-candidate has approximate distance >= tau (the k'-th approximate distance), hence exact
+// distance >= tau - eps with eps a rigorous bound on the tf32 / fp16-query rounding error; if the
+// k-th exact distance is < tau - eps the exact top-k is inside the candidate set.  Queries that fail
+// the certificate (or whose candidate buffer overflowed) are re-searched with the exact scan.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -50,34 +55,40 @@ constexpr int GT_KB_BYTES = 128;                     // one 128B swizzle atom pe
 constexpr int GT_A_BYTES = GT_BM * GT_KB_BYTES;      // 16 KB
 constexpr int GT_B_BYTES = GT_BN_HALF * GT_KB_BYTES; // 16 KB (this CTA's half of the 256-row tile)
 constexpr int GT_STAGE_BYTES = GT_A_BYTES + GT_B_BYTES;
-constexpr int GT_STAGES = 4;
+constexpr int GT_STAGES = 5;
 constexpr int GT_THREADS = 256;
-constexpr int GT_PEND_CAP = 64;                      // pending keys per query (flush at >= 32)
-constexpr int GT_PEND_STRIDE = 65;                   // padded row: same-slot appends of a warp spread over banks
+constexpr int GT_RING = 48;                          // keys per query ring
+constexpr int GT_RING_STRIDE = 49;                   // padded: same-slot appends of a warp spread over banks
 constexpr int GT_EPI_THREADS = 128;
 constexpr int GT_TMEM_COLS = 512;
+constexpr int GT_LEVEL_GROWTH = 8;                   // each level sees 8x the rows seen so far
+constexpr int GT_DENSE_TILES = 4;                    // level 0: 4 tiles = 1024 rows, everything kept
 
 // dynamic shared memory map (base aligned to 1024)
-constexpr int GT_OFF_PEND = GT_STAGES * GT_STAGE_BYTES;                       // 131072
-constexpr int GT_OFF_NORM = GT_OFF_PEND + GT_EPI_THREADS * GT_PEND_STRIDE * 8; // + 66560
-constexpr int GT_OFF_BAR = GT_OFF_NORM + 2 * GT_BN * 4;                       // + 2048
-constexpr int GT_OFF_CTL = GT_OFF_BAR + 128;                                  // EpiCtl
-constexpr int GT_SMEM_BYTES = GT_OFF_CTL + 1600 + 1024;                       // control block + align slack
+constexpr int GT_OFF_RING = GT_STAGES * GT_STAGE_BYTES;                           // 163840
+constexpr int GT_OFF_NORM = GT_OFF_RING + GT_EPI_THREADS * GT_RING_STRIDE * 8;    // + 50176
+constexpr int GT_OFF_BAR = GT_OFF_NORM + 2 * GT_BN * 4;                           // + 2048
+constexpr int GT_OFF_CTL = GT_OFF_BAR + 128;
+constexpr int GT_SMEM_BYTES_FILTER = GT_OFF_CTL + 1088 + 1024;
+static_assert(GT_SMEM_BYTES_FILTER <= 232448, "shared memory budget");
 
 struct GemmParams {
     uint32_t n_rows, nq;
     int num_kb;              // k-blocks per row (row bytes / 128)
     int kb_elems;            // elements per k-block (32 fp32 / 64 fp16)
-    int MB, S, n_tiles, n_items;
-    unsigned long long* stats;   // optional debug counters (null = off)
-    int dbg;                 // experiments only: 1 = epilogue reads TMEM but selects nothing, 2 = releases at once
+    int MB;                  // 256-query blocks (one per CTA pair)
+    int S;                   // slices of this level's position range
+    int n_items;             // MB * S
+    int n_tiles;             // 256-row tiles of the shard
+    int bits;                // tile order = bit reversal over `bits` bits
+    int pos_begin, pos_end;  // this level's positions in that order
+    int dense;               // level 0: keep every score
+    int dbg;                 // experiments only: 2 = epilogue releases TMEM at once
     const float* sqnorm;     // [n_rows] (L2 only)
-    const uint32_t* tomb;    // bitmap or null
-    uint64_t* cand;          // [nq][KP]  ONE sorted candidate list per query, shared by every CTA (L2-resident)
-    uint64_t* gpend;         // [nq][KP]  keys accepted since the last merge (unsorted)
-    int* gcnt;               // [nq]      how many
-    int* locks;              // [nq] spin lock guarding a query's shared state
-    uint32_t* thr_g;         // [nq] ordered bits of the list's k'-th approximate value (0xFFFFFFFF until full)
+    const float* thr;        // [nq] threshold of this level (approximate distance); unused when dense
+    uint64_t* buf;           // [nq][cap] candidate keys (approximate distance bits << 32 | row)
+    int* cnt;                // [nq] keys in buf
+    int cap;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -173,180 +184,57 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t M, uint
 }
 
 // ------------------------------------------------------------------------------------------
-// warp-level sorting networks on 64-bit keys
+// helpers
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t shfl_xor64(uint64_t v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
-__device__ __forceinline__ uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
-__device__ __forceinline__ uint64_t umax64(uint64_t a, uint64_t b) { return a < b ? b : a; }
-
-// one key per lane, full sort, ascending by lane
-__device__ __forceinline__ uint64_t warp_sort32(uint64_t key, int lane) {
+// 32 consecutive floats from shared memory (explicit shared-space loads: a generic pointer into the
+// dynamic shared array would compile to generic LD, ordered against every ring store)
+__device__ __forceinline__ void lds_f32x32(uint32_t addr, float (&o)[32]) {
 #pragma unroll
-    for (int size = 2; size <= 32; size <<= 1) {
-#pragma unroll
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            const uint64_t other = shfl_xor64(key, stride);
-            const bool asc = (lane & size) == 0 || size == 32;
-            const bool lower = (lane & stride) == 0;
-            key = (lower == asc) ? umin64(key, other) : umax64(key, other);
-        }
-    }
-    return key;
+    for (int i = 0; i < 8; ++i)
+        asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+            : "=f"(o[4 * i]), "=f"(o[4 * i + 1]), "=f"(o[4 * i + 2]), "=f"(o[4 * i + 3])
+            : "r"(addr + 16 * i));
 }
-// bitonic merge across lanes (strides 16..1): bitonic input -> ascending (or descending) by lane
-template <bool ASC>
-__device__ __forceinline__ uint64_t warp_bitonic_merge32(uint64_t key, int lane) {
-#pragma unroll
-    for (int stride = 16; stride > 0; stride >>= 1) {
-        const uint64_t other = shfl_xor64(key, stride);
-        const bool lower = (lane & stride) == 0;
-        key = (lower == ASC) ? umin64(key, other) : umax64(key, other);
-    }
-    return key;
-}
-
-// Full bitonic sort of KP = R*32 keys held R per lane, element index e = r*32 + lane, ascending in e.
-template <int R>
-__device__ __forceinline__ void warp_sort_striped(uint64_t (&v)[R], int lane) {
-    constexpr int KP = R * 32;
-#pragma unroll
-    for (int size = 2; size <= KP; size <<= 1) {
-#pragma unroll
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            if (stride >= 32) {
-                const int rs = stride >> 5;
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    if ((r & rs) == 0) {
-                        const bool asc = (((r * 32) & size) == 0) || size == KP;
-                        const uint64_t lo = umin64(v[r], v[r + rs]), hi = umax64(v[r], v[r + rs]);
-                        v[r] = asc ? lo : hi;
-                        v[r + rs] = asc ? hi : lo;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const uint64_t other = shfl_xor64(v[r], stride);
-                    const bool asc = ((((r * 32) | lane) & size) == 0) || size == KP;
-                    const bool lower = (lane & stride) == 0;
-                    v[r] = (lower == asc) ? umin64(v[r], other) : umax64(v[r], other);
-                }
-            }
-        }
-    }
-}
-// Bitonic merge (ascending) of a bitonic sequence of KP = R*32 keys, striped layout.
-template <int R>
-__device__ __forceinline__ void warp_merge_striped(uint64_t (&v)[R], int lane) {
-#pragma unroll
-    for (int rs = R / 2; rs > 0; rs >>= 1) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if ((r & rs) == 0) {
-                const uint64_t lo = umin64(v[r], v[r + rs]), hi = umax64(v[r], v[r + rs]);
-                v[r] = lo;
-                v[r + rs] = hi;
-            }
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = warp_bitonic_merge32<true>(v[r], lane);
-}
-
-// Per-query shared candidate state in global memory (L2-resident), guarded by locks[q]:
-//   cand[q][KP]   sorted ascending: the KP best approximate keys merged so far
-//   gpend[q][KP]  unsorted keys accepted since the last merge, gcnt[q] of them
-//   thr_g[q]      ordered bits of cand[q][KP-1] (0xFFFFFFFF until the list is full): the pruning threshold
-// Appending is cheap; the sort + merge runs once per KP accepted keys.
-template <int KP>
-__device__ __forceinline__ uint64_t heavy_merge(uint64_t* list, const uint64_t* gpend, int n_new, int lane) {
-    constexpr int R = KP / 32;
-    uint64_t pn[R], m[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int e = r * 32 + lane;
-        pn[r] = e < n_new ? __ldcg(reinterpret_cast<const unsigned long long*>(gpend) + e) : KEY_SENTINEL;
-        m[r] = __ldcg(reinterpret_cast<const unsigned long long*>(list) + e);
-    }
-    warp_sort_striped<R>(pn, lane);
-    // half-cleaner against the reversed new keys: keeps the KP smallest of the union as a bitonic sequence
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const uint64_t rev = __shfl_sync(0xffffffffu, pn[R - 1 - r], 31 - lane);
-        m[r] = umin64(m[r], rev);
-    }
-    warp_merge_striped<R>(m, lane);
-#pragma unroll
-    for (int r = 0; r < R; ++r) __stcg(reinterpret_cast<unsigned long long*>(list) + r * 32 + lane, m[r]);
-    return __shfl_sync(0xffffffffu, m[R - 1], 31);
-}
-
-struct QueryShared {
-    uint64_t* cand; uint64_t* gpend; int* gcnt; int* locks; uint32_t* thr_g;
-};
-
-// Hand `key` (one per lane, `valid` lanes only) of query q to the shared state.  Whole converged warp.
-// Returns the query's current threshold bits.
-template <int KP>
-__device__ __forceinline__ uint32_t share_keys(const QueryShared& g, uint32_t q, uint64_t key, bool valid, int lane) {
-    const uint32_t mask = __ballot_sync(0xffffffffu, valid);
-    const int ns = __popc(mask);
-    if (ns == 0) return __ldcg(g.thr_g + q);
-    int* lock = g.locks + q;
-    if (lane == 0) {
-        while (atomicCAS(lock, 0, 1) != 0) __nanosleep(40);
-        __threadfence();
-    }
-    __syncwarp();
-    uint64_t* gp = g.gpend + (size_t)q * KP;
-    uint64_t* list = g.cand + (size_t)q * KP;
-    int gc = __ldcg(g.gcnt + q);
-    const int idx = __popc(mask & ((1u << lane) - 1u));
-    const int room = KP - gc;
-    if (valid && idx < room) __stcg(reinterpret_cast<unsigned long long*>(gp) + gc + idx, key);
-    uint32_t thr_bits = 0xFFFFFFFFu;
-    if (ns >= room) {   // buffer full: sort it and merge it into the sorted list
-        __threadfence();
-        __syncwarp();
-        const uint64_t last = heavy_merge<KP>(list, gp, KP, lane);
-        if (last != KEY_SENTINEL) thr_bits = (uint32_t)(last >> 32);
-        __syncwarp();
-        if (valid && idx >= room) __stcg(reinterpret_cast<unsigned long long*>(gp) + (idx - room), key);
-        gc = ns - room;
-        if (lane == 0 && thr_bits != 0xFFFFFFFFu) atomicMin(g.thr_g + q, thr_bits);
-    } else {
-        gc += ns;
-        thr_bits = __ldcg(g.thr_g + q);
-    }
-    __syncwarp();
-    if (lane == 0) {
-        __stcg(g.gcnt + q, gc);
-        __threadfence();
-        atomicExch(lock, 0);
-    }
-    return thr_bits;
+__host__ __device__ __forceinline__ uint32_t bitrev(uint32_t x, int bits) {
+#ifdef __CUDA_ARCH__
+    return bits ? (__brev(x) >> (32 - bits)) : 0u;
+#else
+    uint32_t r = 0;
+    for (int i = 0; i < bits; ++i) r |= ((x >> i) & 1u) << (bits - 1 - i);
+    return r;
+#endif
 }
 
 // shared-memory control block between the epilogue threads (producers of candidate keys) and the
-// merger warps (consumers): one ring of GT_PEND_CAP keys per query
+// mover warps (consumers)
 struct EpiCtl {
     uint32_t head_pub[GT_EPI_THREADS];   // keys appended so far (published by the epilogue thread)
-    uint32_t tail[GT_EPI_THREADS];       // keys consumed so far (merger)
-    float thr_s[GT_EPI_THREADS];         // latest threshold the merger has seen for the query
+    uint32_t tail[GT_EPI_THREADS];       // keys moved out so far
     uint32_t qbase[4];                   // first query of each epilogue warp's current item
     uint32_t done;                       // epilogue warps that have finished all items
 };
 
+// item -> (slice, query block) and the slice's position range inside the level
+struct ItemRange { int mb, p0, p1; };
+__device__ __forceinline__ ItemRange item_range(const GemmParams& p, int item) {
+    ItemRange r;
+    const int slice = item / p.MB;
+    r.mb = item - slice * p.MB;
+    const long long n = p.pos_end - p.pos_begin;
+    r.p0 = p.pos_begin + (int)(n * slice / p.S);
+    r.p1 = p.pos_begin + (int)(n * (slice + 1) / p.S);
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------
 // K2
 // ------------------------------------------------------------------------------------------
-template <bool F16, int KP, bool L2>
+template <bool F16, bool L2>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GT_THREADS, 1)
-gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* pend_all = reinterpret_cast<uint64_t*>(smem + GT_OFF_PEND);
+    uint64_t* ring_all = reinterpret_cast<uint64_t*>(smem + GT_OFF_RING);
     float* norm_s = reinterpret_cast<float*>(smem + GT_OFF_NORM);   // [2][256]
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + GT_OFF_BAR);
     uint64_t* empty = full + GT_STAGES;
@@ -373,7 +261,6 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (threadIdx.x < GT_EPI_THREADS) {
         ctl->head_pub[threadIdx.x] = 0;
         ctl->tail[threadIdx.x] = 0;
-        ctl->thr_s[threadIdx.x] = __int_as_float(0x7f800000);
         if (threadIdx.x < 4) ctl->qbase[threadIdx.x] = 0;
         if (threadIdx.x == 0) ctl->done = 0;
     }
@@ -383,7 +270,6 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     cluster_sync_all();                  // barriers of both CTAs are initialised before any remote arrive / copy
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
-    const QueryShared gsh{p.cand, p.gpend, p.gcnt, p.locks, p.thr_g};
 
     if (warp == 0) {
         // ================= TMA producer (both CTAs: own query rows, own half of the shard tile) =================
@@ -395,10 +281,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint64_t pol_keep = l2_policy_evict_last();
             uint32_t it = 0;
             for (int item = pair; item < p.n_items; item += num_pairs) {
-                const int slice = item / p.MB, mb = item - slice * p.MB;
-                const int t0 = (int)((long long)slice * p.n_tiles / p.S), t1 = (int)((long long)(slice + 1) * p.n_tiles / p.S);
-                const int arow = mb * (2 * GT_BM) + (int)cta_rank * GT_BM;
-                for (int tile = t0; tile < t1; ++tile) {
+                const ItemRange ir = item_range(p, item);
+                const int arow = ir.mb * (2 * GT_BM) + (int)cta_rank * GT_BM;
+                for (int pos = ir.p0; pos < ir.p1; ++pos) {
+                    const int tile = (int)bitrev((uint32_t)pos, p.bits);
+                    if (tile >= p.n_tiles) continue;
                     const int brow = tile * GT_BN + (int)cta_rank * GT_BN_HALF;
                     for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
                         const int s = it % GT_STAGES;
@@ -419,9 +306,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             constexpr uint32_t idesc = make_idesc(F16 ? 0u : 2u, 2 * GT_BM, GT_BN);
             uint32_t it = 0, tcount = 0;
             for (int item = pair; item < p.n_items; item += num_pairs) {
-                const int slice = item / p.MB;
-                const int t0 = (int)((long long)slice * p.n_tiles / p.S), t1 = (int)((long long)(slice + 1) * p.n_tiles / p.S);
-                for (int tile = t0; tile < t1; ++tile, ++tcount) {
+                const ItemRange ir = item_range(p, item);
+                for (int pos = ir.p0; pos < ir.p1; ++pos) {
+                    if ((int)bitrev((uint32_t)pos, p.bits) >= p.n_tiles) continue;
                     const uint32_t acc = tcount & 1;
                     mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
                     tc_fence_after();
@@ -439,173 +326,194 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         umma_commit_pair(&empty[s]);           // both CTAs may refill this stage once the MMAs retire
                     }
                     umma_commit_pair(&tmem_full[acc]);         // accumulators ready in both CTAs' TMEM
+                    ++tcount;
                 }
             }
         }
     } else if (warp == 2 || warp == 3) {
-        // ================= mergers: drain the per-query rings into the shared lists =================
-        // Global-memory latency (lock, list) stays off the TMEM-drain path of the epilogue warps.
-        const int base = (warp - 2) * 64;    // warp 2 serves epilogue warps 4,5; warp 3 serves 6,7
-        volatile uint32_t* v_head = ctl->head_pub;
-        volatile uint32_t* v_tail = ctl->tail;
-        volatile float* v_thr = ctl->thr_s;
-        long long mg_busy = 0, mg_hand = 0, mg_kept = 0, mg_t0 = clock64();
-        for (;;) {
-            const bool fin = *reinterpret_cast<volatile uint32_t*>(&ctl->done) == 4;
-            __threadfence_block();
-            const uint32_t av0 = v_head[base + lane] - v_tail[base + lane];
-            const uint32_t av1 = v_head[base + 32 + lane] - v_tail[base + 32 + lane];
-            const uint32_t big0 = __ballot_sync(0xffffffffu, av0 >= 16), big1 = __ballot_sync(0xffffffffu, av1 >= 16);
-            const uint32_t any0 = __ballot_sync(0xffffffffu, av0 > 0), any1 = __ballot_sync(0xffffffffu, av1 > 0);
-            if ((any0 | any1) == 0) {
-                if (fin) {
-                    if (p.stats && lane == 0) {
-                        atomicAdd(p.stats + 5, (unsigned long long)mg_busy);   // merger warp-cycles in hand-offs
-                        atomicAdd(p.stats + 6, (unsigned long long)mg_hand);   // hand-offs
-                        atomicAdd(p.stats + 7, (unsigned long long)mg_kept);   // keys surviving the pre-filter
-                        atomicAdd(p.stats + 8, (unsigned long long)(clock64() - mg_t0));
-                    }
-                    break;
-                }
-                __nanosleep(200);
-                continue;
-            }
-            const bool take_big = (big0 | big1) != 0;
-            for (int half = 0; half < 2; ++half) {
-                uint32_t m = half == 0 ? (take_big ? big0 : any0) : (take_big ? big1 : any1);
-                while (m) {
-                    const int src = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int qi = base + half * 32 + src;
-                    const long long c0 = clock64();
+        // ================= movers: key rings -> per-query candidate buffers in global memory =================
+        // Lane-parallel: each lane serves two queries; one atomicAdd reserves room for everything that is
+        // waiting in a ring, so global-memory latency never sits on the TMEM-drain path of the epilogue.
+        if (!p.dense) {
+            const int base = (warp - 2) * 64;    // warp 2 serves epilogue warps 4,5; warp 3 serves 6,7
+            volatile uint32_t* v_head = ctl->head_pub;
+            volatile uint32_t* v_tail = ctl->tail;
+            for (;;) {
+                const bool fin = *reinterpret_cast<volatile uint32_t*>(&ctl->done) == 4;
+                __threadfence_block();
+                bool moved = false;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int qi = base + h * 32 + lane;
                     const uint32_t t = v_tail[qi];
-                    const uint32_t n = min(v_head[qi] - t, 32u);
-                    __threadfence_block();
-                    const uint64_t* ring = pend_all + (size_t)qi * GT_PEND_STRIDE;
-                    uint64_t key = KEY_SENTINEL;
-                    if ((uint32_t)lane < n) key = *reinterpret_cast<const volatile uint64_t*>(ring + ((t + lane) & (GT_PEND_CAP - 1)));
-                    const uint32_t q = *reinterpret_cast<volatile uint32_t*>(&ctl->qbase[qi >> 5]) + (qi & 31);
-                    // pre-filter: keys accepted under a threshold that has since tightened, padding rows of the
-                    // last tile, tombstoned rows
-                    const uint32_t tb = __ldcg(p.thr_g + q);
-                    bool valid = key != KEY_SENTINEL;
-                    if (valid) {
-                        const uint32_t row = (uint32_t)key;
-                        valid = (uint32_t)(key >> 32) < tb && row < p.n_rows &&
-                                !(p.tomb && ((p.tomb[row >> 5] >> (row & 31)) & 1u));
-                    }
-                    mg_kept += __popc(__ballot_sync(0xffffffffu, valid));
-                    const uint32_t nb = share_keys<KP>(gsh, q, key, valid, lane);
-                    if (lane == 0) {
-                        if (nb != 0xFFFFFFFFu) v_thr[qi] = fminf(v_thr[qi], ordered_to_float(nb));
+                    const uint32_t n = v_head[qi] - t;
+                    if (n) {
+                        __threadfence_block();
+                        const uint32_t q = *reinterpret_cast<volatile uint32_t*>(&ctl->qbase[qi >> 5]) + (qi & 31);
+                        const int slot = atomicAdd(p.cnt + q, (int)n);
+                        const uint64_t* ring = ring_all + (size_t)qi * GT_RING_STRIDE;
+                        uint64_t* dst = p.buf + (size_t)q * p.cap;
+                        for (uint32_t i = 0; i < n; ++i) {
+                            const uint64_t key = *reinterpret_cast<const volatile uint64_t*>(ring + ((t + i) % GT_RING));
+                            if (slot + (int)i < p.cap) dst[slot + i] = key;     // beyond cap: counted, flagged by K2s
+                        }
                         __threadfence_block();
                         v_tail[qi] = t + n;
+                        moved = true;
                     }
-                    __syncwarp();
-                    mg_busy += clock64() - c0;
-                    ++mg_hand;
+                }
+                if (!__any_sync(0xffffffffu, moved)) {
+                    if (fin) break;
+                    __nanosleep(100);
                 }
             }
         }
     } else {
-        // ================= epilogue: streaming top-k' (each CTA: its own 128 queries) =================
+        // ================= epilogue: threshold filter (each CTA: its own 128 queries) =================
         const int et = threadIdx.x - 128;                  // 0..127 == TMEM lane == query within this CTA's block
         const int ew = et >> 5;                            // == warp % 4 : TMEM lane quadrant
-        const uint32_t my_ring_s = smem_u32(pend_all + (size_t)et * GT_PEND_STRIDE);
+        const uint32_t my_ring_s = smem_u32(ring_all + (size_t)et * GT_RING_STRIDE);
         volatile uint32_t* my_tail = &ctl->tail[et];
-        volatile float* my_thr_s = &ctl->thr_s[et];
         uint32_t head = 0, pub = 0;
         uint32_t tcount = 0;
-        long long st_wait_full = 0, st_wait_ring = 0, st_wait_item = 0, st_busy = 0, st_t0 = clock64();
         for (int item = pair; item < p.n_items; item += num_pairs) {
-            const int slice = item / p.MB, mb = item - slice * p.MB;
-            const int t0 = (int)((long long)slice * p.n_tiles / p.S), t1 = (int)((long long)(slice + 1) * p.n_tiles / p.S);
-            const uint32_t qbase = (uint32_t)mb * (2 * GT_BM) + cta_rank * GT_BM;
+            const ItemRange ir = item_range(p, item);
+            const uint32_t qbase = (uint32_t)ir.mb * (2 * GT_BM) + cta_rank * GT_BM;
             const uint32_t q = qbase + et;
             const bool q_ok = q < p.nq;
-            // the ring still holds keys of the previous item's query until the merger has drained it
-            { const long long c0 = clock64(); while (*my_tail != head) __nanosleep(64); st_wait_item += clock64() - c0; }
-            __syncwarp();
-            *my_thr_s = q_ok ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);
-            if (lane == 0) ctl->qbase[ew] = qbase + ew * 32;
-            __threadfence_block();
-            float thr = q_ok ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);   // +inf / -inf (never passes)
+            float thr = __int_as_float(0xff800000);        // -inf: nothing passes (padding queries)
+            if (!p.dense) {
+                // the ring still holds keys of the previous item's query until the movers have drained it
+                while (*my_tail != head) __nanosleep(64);
+                __syncwarp();
+                if (lane == 0) ctl->qbase[ew] = qbase + ew * 32;
+                __threadfence_block();
+                if (q_ok) thr = p.thr[q];
+            }
+            uint64_t* dense_dst = p.buf + (size_t)(q_ok ? q : 0) * p.cap;
             float n_next0 = 0.0f, n_next1 = 0.0f;
+            bool first_tile = true;
 
-            for (int tile = t0; tile < t1; ++tile, ++tcount) {
+            for (int pos = ir.p0; pos < ir.p1; ++pos) {
+                const int tile = (int)bitrev((uint32_t)pos, p.bits);
+                if (tile >= p.n_tiles) continue;
                 const uint32_t acc = tcount & 1;
                 const uint32_t row0 = (uint32_t)tile * GT_BN;
-                // the query's shared list is tightened by every CTA working on it: a row that is not below its
-                // current k'-th approximate value cannot be in the global top-k'
-                uint32_t tg = 0xFFFFFFFFu;
-                if (q_ok) tg = __ldcg(p.thr_g + q);
                 if constexpr (L2) {
                     // ||d||^2 of this tile's rows: prefetched into registers one tile ahead (first tile of an
                     // item: loaded here), published to the buffer the previous-but-one tile used
-                    float* ns = norm_s + acc * GT_BN;
-                    if (tile == t0) {
+                    float* nsw = norm_s + acc * GT_BN;
+                    if (first_tile) {
                         const uint32_t r_a = row0 + et, r_b = row0 + 128 + et;
                         n_next0 = r_a < p.n_rows ? p.sqnorm[r_a] : 0.0f;
                         n_next1 = r_b < p.n_rows ? p.sqnorm[r_b] : 0.0f;
                     }
-                    ns[et] = n_next0;
-                    ns[et + 128] = n_next1;
+                    nsw[et] = n_next0;
+                    nsw[et + 128] = n_next1;
                     asm volatile("bar.sync 1, 128;" ::: "memory");
-                    if (tile + 1 < t1) {
-                        const uint32_t r_a = row0 + GT_BN + et, r_b = row0 + GT_BN + 128 + et;
+                    // next valid tile of this item
+                    int np = pos + 1;
+                    while (np < ir.p1 && (int)bitrev((uint32_t)np, p.bits) >= p.n_tiles) ++np;
+                    if (np < ir.p1) {
+                        const uint32_t nr0 = bitrev((uint32_t)np, p.bits) * GT_BN;
+                        const uint32_t r_a = nr0 + et, r_b = nr0 + 128 + et;
                         n_next0 = r_a < p.n_rows ? p.sqnorm[r_a] : 0.0f;
                         n_next1 = r_b < p.n_rows ? p.sqnorm[r_b] : 0.0f;
                     }
                 }
-                if (tg != 0xFFFFFFFFu) thr = fminf(thr, ordered_to_float(tg));
-                { const long long c0 = clock64(); mbar_wait(&tmem_full[acc], (tcount >> 1) & 1); st_wait_full += clock64() - c0; }
+                first_tile = false;
+                mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * GT_BN;
-                const float* ns = norm_s + acc * GT_BN;
+                const uint32_t ns_s = smem_u32(norm_s + acc * GT_BN);
+                if (p.dense) {
+                    // level 0: every score of this tile is a candidate; position in the buffer is fixed
+                    uint64_t* dd = dense_dst + (size_t)(pos - p.pos_begin) * GT_BN;
 #pragma unroll 1
-                for (int c = 0; c < GT_BN / 32; ++c) {
-                    if (p.dbg == 2) break;
-                    uint32_t v[32];
-                    tmem_ld32(taddr + c * 32, v);
-                    thr = fminf(thr, *my_thr_s);
-                    // a chunk may append up to 32 keys: wait (rare) until the merger has left that much room
-                    if (head - *my_tail > (uint32_t)(GT_PEND_CAP - 32)) { const long long c0 = clock64(); while (head - *my_tail > (uint32_t)(GT_PEND_CAP - 32)) __nanosleep(32); st_wait_ring += clock64() - c0; }
-                    tmem_ld_wait();
+                    for (int c = 0; c < GT_BN / 32; ++c) {
+                        uint32_t v[32];
+                        float nv[32];
+                        tmem_ld32(taddr + c * 32, v);
+                        if constexpr (L2) lds_f32x32(ns_s + c * 128, nv);
+                        tmem_ld_wait();
+                        if (q_ok) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float dot = __uint_as_float(v[j]);
-                        float a;
-                        if constexpr (L2) a = fmaf(-2.0f, dot, ns[c * 32 + j]);
-                        else a = -dot;
-                        if (a < thr && p.dbg == 0) {
-                            st_shared_u64(my_ring_s + (head & (GT_PEND_CAP - 1)) * 8, make_key(a, row0 + c * 32 + j));
-                            ++head;
+                            for (int j = 0; j < 32; ++j) {
+                                const float dot = __uint_as_float(v[j]);
+                                float a;
+                                if constexpr (L2) a = fmaf(-2.0f, dot, nv[j]);
+                                else a = -dot;
+                                dd[c * 32 + j] = make_key(a, row0 + c * 32 + j);
+                            }
                         }
                     }
-                    if (head != pub) {
-                        __threadfence_block();
-                        ctl->head_pub[et] = head;
-                        pub = head;
-                    }
+                    // all TMEM reads of this accumulator are done: one arrive per warp on the LEADER's barrier
+                    tc_fence_before();
                     __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[acc]), 0));
+                } else if (p.dbg == 2) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[acc]), 0));
+                } else {
+                    // TMEM reads are double-buffered: chunk c+1 is in flight while chunk c is filtered
+                    auto filter_chunk = [&](const uint32_t (&v)[32], int c) {
+                        float a[32];
+                        if constexpr (L2) {
+                            float nv[32];
+                            lds_f32x32(ns_s + c * 128, nv);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) a[j] = fmaf(-2.0f, __uint_as_float(v[j]), nv[j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) a[j] = -__uint_as_float(v[j]);
+                        }
+                        // a chunk may append up to 32 keys: wait (rare) until the movers have left that much room
+                        while (head - *my_tail > (uint32_t)(GT_RING - 32)) __nanosleep(32);
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) {   // one test per 4 scores; survivors are rare
+                            const float m4 = fminf(fminf(a[4 * g], a[4 * g + 1]), fminf(a[4 * g + 2], a[4 * g + 3]));
+                            if (m4 < thr) {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    if (a[4 * g + e] < thr) {
+                                        st_shared_u64(my_ring_s + (head % GT_RING) * 8,
+                                                      make_key(a[4 * g + e], row0 + c * 32 + 4 * g + e));
+                                        ++head;
+                                    }
+                                }
+                            }
+                        }
+                        if (head != pub) {
+                            __threadfence_block();
+                            ctl->head_pub[et] = head;
+                            pub = head;
+                        }
+                    };
+                    uint32_t v0[32], v1[32];
+                    tmem_ld32(taddr, v0);
+                    tmem_ld_wait();
+#pragma unroll 1
+                    for (int c = 0; c < GT_BN / 32; c += 2) {
+                        tmem_ld32(taddr + (c + 1) * 32, v1);
+                        filter_chunk(v0, c);
+                        tmem_ld_wait();
+                        if (c + 2 < GT_BN / 32) {
+                            tmem_ld32(taddr + (c + 2) * 32, v0);
+                        } else {
+                            // the whole accumulator is in registers: hand it back before filtering the last chunk
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[acc]), 0));
+                        }
+                        filter_chunk(v1, c + 1);
+                        tmem_ld_wait();
+                    }
                 }
-                // all TMEM reads of this accumulator are done: one arrive per warp on the LEADER's barrier
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[acc]), 0));
+                ++tcount;
             }
         }
         __syncwarp();
-        if (p.stats) {
-            st_busy = clock64() - st_t0;
-            atomicAdd(p.stats + 0, (unsigned long long)head);            // keys appended
-            if (lane == 0) {
-                atomicAdd(p.stats + 1, (unsigned long long)st_wait_full);   // epilogue warp-cycles waiting for MMA
-                atomicAdd(p.stats + 4, (unsigned long long)st_busy);        // epilogue warp-cycles total
-            }
-            atomicAdd(p.stats + 2, (unsigned long long)st_wait_ring);    // thread-cycles waiting for ring space
-            atomicAdd(p.stats + 3, (unsigned long long)st_wait_item);    // thread-cycles waiting for drain at item switch
-        }
         if (lane == 0) {
             __threadfence_block();
             atomicAdd(&ctl->done, 1u);
@@ -617,21 +525,132 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 2) tmem_dealloc(tmem_base, GT_TMEM_COLS);
 }
 
-// Merges what is still waiting in gpend[q] into cand[q]: one warp per query.
-template <int KP>
-__global__ void finalize_lists_kernel(uint64_t* cand, const uint64_t* gpend, const int* gcnt, size_t nq) {
-    const size_t w = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (w >= nq) return;
-    const int n = gcnt[w];
-    if (n > 0) heavy_merge<KP>(cand + w * KP, gpend + w * KP, n, lane);
+// ------------------------------------------------------------------------------------------
+// K2s: per query, keep the KP best approximate keys of what the level collected; their KP-th value
+// is the next level's threshold.  Padding rows of the last tile and tombstoned rows are dropped here.
+// ------------------------------------------------------------------------------------------
+struct SelectParams {
+    uint64_t* buf; int* cnt; int cap; int kp;
+    float* thr; int* overflow;
+    const uint32_t* tomb; uint32_t n_rows;
+    int dense_cnt;            // > 0: level 0 wrote this many keys per query at fixed positions
+};
+
+// Radix select on the 32 distance bits (4 passes of 8 bits): O(n) instead of a full sort.  Keys whose
+// distance bits equal the KP-th value are taken in arrival order until KP are kept.  Output unordered.
+__global__ void __launch_bounds__(256) select_kernel(const SelectParams p) {
+    extern __shared__ uint64_t sk[];
+    __shared__ int hist[256];
+    __shared__ uint32_t s_prefix, s_rank;
+    __shared__ int s_valid, s_c1, s_c2;
+    const size_t q = blockIdx.x;
+    uint64_t* b = p.buf + q * (size_t)p.cap;
+    int n = p.dense_cnt > 0 ? p.dense_cnt : p.cnt[q];
+    if (n > p.cap) {
+        if (threadIdx.x == 0) p.overflow[q] = 1;
+        n = p.cap;
+    }
+    if (threadIdx.x == 0) { s_valid = 0; s_c1 = 0; s_c2 = 0; s_prefix = 0; }
+    __syncthreads();
+    int my_valid = 0;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        uint64_t key = b[i];
+        if (key != KEY_SENTINEL) {
+            const uint32_t row = (uint32_t)key;
+            if (row >= p.n_rows || (p.tomb && ((p.tomb[row >> 5] >> (row & 31)) & 1u))) key = KEY_SENTINEL;
+        }
+        sk[i] = key;
+        my_valid += key != KEY_SENTINEL;
+    }
+    my_valid = warp_sum_int(my_valid);
+    if ((threadIdx.x & 31) == 0 && my_valid) atomicAdd(&s_valid, my_valid);
+    __syncthreads();
+    const int n_valid = s_valid;
+    __syncthreads();
+    if (n_valid <= p.kp) {
+        // everything valid is kept (no threshold yet)
+        for (int i = threadIdx.x; i < n; i += 256) {
+            const uint64_t key = sk[i];
+            if (key != KEY_SENTINEL) b[atomicAdd(&s_c1, 1)] = key;
+        }
+        __syncthreads();
+        for (int i = n_valid + threadIdx.x; i < p.kp; i += 256) b[i] = KEY_SENTINEL;
+        if (threadIdx.x == 0) {
+            p.cnt[q] = p.kp;
+            p.thr[q] = __int_as_float(0x7f800000);
+        }
+        return;
+    }
+    if (threadIdx.x == 0) s_rank = (uint32_t)p.kp;     // 1-based rank of the key we are looking for
+    uint32_t mask = 0;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        hist[threadIdx.x] = 0;
+        __syncthreads();
+        const uint32_t prefix = s_prefix;
+        for (int i = threadIdx.x; i < n; i += 256) {
+            const uint64_t key = sk[i];
+            if (key != KEY_SENTINEL) {
+                const uint32_t hi = (uint32_t)(key >> 32);
+                if ((hi & mask) == prefix) atomicAdd(&hist[(hi >> shift) & 255], 1);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            // 8 bins per lane, warp prefix sum, find the bin that holds rank s_rank
+            int local[8], sum = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { local[i] = hist[threadIdx.x * 8 + i]; sum += local[i]; }
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)threadIdx.x >= o) incl += t;
+            }
+            const int excl = incl - sum;
+            const int rank = (int)s_rank;
+            if (rank > excl && rank <= incl) {
+                int run = excl;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (rank > run && rank <= run + local[i]) {
+                        s_prefix = prefix | ((uint32_t)(threadIdx.x * 8 + i) << shift);
+                        s_rank = (uint32_t)(rank - run);
+                    }
+                    run += local[i];
+                }
+            }
+        }
+        mask |= 0xFFu << shift;
+        __syncthreads();
+    }
+    const uint32_t T = s_prefix;                  // distance bits of the KP-th best key
+    const int need_eq = (int)s_rank;              // how many keys with exactly these bits to keep
+    const int n_less = p.kp - need_eq;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const uint64_t key = sk[i];
+        if (key == KEY_SENTINEL) continue;
+        const uint32_t hi = (uint32_t)(key >> 32);
+        if (hi < T) b[atomicAdd(&s_c1, 1)] = key;
+        else if (hi == T) {
+            const int s = atomicAdd(&s_c2, 1);
+            if (s < need_eq) b[n_less + s] = key;
+        }
+    }
+    if (threadIdx.x == 0) {
+        p.cnt[q] = p.kp;
+        p.thr[q] = ordered_to_float(T);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
 // K4: exact re-rank of the k' approximate candidates + coverage certificate
 // ------------------------------------------------------------------------------------------
 struct RerankParams {
-    const uint64_t* approx;   // [nq][KP] ascending approximate keys (distance-like value, row)
+    const uint64_t* approx;   // [nq][stride] ascending approximate keys (distance-like value, row); first KP used
+    size_t stride;
+    const int* overflow;      // [nq] 1 = the candidate buffer overflowed: certificate void
+    const float* tau;         // [nq] KP-th best approximate value (+inf: fewer than KP live rows, all are candidates)
     const void* rows; uint32_t row_bytes; uint32_t ld;
     const uint32_t* labels;
     const float* q;           // prepared queries [nq][ld] fp32
@@ -648,7 +667,7 @@ template <typename T, int KP>
 __global__ void __launch_bounds__(256) rerank_kernel(const RerankParams p) {
     __shared__ uint64_t ek[KP];
     const int q = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint64_t* ap = p.approx + (size_t)q * KP;
+    const uint64_t* ap = p.approx + (size_t)q * p.stride;
     const float* qv = p.q + (size_t)q * p.ld;
     const int nld16 = p.row_bytes / 512;
     constexpr int PER16 = 16 / sizeof(T);
@@ -721,9 +740,8 @@ __global__ void __launch_bounds__(256) rerank_kernel(const RerankParams p) {
         for (int i = 0; i < k; ++i) cnt += ek[i] != KEY_SENTINEL;
         if (p.out_counts) p.out_counts[q] = cnt;
         bool ok = true;
-        const uint64_t last = ap[KP - 1];
-        if (last != KEY_SENTINEL) {   // candidate list full: rows outside it exist, prove they cannot matter
-            const float a_tau = key_dist(last);
+        const float a_tau = p.tau[q];
+        if (a_tau < __int_as_float(0x7f800000)) {   // candidate list full: rows outside it exist, prove they cannot matter
             const float qn2 = p.qn2[q];
             const float dmax2 = __uint_as_float(*p.max_sqnorm_bits);
             const float eb = p.eps_rel * sqrtf(qn2) * sqrtf(dmax2);
@@ -733,6 +751,7 @@ __global__ void __launch_bounds__(256) rerank_kernel(const RerankParams p) {
             const uint64_t kth = ek[k - 1];
             ok = kth != KEY_SENTINEL && key_dist(kth) < tau - eps;
         }
+        if (p.overflow[q]) ok = false;
         p.flags[q] = ok ? 0 : 1;
         if (!ok) atomicAdd(p.n_flagged, 1);
     }
@@ -747,16 +766,14 @@ __global__ void f32_to_f16_kernel(const float* __restrict__ in, __half* __restri
 // host side
 // ------------------------------------------------------------------------------------------
 struct GemmWsImpl {
-    uint64_t* cand = nullptr; size_t cand_cap = 0;
-    int* locks = nullptr; size_t locks_cap = 0;
-    uint64_t* gpend = nullptr; size_t gpend_cap = 0;
-    int* gcnt = nullptr; size_t gcnt_cap = 0;
+    uint64_t* buf = nullptr; size_t buf_cap = 0;
+    int* cnt = nullptr; size_t cnt_cap = 0;
+    float* thr = nullptr; size_t thr_cap = 0;
+    int* overflow = nullptr; size_t ovf_cap = 0;
     __half* q16 = nullptr; size_t q16_cap = 0;
     int* flags = nullptr; size_t flags_cap = 0;
-    uint32_t* thr_g = nullptr; size_t thr_cap = 0;
     int* n_flagged = nullptr;
     int* h_n_flagged = nullptr;   // pinned
-    unsigned long long* stats = nullptr;
 };
 struct GemmPlanImpl {
     long fallbacks = 0;
@@ -795,6 +812,7 @@ static int kp_for_k(int k) {
     while (kp < 2 * k) kp <<= 1;
     return kp;
 }
+static int cap_for_kp(int kp) { return std::max(16 * kp, GT_DENSE_TILES * GT_BN); }
 
 bool gemm_topk_supported(int dim, int ld, bool f16, int k, size_t n_rows) {
     (void)dim;
@@ -814,28 +832,17 @@ static cudaError_t grow_dev(T*& ptr, size_t& cap, size_t need) {
     return e;
 }
 
-template <bool F16, int KP, bool L2>
+template <bool F16, bool L2>
 static cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& gp, int grid, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_topk_kernel<F16, KP, L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(gemm_filter_kernel<F16, L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES_FILTER);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    gemm_topk_kernel<F16, KP, L2><<<grid, GT_THREADS, GT_SMEM_BYTES, st>>>(tmA, tmB, gp);
+    gemm_filter_kernel<F16, L2><<<grid, GT_THREADS, GT_SMEM_BYTES_FILTER, st>>>(tmA, tmB, gp);
     count_launch();
     return cudaGetLastError();
-}
-
-template <bool F16, bool L2>
-static cudaError_t launch_gemm_kp(int kp, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& gp, int grid, cudaStream_t st) {
-    switch (kp) {
-        case 32: return launch_gemm<F16, 32, L2>(tmA, tmB, gp, grid, st);
-        case 64: return launch_gemm<F16, 64, L2>(tmA, tmB, gp, grid, st);
-        case 128: return launch_gemm<F16, 128, L2>(tmA, tmB, gp, grid, st);
-        case 256: return launch_gemm<F16, 256, L2>(tmA, tmB, gp, grid, st);
-    }
-    return cudaErrorInvalidValue;
 }
 
 template <typename T>
@@ -851,17 +858,16 @@ static cudaError_t launch_rerank(int kp, const RerankParams& rp, size_t nq, cuda
     return cudaGetLastError();
 }
 
-// picks the number of shard slices: fill the SMs in whole waves, prefer few slices
-static int choose_slices(int MB, int n_tiles, int num_sms) {
+// slices of a level's position range: fill the pairs in whole waves, prefer few slices
+static int choose_slices(int MB, int n_pos, int num_pairs) {
     int best = 1;
     double best_cost = 1e30;
-    const int smax = std::min(n_tiles, 96);
+    const int smax = std::min(n_pos, 128);
     for (int S = 1; S <= smax; ++S) {
         const long items = (long)MB * S;
-        const long waves = (items + num_sms - 1) / num_sms;
-        const double tiles_per_item = (double)n_tiles / S;
-        // time ~ waves * (tiles per item + warm-up of the per-item lists, ~4 tiles worth)
-        const double cost = waves * (tiles_per_item + 4.0);
+        const long waves = (items + num_pairs - 1) / num_pairs;
+        const double tiles_per_item = (double)n_pos / S;
+        const double cost = waves * (tiles_per_item + 1.0);   // ~1 tile-time of pipeline fill per item
         if (cost < best_cost * 0.999) { best_cost = cost; best = S; }
     }
     return best;
@@ -878,22 +884,18 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
     }
     auto* w = static_cast<GemmWsImpl*>(ws.impl);
     const int kp = kp_for_k(a.k);
+    const int cap = cap_for_kp(kp);
     const int MB = (int)((a.nq + 2 * GT_BM - 1) / (2 * GT_BM));   // 256-query blocks, one per CTA pair
     const int n_tiles = (int)((a.n_rows + GT_BN - 1) / GT_BN);
     const int num_pairs_max = a.num_sms / 2;
-    const int S = choose_slices(MB, n_tiles, num_pairs_max);
     const size_t esz = a.f16 ? 2 : 4;
     cudaError_t e;
-    if ((e = grow_dev(w->cand, w->cand_cap, a.nq * (size_t)kp)) != cudaSuccess) return e;
-    if ((e = grow_dev(w->locks, w->locks_cap, a.nq)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(w->cand, 0xFF, a.nq * (size_t)kp * sizeof(uint64_t), st)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(w->locks, 0, a.nq * sizeof(int), st)) != cudaSuccess) return e;
-    if ((e = grow_dev(w->gpend, w->gpend_cap, a.nq * (size_t)kp)) != cudaSuccess) return e;
-    if ((e = grow_dev(w->gcnt, w->gcnt_cap, a.nq)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(w->gcnt, 0, a.nq * sizeof(int), st)) != cudaSuccess) return e;
+    if ((e = grow_dev(w->buf, w->buf_cap, a.nq * (size_t)cap)) != cudaSuccess) return e;
+    if ((e = grow_dev(w->cnt, w->cnt_cap, a.nq)) != cudaSuccess) return e;
+    if ((e = grow_dev(w->thr, w->thr_cap, a.nq)) != cudaSuccess) return e;
+    if ((e = grow_dev(w->overflow, w->ovf_cap, a.nq)) != cudaSuccess) return e;
     if ((e = grow_dev(w->flags, w->flags_cap, a.nq)) != cudaSuccess) return e;
-    if ((e = grow_dev(w->thr_g, w->thr_cap, a.nq)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(w->thr_g, 0xFF, a.nq * sizeof(uint32_t), st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(w->overflow, 0, a.nq * sizeof(int), st)) != cudaSuccess) return e;
     const void* qa = a.q;
     if (a.f16) {
         if ((e = grow_dev(w->q16, w->q16_cap, a.nq * (size_t)a.ld)) != cudaSuccess) return e;
@@ -912,41 +914,60 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
     gp.num_kb = (int)((size_t)a.ld * esz / GT_KB_BYTES);
     gp.kb_elems = (int)(GT_KB_BYTES / esz);
     { const char* d = getenv("VDB_GEMM_DBG"); gp.dbg = d ? atoi(d) : 0; }
-    if (getenv("VDB_GEMM_STATS")) {
-        if (!w->stats) cudaMalloc((void**)&w->stats, 16 * sizeof(unsigned long long));
-        cudaMemsetAsync(w->stats, 0, 16 * sizeof(unsigned long long), st);
-        gp.stats = w->stats;
-    }
-    gp.MB = MB; gp.S = S; gp.n_tiles = n_tiles; gp.n_items = MB * S;
-    gp.sqnorm = a.sqnorm; gp.tomb = a.tomb; gp.cand = w->cand; gp.gpend = w->gpend; gp.gcnt = w->gcnt; gp.locks = w->locks; gp.thr_g = w->thr_g;
-    const int grid = 2 * std::min(gp.n_items, num_pairs_max);   // whole CTA pairs
+    gp.MB = MB; gp.n_tiles = n_tiles;
+    gp.bits = 0;
+    while ((1 << gp.bits) < n_tiles) ++gp.bits;
+    const int n_pos = 1 << gp.bits;          // positions in bit-reversed order; those mapping past n_tiles are skipped
+    gp.sqnorm = a.sqnorm; gp.thr = w->thr; gp.buf = w->buf; gp.cnt = w->cnt; gp.cap = cap;
     const bool l2 = a.metric == 0;
-    if (a.f16) e = l2 ? launch_gemm_kp<true, true>(kp, tmA, tmB, gp, grid, st) : launch_gemm_kp<true, false>(kp, tmA, tmB, gp, grid, st);
-    else       e = l2 ? launch_gemm_kp<false, true>(kp, tmA, tmB, gp, grid, st) : launch_gemm_kp<false, false>(kp, tmA, tmB, gp, grid, st);
-    if (e != cudaSuccess) return e;
 
-    {   // keys still waiting in the per-query pending buffers
-        const unsigned blocks = (unsigned)((a.nq * 32 + 255) / 256);
-        switch (kp) {
-            case 32: finalize_lists_kernel<32><<<blocks, 256, 0, st>>>(w->cand, w->gpend, w->gcnt, a.nq); break;
-            case 64: finalize_lists_kernel<64><<<blocks, 256, 0, st>>>(w->cand, w->gpend, w->gcnt, a.nq); break;
-            case 128: finalize_lists_kernel<128><<<blocks, 256, 0, st>>>(w->cand, w->gpend, w->gcnt, a.nq); break;
-            default: finalize_lists_kernel<256><<<blocks, 256, 0, st>>>(w->cand, w->gpend, w->gcnt, a.nq); break;
+    SelectParams sp{};
+    sp.buf = w->buf; sp.cnt = w->cnt; sp.cap = cap; sp.kp = kp; sp.thr = w->thr; sp.overflow = w->overflow;
+    sp.tomb = a.tomb; sp.n_rows = a.n_rows;
+    static bool sel_configured = false;
+    if (!sel_configured) {
+        if ((e = cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return e;
+        sel_configured = true;
+    }
+    int sel_np = 2;
+    while (sel_np < cap) sel_np <<= 1;
+
+    // levels over positions: [0, d0) dense, then each level GT_LEVEL_GROWTH x what has been seen, the last one
+    // takes what is left if that is at most 1.5 x the growth
+    int pos = 0;
+    int level = 0;
+    while (pos < n_pos) {
+        int next;
+        if (level == 0) next = std::min(n_pos, GT_DENSE_TILES);
+        else {
+            // positions scale with tiles by n_pos / n_tiles (< 2): use positions directly
+            long want = (long)pos * GT_LEVEL_GROWTH;
+            next = (int)std::min<long>(n_pos, pos + want);
+            if ((long)(n_pos - pos) <= want + want / 2) next = n_pos;
         }
+        gp.pos_begin = pos; gp.pos_end = next; gp.dense = level == 0 ? 1 : 0;
+        gp.S = choose_slices(MB, next - pos, num_pairs_max);
+        gp.n_items = MB * gp.S;
+        const int grid = 2 * std::min(gp.n_items, num_pairs_max);   // whole CTA pairs
+        if (level == 0) {
+            // dense level writes fixed positions; positions whose tile is past the end stay sentinel
+            if ((e = cudaMemsetAsync(w->buf, 0xFF, a.nq * (size_t)cap * sizeof(uint64_t), st)) != cudaSuccess) return e;
+        }
+        if (a.f16) e = l2 ? launch_gemm<true, true>(tmA, tmB, gp, grid, st) : launch_gemm<true, false>(tmA, tmB, gp, grid, st);
+        else       e = l2 ? launch_gemm<false, true>(tmA, tmB, gp, grid, st) : launch_gemm<false, false>(tmA, tmB, gp, grid, st);
+        if (e != cudaSuccess) return e;
+        sp.dense_cnt = level == 0 ? (next - pos) * GT_BN : 0;
+        select_kernel<<<(unsigned)a.nq, 256, (size_t)sel_np * 8, st>>>(sp);
         count_launch();
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        pos = next;
+        ++level;
     }
-    if (gp.stats) {
-        unsigned long long hs[16];
-        cudaMemcpyAsync(hs, w->stats, sizeof(hs), cudaMemcpyDeviceToHost, st);
-        cudaStreamSynchronize(st);
-        fprintf(stderr, "[gemm stats] S=%d items=%d grid=%d | appended=%llu kept=%llu handoffs=%llu | epi wait_full=%.1f%% ring=%.2f%% item=%.2f%% | merger busy=%.1f%%\n",
-                S, gp.n_items, grid, hs[0], hs[7], hs[6], 100.0 * hs[1] / (double)(hs[4] + 1),
-                100.0 * hs[2] / 32.0 / (double)(hs[4] + 1), 100.0 * hs[3] / 32.0 / (double)(hs[4] + 1), 100.0 * hs[5] / (double)(hs[8] + 1));
-    }
+
     if ((e = cudaMemsetAsync(w->n_flagged, 0, sizeof(int), st)) != cudaSuccess) return e;
     RerankParams rp{};
-    rp.approx = w->cand; rp.rows = a.rows; rp.row_bytes = (uint32_t)((size_t)a.ld * esz); rp.ld = a.ld;
+    rp.approx = w->buf; rp.stride = (size_t)cap; rp.overflow = w->overflow; rp.tau = w->thr;
+    rp.rows = a.rows; rp.row_bytes = (uint32_t)((size_t)a.ld * esz); rp.ld = a.ld;
     rp.labels = a.labels; rp.q = a.q; rp.qn2 = a.qn2; rp.max_sqnorm_bits = a.d_max_sqnorm_bits;
     rp.k = a.k; rp.metric = a.metric;
     rp.eps_rel = a.f16 ? 6.5e-4f : 2.5e-3f;
@@ -987,13 +1008,12 @@ void gemm_plan_free(GemmPlan& plan) {
 void gemm_workspace_free(GemmWorkspace& ws) {
     auto* w = static_cast<GemmWsImpl*>(ws.impl);
     if (!w) return;
-    if (w->cand) cudaFree(w->cand);
-    if (w->locks) cudaFree(w->locks);
-    if (w->gpend) cudaFree(w->gpend);
-    if (w->gcnt) cudaFree(w->gcnt);
+    if (w->buf) cudaFree(w->buf);
+    if (w->cnt) cudaFree(w->cnt);
+    if (w->thr) cudaFree(w->thr);
+    if (w->overflow) cudaFree(w->overflow);
     if (w->q16) cudaFree(w->q16);
     if (w->flags) cudaFree(w->flags);
-    if (w->thr_g) cudaFree(w->thr_g);
     if (w->n_flagged) cudaFree(w->n_flagged);
     if (w->h_n_flagged) cudaFreeHost(w->h_n_flagged);
     delete w;
