@@ -121,7 +121,7 @@ def workload_name(a):
 # --------------------------------------------------------------------------------------------
 # CPU legs (oracle port: the reference's own path -- hnswlib/plyvel/thrift -- is not installable)
 # --------------------------------------------------------------------------------------------
-def cpu_knn_qps(a, nq: int, rows_cap: int = 1_000_000):
+def cpu_knn_qps(a, nq: int, rows_cap: int = 1_000_000, return_ids: bool = False):
     """Times the oracle's exact scan (oracle/knn_ref.c, OpenMP, all host threads) for nq queries
     over min(rows, rows_cap) rows and scales linearly to the full row count."""
     from oracle import c_ref
@@ -133,11 +133,12 @@ def cpu_knn_qps(a, nq: int, rows_cap: int = 1_000_000):
     q = c_ref.synth_rows(SEED_QUERY, 0, nq, a.dim)
     c_ref.knn(q[:1], stored[:1000], None, a.k, a.metric)        # warm the OpenMP pool
     t0 = time.perf_counter()
-    c_ref.knn(q, stored, None, a.k, a.metric)
+    ids, _, _ = c_ref.knn(q, stored, None, a.k, a.metric)
     dt = time.perf_counter() - t0
     dt_full = dt * (a.rows / n)
-    return nq / dt_full, c_ref.num_threads(), f"{nq} queries x {n} rows in {dt:.2f}s" + (
-        f", scaled x{a.rows / n:.1f} to {a.rows} rows" if n != a.rows else "")
+    out = (nq / dt_full, c_ref.num_threads(), f"{nq} queries x {n} rows in {dt:.2f}s" + (
+        f", scaled x{a.rows / n:.1f} to {a.rows} rows" if n != a.rows else ""))
+    return out + ((ids if n == a.rows else None),) if return_ids else out
 
 
 def run_reference(a):
@@ -245,7 +246,7 @@ def run_ours(a):
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        final = (o_ids if world > 1 else ids)[:1].cpu().numpy()
+        final = (o_ids if world > 1 else ids)[:64].cpu().numpy()
         return float(ms.item()) * 1e-3, kern_ns, nprof, launches, final
 
     def e2e_leg(nq, steps, warmup):
@@ -286,8 +287,29 @@ def run_ours(a):
         return float(dt.item())
 
     peaks = measured_peaks()
+
+    def cublas_tf32_tflops():
+        """fp32 rows go through kind::tf32: the fair tensor denominator is the TF32 dense rate this box
+        sustains, measured here the way MEASURED_PEAKS.json measures bf16 (torch.matmul 8192^3, best of 5)."""
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            x = torch.randn(8192, 8192, device=dev)
+            y = torch.randn(8192, 8192, device=dev)
+            torch.matmul(x, y)
+            best = 1e9
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); torch.matmul(x, y); e1.record(); torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            return 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = old
+            del x, y
+
+    tf32_peak = cublas_tf32_tflops() if a.store == "f32" else None
     with ClockSampler(local) as clk:
-        sec, kern_ns, nprof, launches, _ = device_leg(a.batch, a.steps, a.warmup)
+        sec, kern_ns, nprof, launches, got_ids = device_leg(a.batch, a.steps, a.warmup)
         e2e_sec = e2e_leg(a.batch, a.steps, a.warmup)
         single = None
         if not a.no_single:
@@ -311,13 +333,21 @@ def run_ours(a):
     t_kernel = kern_ns * 1e-9 / max(nprof, 1)
     tensor_batches = ix.get_stat("tensor_batches")
     if tensor_batches > 0:
+        # one search = `passes_per_step` launches of gemm_filter_kernel (one per threshold level) that together
+        # contract every query with every row once: algorithmic flops per search / summed launch time
         flops = 2.0 * a.batch * (hi - lo) * a.dim
-        ach = flops / t_kernel / 1e12
+        t_step = kern_ns * 1e-9 / max(a.steps, 1)
+        ach = flops / t_step / 1e12
         tf32 = a.store == "f32"
-        peak = peaks["bf16_tflops_sustained"] * (0.5 if tf32 else 1.0)
-        roof = {"bound": "tensor", "kernel": "gemm_topk_kernel", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                "frac": ach / peak, "peak_source": peaks["source"] + (" bf16 sustained x0.5 (tf32)" if tf32 else " bf16 sustained"),
-                "algorithmic_flops_per_launch": flops, "kernel_us": t_kernel * 1e6, "traffic": None}
+        peak = tf32_peak if tf32 else peaks["bf16_tflops"]
+        roof = {"bound": "tensor", "kernel": "gemm_filter_kernel", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": ach / peak,
+                "peak_source": ("cuBLAS TF32 8192^3 measured in this run (fp32 rows use kind::tf32); "
+                                f"MEASURED_PEAKS bf16 = {peaks['bf16_tflops']:.0f} burst / {peaks['bf16_tflops_sustained']:.0f} sustained")
+                if tf32 else peaks["source"] + " bf16 burst (fp16 rows use kind::f16)",
+                "frac_of_measured_bf16": ach / peaks["bf16_tflops"],
+                "algorithmic_flops_per_step": flops, "kernel_us_per_step": t_step * 1e6,
+                "launches_per_step": passes_per_step, "traffic": None}
     else:
         ach = shard_bytes / t_kernel / 1e9
         roof = {"bound": "hbm", "kernel": "scan_topk_kernel", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -327,10 +357,15 @@ def run_ours(a):
 
     if rank == 0:
         cpu = None
+        recall = None
         if not a.no_cpu and world == 1:
-            qps, cores, desc = cpu_knn_qps(a, a.cpu_queries or 64)
+            qps, cores, desc, want_ids = cpu_knn_qps(a, a.cpu_queries or 64, return_ids=True)
             cpu = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
                    "sample": desc + " (oracle/knn_ref.c exact scan, OpenMP)"}
+            if want_ids is not None and a.rows <= 1_000_000:
+                m = min(len(want_ids), len(got_ids))
+                hits = sum(len(set(got_ids[i].tolist()) & set(want_ids[i].tolist())) for i in range(m))
+                recall = hits / float(m * a.k)
         line = {
             "metric": "queries/sec exact top-k", "value": a.batch * a.steps / sec, "unit": "queries/s",
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * sec / a.steps,
@@ -345,7 +380,7 @@ def run_ours(a):
             "cpu_baseline": cpu,
             "single_query": single,
             "clocks": clk.summary(),
-            "recall_at_k": None,
+            "recall_at_k": recall,
             "fallback_queries": ix.get_stat("fallback_queries"),
         }
         print(json.dumps(line), flush=True)

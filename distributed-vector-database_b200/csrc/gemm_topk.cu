@@ -953,8 +953,10 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
             // dense level writes fixed positions; positions whose tile is past the end stay sentinel
             if ((e = cudaMemsetAsync(w->buf, 0xFF, a.nq * (size_t)cap * sizeof(uint64_t), st)) != cudaSuccess) return e;
         }
+        if (a.prof_begin) a.prof_begin(a.prof_ctx, st);
         if (a.f16) e = l2 ? launch_gemm<true, true>(tmA, tmB, gp, grid, st) : launch_gemm<true, false>(tmA, tmB, gp, grid, st);
         else       e = l2 ? launch_gemm<false, true>(tmA, tmB, gp, grid, st) : launch_gemm<false, false>(tmA, tmB, gp, grid, st);
+        if (a.prof_end) a.prof_end(a.prof_ctx, st);
         if (e != cudaSuccess) return e;
         sp.dense_cnt = level == 0 ? (next - pos) * GT_BN : 0;
         select_kernel<<<(unsigned)a.nq, 256, (size_t)sel_np * 8, st>>>(sp);

@@ -23,6 +23,10 @@ struct GemmSearchArgs {
     const unsigned int* d_max_sqnorm_bits;
     int num_sms;
     int64_t* out_ids; float* out_dist; int* out_counts;
+    // optional: called around every launch of the dominant (tensor-core) kernel so the caller can time it
+    void (*prof_begin)(void* ctx, cudaStream_t st) = nullptr;
+    void (*prof_end)(void* ctx, cudaStream_t st) = nullptr;
+    void* prof_ctx = nullptr;
 };
 
 bool gemm_topk_supported(int dim, int ld, bool f16, int k, size_t n_rows);

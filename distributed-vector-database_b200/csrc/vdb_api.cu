@@ -226,20 +226,26 @@ struct WsGuard {
 
 struct ProfScope {   // records start/stop events around the dominant kernel when profiling is on
     vdb* db; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
-    ProfScope(vdb* d, cudaStream_t s) : db(d), st(s) {
+    ProfScope(vdb* d, cudaStream_t s) : db(d), st(s) { begin(); }
+    ProfScope(vdb* d, cudaStream_t s, bool deferred) : db(d), st(s) { (void)deferred; }
+    void begin() {
         if (!db->opt_profile.load()) return;
         std::lock_guard<std::mutex> lk(db->prof_mu);
         if (!db->prof_pool.empty()) { a = db->prof_pool.back().first; b = db->prof_pool.back().second; db->prof_pool.pop_back(); }
         else { cudaEventCreate(&a); cudaEventCreate(&b); }
         cudaEventRecord(a, st);
     }
-    ~ProfScope() {
+    void end() {
         if (!a) return;
         cudaEventRecord(b, st);
         std::lock_guard<std::mutex> lk(db->prof_mu);
         db->prof_events.emplace_back(a, b);
+        a = b = nullptr;
     }
+    ~ProfScope() { end(); }
 };
+static void prof_begin_cb(void* ctx, cudaStream_t) { static_cast<ProfScope*>(ctx)->begin(); }
+static void prof_end_cb(void* ctx, cudaStream_t) { static_cast<ProfScope*>(ctx)->end(); }
 
 // Exact scan (K1 + K5) of nq PREPARED queries [nq][ld]; groups of up to 8 queries per pass.
 int scan_prepared(vdb* db, Workspace* ws, const float* d_qp, size_t nq, int k, int64_t* d_ids, float* d_dist,
@@ -320,11 +326,9 @@ int search_core(vdb* db, Workspace* ws, const float* d_q_raw, size_t nq, int k, 
         a.num_sms = db->num_sms;
         a.out_ids = d_ids; a.out_dist = d_dist; a.out_counts = d_cnt;
         std::string err;
-        cudaError_t e;
-        {
-            ProfScope prof(db, st);
-            e = gemm_topk_search(db->gemm_plan, ws->gemm, a, st, err);
-        }
+        ProfScope prof(db, st, true);       // one event pair per launch of the tensor-core kernel
+        a.prof_begin = prof_begin_cb; a.prof_end = prof_end_cb; a.prof_ctx = &prof;
+        cudaError_t e = gemm_topk_search(db->gemm_plan, ws->gemm, a, st, err);
         if (e != cudaSuccess) {
             cudaGetLastError();
             return fail(VDB_ECUDA, "gemm_topk_search: " + (err.empty() ? std::string(cudaGetErrorString(e)) : err));
