@@ -1,0 +1,97 @@
+"""Coordinator side of the search path: scatter to every shard, gather, merge
+(reference src/coordinator/handler.py:117-228).  RPC pooling and ZooKeeper are out of scope; the
+"nodes" here are handler objects living in this process (one per GPU), or ranks of a
+torch.distributed job (`ShardedSearcher`)."""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .sharding import assign_shards_to_nodes, get_shard_id
+from .ttypes import Response, SearchRequest, SearchResult, VectorData
+
+
+def merge_search_results(per_node: Sequence[Optional[SearchResult]], top_k: int) -> SearchResult:
+    """The merge of `CoordinatorHandler.search` (coordinator/handler.py:200-225): concatenate in node order,
+    the first occurrence of a key wins, stable ascending sort by score, slice top_k."""
+    all_keys, all_scores, all_vectors, seen = [], [], [], set()
+    for res in per_node:
+        if res is None:
+            continue
+        vecs = res.vectors if res.vectors is not None else [None] * len(res.keys or [])
+        for k, s, v in zip(res.keys or [], res.scores or [], vecs):
+            if k in seen:
+                continue
+            seen.add(k)
+            all_keys.append(k)
+            all_scores.append(s)
+            all_vectors.append(v)
+    if not all_scores:
+        return SearchResult([], [], [])
+    order = sorted(range(len(all_scores)), key=lambda i: all_scores[i])[:top_k]
+    return SearchResult(keys=[all_keys[i] for i in order], scores=[all_scores[i] for i in order],
+                        vectors=[all_vectors[i] for i in order])
+
+
+class LocalCoordinator:
+    """`CoordinatorHandler` over handlers in this process (one per GPU): md5 routing of put/delete/get
+    to the shard master (coordinator/handler.py:117-170), broadcast search + merge (:173-228)."""
+
+    def __init__(self, nodes: Dict[str, object], shard_count: Optional[int] = None):
+        self.nodes = dict(nodes)
+        self.node_ids = list(self.nodes)
+        # with SHARD_COUNT=4 and 8 nodes only 4 nodes would receive data: default to one shard per node
+        self.shard_count = shard_count or len(self.node_ids)
+        self.mapping = assign_shards_to_nodes(self.node_ids, self.shard_count)
+
+    def _master(self, key: str):
+        return self.nodes[self.mapping[get_shard_id(key, self.shard_count)]["master"]]
+
+    def put(self, data: VectorData) -> Response:
+        return self._master(data.key).put(data)
+
+    def delete(self, key: str) -> Response:
+        return self._master(key).delete(key)
+
+    def get(self, key: str) -> Response:
+        return self._master(key).get(key)
+
+    def search(self, req: SearchRequest) -> Response:
+        if not self.nodes:
+            return Response(success=False, message="无在线数据节点")               # :177-178
+        sub = SearchRequest(query_vector=req.query_vector, top_k=req.top_k)       # :186-189 (filter/threshold dropped)
+        results = []
+        for node_id in self.node_ids:                                              # :191
+            resp = self.nodes[node_id].search(sub)
+            results.append(resp.search_result if resp.success and resp.search_result else None)   # :198-199
+        merged = merge_search_results(results, req.top_k)
+        return Response(success=True, search_result=merged)
+
+
+class ShardedSearcher:
+    """One rank per GPU (torch.distributed): every rank searches its shard, the per-rank top-k lists are
+    all-gathered (NCCL over NVLink on GPUs; gloo in the CPU tests) and merged by (distance, id) -- the GPU form
+    of coordinator/handler.py:191-216.
+
+    `local_search(queries[nq, dim], k) -> (ids int64 [nq,k] global ids, -1 padded; dist float32 [nq,k])`
+    `merge(dist [G,nq,k], ids [G,nq,k], k) -> (dist [nq,k], ids [nq,k])`   (the CUDA merge kernel in production)
+    Tensors are torch tensors on the device of the process group's backend."""
+
+    def __init__(self, local_search: Callable, merge: Callable, group=None):
+        import torch.distributed as dist
+        self._dist = dist
+        self.local_search, self.merge, self.group = local_search, merge, group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def search(self, queries, k: int):
+        import torch
+        ids, dd = self.local_search(queries, k)
+        nq = ids.shape[0]
+        # concatenated along dim 0 (the layout both NCCL and gloo accept), viewed as [G, nq, k]
+        g_ids = torch.empty((self.world * nq,) + tuple(ids.shape[1:]), dtype=ids.dtype, device=ids.device)
+        g_dd = torch.empty((self.world * nq,) + tuple(dd.shape[1:]), dtype=dd.dtype, device=dd.device)
+        self._dist.all_gather_into_tensor(g_ids, ids.contiguous(), group=self.group)
+        self._dist.all_gather_into_tensor(g_dd, dd.contiguous(), group=self.group)
+        return self.merge(g_dd.view(self.world, nq, -1), g_ids.view(self.world, nq, -1), k)

