@@ -82,6 +82,18 @@ __device__ __forceinline__ int lane_of_value_index(int v) {
     return lane;
 }
 
+// lane-strided sum of squares in the canonical order (16-byte lane chunks, then butterfly)
+__device__ __forceinline__ float warp_sumsq_f32(const float* x, int dim) {
+    const int lane = lane_id();
+    float a = 0.0f;
+    for (int c = lane * 4; c < dim; c += 128) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (c + e < dim) a = fmaf(x[c + e], x[c + e], a);
+    }
+    return warp_sum_butterfly(a);
+}
+
 __device__ __forceinline__ int warp_sum_int(int v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

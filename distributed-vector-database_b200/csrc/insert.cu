@@ -10,18 +10,6 @@
 
 namespace vdbk {
 
-// lane-strided sum of squares in the canonical order (16-byte lane chunks, then butterfly)
-__device__ __forceinline__ float warp_sumsq_f32(const float* x, int dim) {
-    const int lane = lane_id();
-    float a = 0.0f;
-    for (int c = lane * 4; c < dim; c += 128) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-            if (c + e < dim) a = fmaf(x[c + e], x[c + e], a);
-    }
-    return warp_sum_butterfly(a);
-}
-
 __global__ void prepare_queries_kernel(const float* __restrict__ q, size_t nq, int dim, int ld, bool normalize,
                                        float* __restrict__ out, float* __restrict__ qn2) {
     const size_t w = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;

@@ -14,14 +14,19 @@ struct ScanParams {
     uint32_t n_rows;
     const uint32_t* labels;  // [n_rows] or null (label == row)
     const uint32_t* tomb;    // bitmap, 1 = deleted, or null
-    const float* q;          // [nq][ld] prepared queries (fp32, zero padded)
+    const float* q;          // [nq][ld] prepared queries (fp32, zero padded) -- or:
+    const float* q_raw;      // [nq][dim] raw queries, prepared inside the kernel (saves a launch)
+    int dim, normalize;
     int nq;                  // 1..8
     int k;
     int metric;              // 0 = squared L2 (direct form), 1 = 1 - dot
     int stages;              // filled by the launcher
+    int dbg;                 // experiments (VDB_SCAN_DBG): 1 = no FMA loop, 2 = no L2 policy hint, 4 = no select
     uint64_t* out_keys;      // [nq][grid][k]
 };
-cudaError_t launch_scan_topk(ScanParams p, bool f16, int num_sms, int* grid_out, cudaStream_t st);
+struct ScanPlan { int grid, ctas_per_sm, stages; size_t smem; };   // grid == 0: does not fit
+ScanPlan scan_plan(int nq, uint32_t ld, uint32_t row_bytes, int k, uint32_t n_rows, int num_sms);
+cudaError_t launch_scan_topk(ScanParams p, bool f16, const ScanPlan& pl, cudaStream_t st);
 int scan_max_k(int nq_t, int ld, uint32_t row_bytes);
 
 // ---- K5 merge (merge_topk.cu) -------------------------------------------------------------

@@ -40,30 +40,12 @@ __device__ __forceinline__ uint64_t merge_load(const MergeParams& p, size_t q, i
     return make_key(p.in_dist[off], (uint32_t)id);
 }
 
-__global__ void __launch_bounds__(MERGE_THREADS) merge_topk_kernel(const MergeParams p) {
-    __shared__ uint64_t buf[MERGE_BUF];
-    const size_t q = blockIdx.x;
-    const int total = p.n_in;
+// write K sorted keys from buf[0..) to the outputs of query q
+__device__ __forceinline__ void merge_emit(const MergeParams& p, size_t q, const uint64_t* buf, int n_sorted) {
     const int K = p.k_out;
-    int n = 2;
-    while (n < total && n < MERGE_BUF) n <<= 1;
-    while (n < 2 * K && n < MERGE_BUF) n <<= 1;   // room to keep K and still take new keys
-
-    int consumed = min(total, n);
-    for (int i = threadIdx.x; i < n; i += MERGE_THREADS) buf[i] = i < consumed ? merge_load(p, q, i) : KEY_SENTINEL;
-    __syncthreads();
-    bitonic_sort_smem(buf, n);
-    while (consumed < total) {
-        const int take = min(total - consumed, n - K);
-        for (int i = threadIdx.x; i < n - K; i += MERGE_THREADS)
-            buf[K + i] = i < take ? merge_load(p, q, consumed + i) : KEY_SENTINEL;
-        consumed += take;
-        __syncthreads();
-        bitonic_sort_smem(buf, n);
-    }
     int cnt = 0;
     for (int i = threadIdx.x; i < K; i += MERGE_THREADS) {
-        const uint64_t key = i < n ? buf[i] : KEY_SENTINEL;
+        const uint64_t key = i < n_sorted ? buf[i] : KEY_SENTINEL;
         const bool real = key != KEY_SENTINEL;
         cnt += real ? 1 : 0;
         if (p.out_keys) p.out_keys[q * K + i] = key;
@@ -81,10 +63,122 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_topk_kernel(const MergePa
     }
 }
 
+// streaming bitonic path: any input length, 2048-key window
+__device__ __forceinline__ void merge_stream(const MergeParams& p, size_t q, uint64_t* buf) {
+    const int total = p.n_in;
+    const int K = p.k_out;
+    int n = 2;
+    while (n < total && n < MERGE_BUF) n <<= 1;
+    while (n < 2 * K && n < MERGE_BUF) n <<= 1;   // room to keep K and still take new keys
+    int consumed = min(total, n);
+    for (int i = threadIdx.x; i < n; i += MERGE_THREADS) buf[i] = i < consumed ? merge_load(p, q, i) : KEY_SENTINEL;
+    __syncthreads();
+    bitonic_sort_smem(buf, n);
+    while (consumed < total) {
+        const int take = min(total - consumed, n - K);
+        for (int i = threadIdx.x; i < n - K; i += MERGE_THREADS)
+            buf[K + i] = i < take ? merge_load(p, q, consumed + i) : KEY_SENTINEL;
+        consumed += take;
+        __syncthreads();
+        bitonic_sort_smem(buf, n);
+    }
+    merge_emit(p, q, buf, n);
+}
+
+__global__ void __launch_bounds__(MERGE_THREADS) merge_topk_kernel(const MergeParams p) {
+    __shared__ uint64_t buf[MERGE_BUF];
+    merge_stream(p, blockIdx.x, buf);
+}
+
+// Long inputs (the 148 per-CTA lists of the scan kernel): radix select on the 32 distance bits finds the
+// k-th distance in 4 passes over the keys, only keys at or below it are sorted.  Falls back to the streaming
+// path when exact distance ties make more than MERGE_BUF keys qualify.
+__global__ void __launch_bounds__(MERGE_THREADS) merge_select_kernel(const MergeParams p) {
+    __shared__ uint64_t buf[MERGE_BUF];
+    __shared__ int hist[256];
+    __shared__ uint32_t s_prefix, s_rank;
+    __shared__ int s_valid, s_m;
+    const size_t q = blockIdx.x;
+    const int n = p.n_in, K = p.k_out;
+    if (threadIdx.x == 0) { s_valid = 0; s_m = 0; s_prefix = 0; s_rank = (uint32_t)K; }
+    __syncthreads();
+    int v = 0;
+    for (int i = threadIdx.x; i < n; i += MERGE_THREADS) v += merge_load(p, q, i) != KEY_SENTINEL;
+    v = warp_sum_int(v);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_valid, v);
+    __syncthreads();
+    uint32_t T = 0xFFFFFFFFu;          // keep everything valid
+    if (s_valid > K) {
+        uint32_t mask = 0;
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+            __syncthreads();
+            const uint32_t prefix = s_prefix;
+            for (int i = threadIdx.x; i < n; i += MERGE_THREADS) {
+                const uint64_t key = merge_load(p, q, i);
+                if (key != KEY_SENTINEL) {
+                    const uint32_t hi = (uint32_t)(key >> 32);
+                    if ((hi & mask) == prefix) atomicAdd(&hist[(hi >> shift) & 255], 1);
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                int local[8], sum = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { local[i] = hist[threadIdx.x * 8 + i]; sum += local[i]; }
+                int incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if ((int)threadIdx.x >= o) incl += t;
+                }
+                const int excl = incl - sum, rank = (int)s_rank;
+                if (rank > excl && rank <= incl) {
+                    int run = excl;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (rank > run && rank <= run + local[i]) {
+                            s_prefix = prefix | ((uint32_t)(threadIdx.x * 8 + i) << shift);
+                            s_rank = (uint32_t)(rank - run);
+                        }
+                        run += local[i];
+                    }
+                }
+            }
+            mask |= 0xFFu << shift;
+            __syncthreads();
+        }
+        T = s_prefix;
+    }
+    // gather keys whose distance bits are <= T
+    for (int i = threadIdx.x; i < n; i += MERGE_THREADS) {
+        const uint64_t key = merge_load(p, q, i);
+        if (key != KEY_SENTINEL && (uint32_t)(key >> 32) <= T) {
+            const int s = atomicAdd(&s_m, 1);
+            if (s < MERGE_BUF) buf[s] = key;
+        }
+    }
+    __syncthreads();
+    const int m = s_m;
+    if (m > MERGE_BUF) {               // a flood of exact ties: take the slow, always-correct road
+        __syncthreads();
+        merge_stream(p, q, buf);
+        return;
+    }
+    int np = 2;
+    while (np < m) np <<= 1;
+    for (int i = m + threadIdx.x; i < np; i += MERGE_THREADS) buf[i] = KEY_SENTINEL;
+    __syncthreads();
+    bitonic_sort_smem(buf, np);
+    merge_emit(p, q, buf, np);
+}
+
 cudaError_t launch_merge_topk(const MergeParams& p, cudaStream_t st) {
     if (p.nq == 0) return cudaSuccess;
     if (p.k_out < 1 || p.k_out > MERGE_BUF / 2) return cudaErrorInvalidValue;
-    merge_topk_kernel<<<(unsigned)p.nq, MERGE_THREADS, 0, st>>>(p);
+    if (p.n_in >= 512 && p.n_in >= 8 * p.k_out) merge_select_kernel<<<(unsigned)p.nq, MERGE_THREADS, 0, st>>>(p);
+    else merge_topk_kernel<<<(unsigned)p.nq, MERGE_THREADS, 0, st>>>(p);
     count_launch();
     return cudaGetLastError();
 }

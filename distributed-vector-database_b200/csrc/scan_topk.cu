@@ -3,13 +3,21 @@
 // Replaces hnswlib.Index.knn_query for 1..8 queries per pass (reference call site
 // src/datanode/handler.py:364).  Bandwidth-bound: every live row of the shard is read exactly
 // once per pass (algorithmic bytes = n_rows * row_bytes); the distance vector never exists in
-// memory.  One persistent CTA per SM:
+// memory.  Persistent CTAs, two per SM when two rings fit (scan_plan), 10 warps each:
 //   warp 8        producer: one 1-D bulk async copy (UBLKCP) of 16 contiguous rows per stage
 //                 into a ring of shared-memory stages, completion on an mbarrier
 //   warps 0..7    consumers: 2 rows each per stage, 128-bit LDS, fp32 FMA against the queries
-//                 (held in shared memory), canonical butterfly reduction, threshold test
-//                 against the CTA's current k-th key, rare warp-cooperative sorted insert.
+//                 (held in shared memory).  Per-lane partial sums of 32 (row, query) values are kept in
+//                 registers across stages and reduced together (canonical butterfly pairing, 31 shuffles),
+//                 so each lane ends with one distance: one threshold test + one ballot per 32 values.
+//                 Survivors are pushed (warp-aggregated atomicAdd) into a shared-memory candidate ring.
+//   warp 9        selector: the only writer of the CTA's sorted top-k lists; drains the ring 32 slots at a
+//                 time, pre-filters against the current k-th key, inserts.  Consumers never take a lock or
+//                 wait for an insert (measured: inserts under a lock on the consumer path cost 50 us of a
+//                 335 us scan; with the selector the scan runs at the speed of the bare copy ring).
 // Each CTA leaves a sorted list of k keys per query; merge_topk.cu reduces grid lists to one.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -18,7 +26,8 @@ namespace vdbk {
 constexpr int SCAN_WARPS = 8;
 constexpr int SCAN_R = 2;                                  // rows per consumer warp per stage
 constexpr int SCAN_STAGE_ROWS = SCAN_WARPS * SCAN_R;       // 16
-constexpr int SCAN_THREADS = (SCAN_WARPS + 1) * 32;
+constexpr int SCAN_THREADS = (SCAN_WARPS + 2) * 32;        // + producer warp + selector warp
+constexpr int SCAN_RING = 512;                             // candidate ring slots (power of two)
 
 template <typename T> struct Elem;
 template <> struct Elem<float> {
@@ -41,40 +50,43 @@ template <> struct Elem<__half> {
     }
 };
 
-// Sorted insert of `key` into list[0..k) (ascending), executed by a whole converged warp.
-__device__ __forceinline__ void list_insert(volatile uint64_t* list, int k, uint64_t key, int* lock) {
+// Sorted insert of `key` into list[0..k) (ascending) by the selector warp (the only writer).
+// Consumers concurrently read the high word of list[k-1] as their threshold: during the shift it only
+// ever moves from the old tail to a smaller-or-equal value, so a racing read is a valid (stale) bound.
+__device__ __forceinline__ void list_insert(volatile uint64_t* list, int k, uint64_t key) {
     const int lane = lane_id();
-    if (lane == 0) {
-        while (atomicCAS(lock, 0, 1) != 0) {
-        }
+    if (key >= list[k - 1]) return;
+    int cnt = 0;
+    for (int i = lane; i < k; i += 32) cnt += (list[i] < key) ? 1 : 0;
+    const int pos = warp_sum_int(cnt);
+    for (int hi = k - 2; hi >= pos; hi -= 32) {
+        const int i = hi - lane;
+        uint64_t v = 0;
+        if (i >= pos) v = list[i];
+        __syncwarp();
+        if (i >= pos) list[i + 1] = v;
+        __syncwarp();
     }
+    if (lane == 0) list[pos] = key;
     __syncwarp();
-    __threadfence_block();
-    if (key < list[k - 1]) {
-        int cnt = 0;
-        for (int i = lane; i < k; i += 32) cnt += (list[i] < key) ? 1 : 0;
-        const int pos = warp_sum_int(cnt);
-        for (int hi = k - 2; hi >= pos; hi -= 32) {
-            const int i = hi - lane;
-            uint64_t v = 0;
-            if (i >= pos) v = list[i];
-            __syncwarp();
-            if (i >= pos) list[i + 1] = v;
-            __syncwarp();
-        }
-        if (lane == 0) list[pos] = key;
-    }
-    __syncwarp();
-    if (lane == 0) {
-        __threadfence_block();
-        atomicExch(lock, 0);
-    }
 }
 
+__device__ __forceinline__ void named_barrier_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+struct ScanCtl {            // shared-memory control block of the candidate ring
+    uint32_t tail;          // slots reserved by consumers (monotonic)
+    uint32_t head;          // slots retired by the selector (monotonic)
+    uint32_t done;          // consumer warps that have finished
+    uint32_t pad;
+};
+
 template <typename T, int NQ>
-__global__ void __launch_bounds__(SCAN_THREADS, 1) scan_topk_kernel(const ScanParams p) {
+__global__ void __launch_bounds__(SCAN_THREADS, 2) scan_topk_kernel(const ScanParams p) {
     constexpr int PER16 = Elem<T>::PER16;
-    constexpr int V = SCAN_R * NQ;
+    constexpr int VS = SCAN_R * NQ;   // (row, query) values a warp produces per stage
+    constexpr int G = 32 / VS;        // stages whose partial sums are reduced together
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t row_bytes = p.row_bytes;
     const uint32_t stage_bytes = row_bytes * SCAN_STAGE_ROWS;
@@ -82,20 +94,19 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_topk_kernel(const ScanPa
     uint8_t* stage_base = smem;
     float* qs = reinterpret_cast<float*>(smem + (size_t)stages * stage_bytes);          // [NQ][ld]
     uint64_t* lists = reinterpret_cast<uint64_t*>(qs + (size_t)NQ * p.ld);                // [NQ][k]
-    uint64_t* full = lists + (size_t)NQ * p.k;
+    uint64_t* ring = lists + (size_t)NQ * p.k;                                            // [SCAN_RING]
+    uint64_t* full = ring + SCAN_RING;
     uint64_t* empty = full + stages;
-    int* locks = reinterpret_cast<int*>(empty + stages);
+    ScanCtl* ctl = reinterpret_cast<ScanCtl*>(empty + stages);
+    uint8_t* ring_q = reinterpret_cast<uint8_t*>(ctl + 1);                                // [SCAN_RING]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int k = p.k;
 
-    for (int i = threadIdx.x; i < NQ * (int)p.ld; i += SCAN_THREADS) {
-        const int qi = i / (int)p.ld, c = i - qi * (int)p.ld;
-        qs[i] = (qi < p.nq) ? p.q[(size_t)qi * p.ld + c] : 0.0f;
-    }
     for (int i = threadIdx.x; i < NQ * k; i += SCAN_THREADS) lists[i] = KEY_SENTINEL;
-    if (threadIdx.x < NQ) locks[threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < SCAN_RING; i += SCAN_THREADS) ring[i] = KEY_SENTINEL;
     if (threadIdx.x == 0) {
+        ctl->tail = 0; ctl->head = 0; ctl->done = 0;
         for (int s = 0; s < stages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], SCAN_WARPS);
@@ -107,95 +118,183 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_topk_kernel(const ScanPa
     const uint32_t nchunks = (p.n_rows + SCAN_STAGE_ROWS - 1) / SCAN_STAGE_ROWS;
 
     if (warp == SCAN_WARPS) {
-        // ---------------- producer ----------------
+        // ---------------- producer: starts streaming while the consumers fetch the queries ----------------
         if (lane == 0) {
             const uint64_t policy = l2_policy_evict_first();
-            uint32_t it = 0;
-            for (uint32_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, ++it) {
-                const int s = it % stages;
-                const uint32_t ph = (it / stages) & 1;
+            int s = 0;
+            uint32_t ph = 0;
+            for (uint32_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
                 mbar_wait(&empty[s], ph ^ 1);
                 const uint32_t r0 = chunk * SCAN_STAGE_ROWS;
                 const uint32_t nr = min((uint32_t)SCAN_STAGE_ROWS, p.n_rows - r0);
                 const uint32_t bytes = nr * row_bytes;
                 mbar_arrive_expect_tx(&full[s], bytes);
-                bulk_copy_g2s_stream(stage_base + (size_t)s * stage_bytes,
-                                     reinterpret_cast<const uint8_t*>(p.rows) + (size_t)r0 * row_bytes, bytes,
-                                     &full[s], policy);
+                if (p.dbg & 2)
+                    bulk_copy_g2s(stage_base + (size_t)s * stage_bytes,
+                                  reinterpret_cast<const uint8_t*>(p.rows) + (size_t)r0 * row_bytes, bytes, &full[s]);
+                else
+                    bulk_copy_g2s_stream(stage_base + (size_t)s * stage_bytes,
+                                         reinterpret_cast<const uint8_t*>(p.rows) + (size_t)r0 * row_bytes, bytes,
+                                         &full[s], policy);
+                if (++s == stages) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == SCAN_WARPS + 1) {
+        // ---------------- selector: drains the candidate ring into the sorted lists ----------------
+        volatile uint64_t* vring = ring;
+        volatile uint64_t* vlists = lists;
+        volatile ScanCtl* vctl = ctl;
+        uint32_t head = 0;
+        for (;;) {
+            const uint32_t slot = (head + lane) & (SCAN_RING - 1);
+            const uint64_t key = vring[slot];
+            const uint32_t ready = __ballot_sync(0xffffffffu, key != KEY_SENTINEL);
+            const int n = (ready == 0xffffffffu) ? 32 : __ffs(~ready) - 1;   // leading run of written slots
+            if (n == 0) {
+                // all pushes of a finished warp are visible before its `done` increment
+                if (vctl->done == SCAN_WARPS && head == vctl->tail) break;
+                __nanosleep(100);
+                continue;
+            }
+            __threadfence_block();
+            const int q = lane < n ? reinterpret_cast<volatile uint8_t*>(ring_q)[slot] : 0;
+            if (lane < n) vring[slot] = KEY_SENTINEL;
+            __syncwarp();
+            head += n;
+            if (lane == 0) {
+                __threadfence_block();
+                vctl->head = head;
+            }
+            const bool cand = lane < n && key < vlists[(size_t)q * k + (k - 1)];
+            uint32_t cm = __ballot_sync(0xffffffffu, cand);
+            while (cm) {
+                const int src = __ffs(cm) - 1;
+                cm &= cm - 1;
+                const uint64_t kk = __shfl_sync(0xffffffffu, key, src);
+                const int qq = __shfl_sync(0xffffffffu, q, src);
+                list_insert(vlists + (size_t)qq * k, k, kk);
             }
         }
     } else {
         // ---------------- consumers ----------------
+        for (int i = threadIdx.x; i < NQ * (int)p.ld; i += SCAN_WARPS * 32) {
+            const int qi = i / (int)p.ld, c = i - qi * (int)p.ld;
+            float v = 0.0f;
+            if (qi < p.nq) {
+                if (p.q_raw) v = c < p.dim ? p.q_raw[(size_t)qi * p.dim + c] : 0.0f;
+                else v = p.q[(size_t)qi * p.ld + c];
+            }
+            qs[i] = v;
+        }
+        if (p.q_raw && p.normalize) {
+            // same arithmetic as prepare_queries_kernel (insert.cu), so both paths see identical queries
+            named_barrier_sync(1, SCAN_WARPS * 32);
+            for (int qi = warp; qi < p.nq; qi += SCAN_WARPS) {
+                float* qv = qs + (size_t)qi * p.ld;
+                const float ssq = warp_sumsq_f32(qv, p.dim);
+                const float scale = 1.0f / (sqrtf(ssq) + 1e-30f);
+                for (int c = lane; c < p.dim; c += 32) qv[c] = qv[c] * scale;
+            }
+        }
+        named_barrier_sync(1, SCAN_WARPS * 32);
+
+        // Per-lane partial sums of G consecutive stages (32 (row, query) values) stay in registers and are
+        // reduced together: 31 shuffles + one threshold test + one ballot per 32 values instead of per stage.
         const int nld16 = row_bytes / 512;  // 16-byte lane loads per row
-        uint32_t it = 0;
-        for (uint32_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, ++it) {
-            const int s = it % stages;
-            const uint32_t ph = (it / stages) & 1;
-            mbar_wait(&full[s], ph);
-            const uint32_t row0 = chunk * SCAN_STAGE_ROWS + warp * SCAN_R;
-            const uint8_t* sbase = stage_base + (size_t)s * stage_bytes + (size_t)(warp * SCAN_R) * row_bytes;
-
-            float acc[V];
+        const uint32_t my_iters = nchunks > blockIdx.x ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        volatile ScanCtl* vctl = ctl;
+        int s = 0;
+        uint32_t ph = 0;
+        for (uint32_t it0 = 0; it0 < my_iters; it0 += G) {
+            float acc[32];
 #pragma unroll
-            for (int i = 0; i < V; ++i) acc[i] = 0.0f;
-
-            if (row0 < p.n_rows) {
+            for (int i = 0; i < 32; ++i) acc[i] = 0.0f;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                if (it0 + g < my_iters) {   // warp-uniform
+                    mbar_wait(&full[s], ph);
+                    const uint8_t* sbase = stage_base + (size_t)s * stage_bytes + (size_t)(warp * SCAN_R) * row_bytes;
+                    if (!(p.dbg & 1)) {
 #pragma unroll 2
-                for (int c = 0; c < nld16; ++c) {
-                    float dv[SCAN_R][PER16];
+                        for (int c = 0; c < nld16; ++c) {
+                            float dv[SCAN_R][PER16];
 #pragma unroll
-                    for (int r = 0; r < SCAN_R; ++r)
-                        Elem<T>::load(sbase + (size_t)r * row_bytes + (size_t)(c * 32 + lane) * 16, dv[r]);
+                            for (int r = 0; r < SCAN_R; ++r)
+                                Elem<T>::load(sbase + (size_t)r * row_bytes + (size_t)(c * 32 + lane) * 16, dv[r]);
 #pragma unroll
-                    for (int qi = 0; qi < NQ; ++qi) {
-                        float qv[PER16];
-                        const float* qp = qs + (size_t)qi * p.ld + (size_t)(c * 32 + lane) * PER16;
+                            for (int qi = 0; qi < NQ; ++qi) {
+                                float qv[PER16];
+                                const float* qp = qs + (size_t)qi * p.ld + (size_t)(c * 32 + lane) * PER16;
 #pragma unroll
-                        for (int e = 0; e < PER16; e += 4) {
-                            float4 t = *reinterpret_cast<const float4*>(qp + e);
-                            qv[e] = t.x; qv[e + 1] = t.y; qv[e + 2] = t.z; qv[e + 3] = t.w;
-                        }
-#pragma unroll
-                        for (int r = 0; r < SCAN_R; ++r) {
-                            float a = acc[r * NQ + qi];
-                            if (p.metric == 0) {
-#pragma unroll
-                                for (int e = 0; e < PER16; ++e) {
-                                    const float t = dv[r][e] - qv[e];
-                                    a = fmaf(t, t, a);
+                                for (int e = 0; e < PER16; e += 4) {
+                                    float4 t = *reinterpret_cast<const float4*>(qp + e);
+                                    qv[e] = t.x; qv[e + 1] = t.y; qv[e + 2] = t.z; qv[e + 3] = t.w;
                                 }
-                            } else {
 #pragma unroll
-                                for (int e = 0; e < PER16; ++e) a = fmaf(dv[r][e], qv[e], a);
+                                for (int r = 0; r < SCAN_R; ++r) {
+                                    float a = acc[g * VS + r * NQ + qi];
+                                    if (p.metric == 0) {
+#pragma unroll
+                                        for (int e = 0; e < PER16; ++e) {
+                                            const float t = dv[r][e] - qv[e];
+                                            a = fmaf(t, t, a);
+                                        }
+                                    } else {
+#pragma unroll
+                                        for (int e = 0; e < PER16; ++e) a = fmaf(dv[r][e], qv[e], a);
+                                    }
+                                    acc[g * VS + r * NQ + qi] = a;
+                                }
                             }
-                            acc[r * NQ + qi] = a;
                         }
                     }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[s]);   // data is in registers: free the slot
+                    if (++s == stages) { s = 0; ph ^= 1; }
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);   // data is in registers: free the slot
-
-            if (row0 >= p.n_rows) continue;
-            warp_sum_multi<V>(acc);
-            const int vi = value_index_of_lane<V>(lane);
-            const int r = vi / NQ, qi = vi - r * NQ;
-            const uint32_t row = row0 + r;
-            float dist = (p.metric == 0) ? acc[0] : 1.0f - acc[0];
-            const bool holder = (lane == lane_of_value_index<V>(vi)) && row < p.n_rows && qi < p.nq;
-            const uint32_t tail_hi = (uint32_t)(((volatile uint64_t*)lists)[(size_t)qi * k + (k - 1)] >> 32);
-            const bool pass = holder && float_to_ordered(dist) <= tail_hi;
-            uint32_t m = __ballot_sync(0xffffffffu, pass);
-            while (m) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                const float d = __shfl_sync(0xffffffffu, dist, src);
-                const uint32_t rw = __shfl_sync(0xffffffffu, row, src);
-                const int q = __shfl_sync(0xffffffffu, qi, src);
-                if (p.tomb && ((p.tomb[rw >> 5] >> (rw & 31)) & 1u)) continue;
-                const uint32_t label = p.labels ? p.labels[rw] : rw;
-                list_insert(lists + (size_t)q * k, k, make_key(d, label), &locks[q]);
+            if (p.dbg & 4) {   // experiment: no reduction / selection
+                if (acc[0] == 123.456f) lists[0] = 0;
+                continue;
             }
+            warp_sum_multi<32>(acc);        // lane L now holds the total of value index vi
+            const int vi = value_index_of_lane<32>(lane);
+            const int g = vi / VS, rem = vi - g * VS;
+            const int r = rem / NQ, qi = rem - r * NQ;
+            const uint32_t it = it0 + g;
+            const uint32_t row = (blockIdx.x + it * gridDim.x) * SCAN_STAGE_ROWS + warp * SCAN_R + r;
+            const float dist = (p.metric == 0) ? acc[0] : 1.0f - acc[0];
+            const bool valid = it < my_iters && row < p.n_rows && qi < p.nq;
+            // high word (distance bits) of the list tail = current threshold of query qi
+            const uint32_t tail_hi = reinterpret_cast<volatile uint32_t*>(lists + (size_t)qi * k + (k - 1))[1];
+            bool pass = valid && float_to_ordered(dist) <= tail_hi;
+            uint32_t label = row;
+            if (pass) {
+                if (p.tomb && ((p.tomb[row >> 5] >> (row & 31)) & 1u)) pass = false;
+                else if (p.labels) label = p.labels[row];
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, pass);
+            if (m) {
+                // warp-aggregated push into the candidate ring; the selector warp owns the lists
+                const int n = __popc(m);
+                const int leader = __ffs(m) - 1;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(&ctl->tail, (uint32_t)n);
+                base = __shfl_sync(0xffffffffu, base, leader);
+                while ((int)(base + n - vctl->head) > SCAN_RING) {
+                }
+                if (pass) {
+                    const uint32_t slot = (base + __popc(m & ((1u << lane) - 1))) & (SCAN_RING - 1);
+                    ring_q[slot] = (uint8_t)qi;
+                    __threadfence_block();
+                    reinterpret_cast<volatile uint64_t*>(ring)[slot] = make_key(dist, label);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            atomicAdd(&ctl->done, 1u);
         }
     }
     __syncthreads();
@@ -206,7 +305,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_topk_kernel(const ScanPa
 }
 
 static size_t scan_fixed_smem(int nq_t, int ld, int k, int stages) {
-    return (size_t)nq_t * ld * 4 + (size_t)nq_t * k * 8 + (size_t)stages * 16 + 64 + 128;
+    return (size_t)nq_t * ld * 4 + (size_t)nq_t * k * 8 + (size_t)SCAN_RING * 9 + (size_t)stages * 16 + 64 + 128;
 }
 
 template <typename T, int NQ>
@@ -233,20 +332,47 @@ int scan_max_k(int nq_t, int ld, uint32_t row_bytes) {
     return (int)((budget - min_stage - fixed0) / ((size_t)nq_t * 8));
 }
 
-// Launch K1.  p.nq in 1..8.  Returns the grid used through *grid_out (lists per query).
-cudaError_t launch_scan_topk(ScanParams p, bool f16, int num_sms, int* grid_out, cudaStream_t st) {
+// Launch shape.  Two CTAs per SM whenever two rings fit (measured on B200, 1M x 512 fp32, one query:
+// 1 CTA x 6 stages 360 us, 2 CTAs x 2 stages 335 us, 3 x 2 339 us): a second CTA's consumers fill the
+// bubbles the first one leaves at the reductions.  The rings together keep >= 128 KB of bulk copies in flight
+// per SM when shared memory allows (64 KB/SM already reaches ~7.2 TB/s with bare copies).
+ScanPlan scan_plan(int nq, uint32_t ld, uint32_t row_bytes, int k, uint32_t n_rows, int num_sms) {
+    ScanPlan pl{};
+    const int nq_t = nq <= 1 ? 1 : nq <= 2 ? 2 : nq <= 4 ? 4 : 8;
+    const size_t stage_bytes = (size_t)row_bytes * SCAN_STAGE_ROWS;
+    const size_t sm_budget = 227 * 1024;
+    int ctas = 2, stages = 0;
+    if (const char* e = getenv("VDB_SCAN_CTAS")) ctas = atoi(e);
+    if (ctas < 1) ctas = 1;
+    for (; ctas >= 1; --ctas) {
+        const size_t budget = ctas == 1 ? sm_budget : (228 * 1024) / ctas - 1024;   // 1 KB reserved per CTA
+        int want = (int)((128 * 1024 / ctas + stage_bytes - 1) / stage_bytes);
+        if (want < 2) want = 2;
+        if (want > 8) want = 8;
+        if (const char* e = getenv("VDB_SCAN_STAGES")) want = atoi(e);
+        stages = want;
+        while (stages > 2 && stages * stage_bytes + scan_fixed_smem(nq_t, ld, k, stages) > budget) --stages;
+        if (stages * stage_bytes + scan_fixed_smem(nq_t, ld, k, stages) <= budget) break;
+        stages = 0;
+    }
+    if (stages == 0) return pl;     // does not fit at all (pl.grid == 0)
+    pl.ctas_per_sm = ctas;
+    pl.stages = stages;
+    pl.smem = stages * stage_bytes + scan_fixed_smem(nq_t, ld, k, stages);
+    const uint32_t nchunks = (n_rows + SCAN_STAGE_ROWS - 1) / SCAN_STAGE_ROWS;
+    pl.grid = (int)min((uint32_t)(num_sms * ctas), nchunks);
+    if (pl.grid < 1) pl.grid = 1;
+    return pl;
+}
+
+// Launch K1 with a plan made for >= p.nq queries.  p.nq in 1..8; pl.grid lists of k keys per query come back.
+cudaError_t launch_scan_topk(ScanParams p, bool f16, const ScanPlan& pl, cudaStream_t st) {
     const int nq_t = p.nq <= 1 ? 1 : p.nq <= 2 ? 2 : p.nq <= 4 ? 4 : 8;
-    const uint32_t stage_bytes = p.row_bytes * SCAN_STAGE_ROWS;
-    const size_t budget = 227 * 1024;
-    int stages = 8;
-    while (stages > 2 && (size_t)stages * stage_bytes + scan_fixed_smem(nq_t, p.ld, p.k, stages) > budget) --stages;
-    const size_t smem = (size_t)stages * stage_bytes + scan_fixed_smem(nq_t, p.ld, p.k, stages);
-    if (smem > budget) return cudaErrorInvalidConfiguration;
-    p.stages = stages;
-    const uint32_t nchunks = (p.n_rows + SCAN_STAGE_ROWS - 1) / SCAN_STAGE_ROWS;
-    int grid = (int)min((uint32_t)num_sms, nchunks);
-    if (grid < 1) grid = 1;
-    *grid_out = grid;
+    if (pl.grid == 0) return cudaErrorInvalidConfiguration;
+    if (const char* e = getenv("VDB_SCAN_DBG")) p.dbg = atoi(e);
+    p.stages = pl.stages;
+    const size_t smem = pl.smem;
+    const int grid = pl.grid;
 #define VDB_SCAN_CASE(NQV)                                                        \
     case NQV:                                                                     \
         return f16 ? launch_t<__half, NQV>(p, grid, smem, st) : launch_t<float, NQV>(p, grid, smem, st);

@@ -249,7 +249,7 @@ static void prof_end_cb(void* ctx, cudaStream_t) { static_cast<ProfScope*>(ctx)-
 
 // Exact scan (K1 + K5) of nq PREPARED queries [nq][ld]; groups of up to 8 queries per pass.
 int scan_prepared(vdb* db, Workspace* ws, const float* d_qp, size_t nq, int k, int64_t* d_ids, float* d_dist,
-                  int* d_cnt, cudaStream_t st, size_t n) {
+                  int* d_cnt, cudaStream_t st, size_t n, bool raw = false) {
     const bool f16 = db->dtype == VDB_F16;
     ScanParams sp{};
     sp.rows = db->rows;
@@ -260,19 +260,25 @@ int scan_prepared(vdb* db, Workspace* ws, const float* d_qp, size_t nq, int k, i
     sp.tomb = db->any_dead ? db->tomb : nullptr;
     sp.k = k;
     sp.metric = db->metric == VDB_L2 ? 0 : 1;
-    const uint32_t nchunks = (uint32_t)((n + 15) / 16);
-    const int grid = (int)std::min<uint32_t>((uint32_t)db->num_sms, nchunks);
+    // every pass of this call uses the launch shape of the widest pass (nq_t = min(nq, 8) rounded up)
+    const ScanPlan pl = scan_plan((int)std::min<size_t>(8, nq), (uint32_t)db->ld, sp.row_bytes, k, (uint32_t)n, db->num_sms);
+    if (pl.grid == 0) return fail(VDB_EINVAL, "k too large for the scan kernel at this dimension");
+    const int grid = pl.grid;
     CU_TRY(grow(ws->d_keys, ws->keys_cap, nq * (size_t)grid * k));
     for (size_t g = 0; g < nq; g += 8) {
         sp.nq = (int)std::min<size_t>(8, nq - g);
-        sp.q = d_qp + g * (size_t)db->ld;
+        if (raw) {   // queries as the caller gave them: normalised / padded inside the kernel
+            sp.q_raw = d_qp + g * (size_t)db->dim;
+            sp.dim = db->dim;
+            sp.normalize = db->metric == VDB_COSINE ? 1 : 0;
+        } else {
+            sp.q = d_qp + g * (size_t)db->ld;
+        }
         sp.out_keys = ws->d_keys + g * (size_t)grid * k;
-        int grid_used = 0;
         {
             ProfScope prof(db, st);
-            CU_TRY(launch_scan_topk(sp, f16, db->num_sms, &grid_used, st));
+            CU_TRY(launch_scan_topk(sp, f16, pl, st));
         }
-        if (grid_used != grid) return fail(VDB_ECUDA, "internal: scan grid mismatch");
         db->stat_scan_passes.fetch_add(1);
     }
     MergeParams mp{};
@@ -304,10 +310,6 @@ int search_core(vdb* db, Workspace* ws, const float* d_q_raw, size_t nq, int k, 
         CU_TRY(launch_merge_topk(mp, st));
         return VDB_OK;
     }
-    CU_TRY(grow(ws->d_q, ws->q_cap, nq * (size_t)db->ld));
-    CU_TRY(grow(ws->d_qn2, ws->qn2_cap, nq));
-    CU_TRY(launch_prepare_queries(d_q_raw, nq, db->dim, db->ld, db->metric == VDB_COSINE, ws->d_q, ws->d_qn2, st));
-
     const long path = db->opt_path.load();
     bool tensor = false;
     if (path == 2) tensor = true;
@@ -316,6 +318,11 @@ int search_core(vdb* db, Workspace* ws, const float* d_q_raw, size_t nq, int k, 
         if (path == 2) return fail(VDB_EINVAL, "tensor path forced but unsupported for this shape/k");
         tensor = false;
     }
+    if (!tensor) return scan_prepared(db, ws, d_q_raw, nq, k, d_ids, d_dist, d_cnt, st, n, /*raw=*/true);
+
+    CU_TRY(grow(ws->d_q, ws->q_cap, nq * (size_t)db->ld));
+    CU_TRY(grow(ws->d_qn2, ws->qn2_cap, nq));
+    CU_TRY(launch_prepare_queries(d_q_raw, nq, db->dim, db->ld, db->metric == VDB_COSINE, ws->d_q, ws->d_qn2, st));
     if (tensor) {
         GemmSearchArgs a{};
         a.rows = db->rows; a.ld = db->ld; a.dim = db->dim; a.f16 = f16; a.n_rows = (uint32_t)n;
@@ -359,7 +366,7 @@ int search_core(vdb* db, Workspace* ws, const float* d_q_raw, size_t nq, int k, 
         return VDB_OK;
     }
 
-    return scan_prepared(db, ws, ws->d_q, nq, k, d_ids, d_dist, d_cnt, st, n);
+    return fail(VDB_ECUDA, "internal: unreachable search path");
 }
 
 int check_k(const vdb* db, int k, size_t nq) {
