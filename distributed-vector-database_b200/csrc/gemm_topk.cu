@@ -83,7 +83,7 @@ struct GemmParams {
     int bits;                // tile order = bit reversal over `bits` bits
     int pos_begin, pos_end;  // this level's positions in that order
     int dense;               // level 0: keep every score
-    int dbg;                 // experiments only: 2 = epilogue releases TMEM at once
+    int dbg;                 // experiments only: 2 = epilogue releases TMEM at once, 8 = TMEM reads but no filtering
     const float* sqnorm;     // [n_rows] (L2 only)
     const float* thr;        // [nq] threshold of this level (approximate distance); unused when dense
     uint64_t* buf;           // [nq][cap] candidate keys (approximate distance bits << 32 | row)
@@ -110,7 +110,7 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t ran
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // 2-D tensor copy into THIS CTA's shared memory; completion bytes are counted on the mbarrier at
 // shared::cluster address `bar_cluster` (the pair leader's barrier: its MMA consumes both halves)
@@ -374,7 +374,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int ew = et >> 5;                            // == warp % 4 : TMEM lane quadrant
         const uint32_t my_ring_s = smem_u32(ring_all + (size_t)et * GT_RING_STRIDE);
         volatile uint32_t* my_tail = &ctl->tail[et];
-        uint32_t head = 0, pub = 0;
+        uint32_t head = 0, slot = 0;      // keys appended so far; slot == head % GT_RING
         uint32_t tcount = 0;
         for (int item = pair; item < p.n_items; item += num_pairs) {
             const ItemRange ir = item_range(p, item);
@@ -390,6 +390,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 __threadfence_block();
                 if (q_ok) thr = p.thr[q];
             }
+            const float nthr = -thr;
             uint64_t* dense_dst = p.buf + (size_t)(q_ok ? q : 0) * p.cap;
             float n_next0 = 0.0f, n_next1 = 0.0f;
             bool first_tile = true;
@@ -456,38 +457,50 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[acc]), 0));
                 } else {
-                    // TMEM reads are double-buffered: chunk c+1 is in flight while chunk c is filtered
+                    // TMEM reads are double-buffered: chunk c+1 is in flight while chunk c is filtered.
+                    // Survivors are rare (about 1 score in 3000), so the common case of a chunk of 32 scores is a
+                    // min/max tree and ONE branch.  About a third of the warp-chunks hold a survivor in some lane:
+                    // that path walks the 8 group extrema of the tree and tests single scores only inside a
+                    // group that has one.
                     auto filter_chunk = [&](const uint32_t (&v)[32], int c) {
-                        float a[32];
+                        if (p.dbg == 8) {
+                            if (v[0] == 0x12345678u && v[31] == 0x9abcdef0u) ++head;
+                            return;
+                        }
+                        // s[j] = -(approximate distance): a row passes iff s[j] > nthr  (exactly d < thr)
+                        float s[32], g[8];
                         if constexpr (L2) {
                             float nv[32];
                             lds_f32x32(ns_s + c * 128, nv);
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) a[j] = fmaf(-2.0f, __uint_as_float(v[j]), nv[j]);
+                            for (int j = 0; j < 32; ++j) s[j] = fmaf(2.0f, __uint_as_float(v[j]), -nv[j]);
                         } else {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) a[j] = -__uint_as_float(v[j]);
+                            for (int j = 0; j < 32; ++j) s[j] = __uint_as_float(v[j]);
                         }
-                        // a chunk may append up to 32 keys: wait (rare) until the movers have left that much room
-                        while (head - *my_tail > (uint32_t)(GT_RING - 32)) __nanosleep(32);
 #pragma unroll
-                        for (int g = 0; g < 8; ++g) {   // one test per 4 scores; survivors are rare
-                            const float m4 = fminf(fminf(a[4 * g], a[4 * g + 1]), fminf(a[4 * g + 2], a[4 * g + 3]));
-                            if (m4 < thr) {
+                        for (int gi = 0; gi < 8; ++gi)
+                            g[gi] = fmaxf(fmaxf(s[4 * gi], s[4 * gi + 1]), fmaxf(s[4 * gi + 2], s[4 * gi + 3]));
+                        const float m = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])),
+                                              fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
+                        if (m > nthr) {
+                            // this chunk may append up to 32 keys: wait (rare) until the movers have left that much room
+                            while (head - *my_tail > (uint32_t)(GT_RING - 32)) __nanosleep(32);
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    if (a[4 * g + e] < thr) {
-                                        st_shared_u64(my_ring_s + (head % GT_RING) * 8,
-                                                      make_key(a[4 * g + e], row0 + c * 32 + 4 * g + e));
-                                        ++head;
+                            for (int gi = 0; gi < 8; ++gi) {
+                                if (g[gi] > nthr) {
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        if (s[4 * gi + e] > nthr) {
+                                            st_shared_u64(my_ring_s + slot * 8, make_key(-s[4 * gi + e], row0 + c * 32 + 4 * gi + e));
+                                            ++head;
+                                            if (++slot == GT_RING) slot = 0;
+                                        }
                                     }
                                 }
                             }
-                        }
-                        if (head != pub) {
                             __threadfence_block();
                             ctl->head_pub[et] = head;
-                            pub = head;
                         }
                     };
                     uint32_t v0[32], v1[32];
