@@ -375,6 +375,8 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const uint32_t my_ring_s = smem_u32(ring_all + (size_t)et * GT_RING_STRIDE);
         volatile uint32_t* my_tail = &ctl->tail[et];
         uint32_t head = 0, slot = 0;      // keys appended so far; slot == head % GT_RING
+        uint32_t tail_seen = 0;           // last value read from the movers' tail counter
+        bool dirty = false;               // keys appended since head was last published
         uint32_t tcount = 0;
         for (int item = pair; item < p.n_items; item += num_pairs) {
             const ItemRange ir = item_range(p, item);
@@ -484,8 +486,12 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         const float m = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])),
                                               fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
                         if (m > nthr) {
-                            // this chunk may append up to 32 keys: wait (rare) until the movers have left that much room
-                            while (head - *my_tail > (uint32_t)(GT_RING - 32)) __nanosleep(32);
+                            // this chunk may append up to 32 keys: make sure the movers have left that much room
+                            // (tail_seen is a stale copy: the ring can only be emptier than it says)
+                            if (head - tail_seen > (uint32_t)(GT_RING - 32)) {
+                                if (dirty) { __threadfence_block(); ctl->head_pub[et] = head; dirty = false; }
+                                while (head - (tail_seen = *my_tail) > (uint32_t)(GT_RING - 32)) __nanosleep(32);
+                            }
 #pragma unroll
                             for (int gi = 0; gi < 8; ++gi) {
                                 if (g[gi] > nthr) {
@@ -499,8 +505,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                                     }
                                 }
                             }
-                            __threadfence_block();
-                            ctl->head_pub[et] = head;
+                            dirty = true;
                         }
                     };
                     uint32_t v0[32], v1[32];
@@ -521,6 +526,11 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         }
                         filter_chunk(v1, c + 1);
                         tmem_ld_wait();
+                    }
+                    if (dirty) {    // publish this tile's keys to the movers (once per tile, not per chunk)
+                        __threadfence_block();
+                        ctl->head_pub[et] = head;
+                        dirty = false;
                     }
                 }
                 ++tcount;
@@ -671,6 +681,8 @@ struct RerankParams {
     const unsigned int* max_sqnorm_bits;
     int k, metric;            // metric 0 = L2 (approx value = ||d||^2 - 2 q.d), 1 = ip/cos (approx value = -q.d)
     float eps_rel;            // bound on |approx dot - exact dot| / (||q|| ||d||)
+    float eps_abs;            // + eps_abs * (||q|| + ||d||max): fp16 subnormal rounding of single elements
+    int f16_range;            // operands were rounded to fp16: norms beyond its range void the certificate
     int64_t* out_ids; float* out_dist; int* out_counts;
     int* flags;               // [nq] 1 = certificate failed
     int* n_flagged;
@@ -757,7 +769,7 @@ __global__ void __launch_bounds__(256) rerank_kernel(const RerankParams p) {
         if (a_tau < __int_as_float(0x7f800000)) {   // candidate list full: rows outside it exist, prove they cannot matter
             const float qn2 = p.qn2[q];
             const float dmax2 = __uint_as_float(*p.max_sqnorm_bits);
-            const float eb = p.eps_rel * sqrtf(qn2) * sqrtf(dmax2);
+            const float eb = p.eps_rel * sqrtf(qn2) * sqrtf(dmax2) + p.eps_abs * (sqrtf(qn2) + sqrtf(dmax2));
             float tau, eps;
             if (p.metric == 0) { tau = a_tau + qn2; eps = 2.0f * eb + 4e-7f * (qn2 + dmax2 + fabsf(tau)); }
             else               { tau = 1.0f + a_tau; eps = eb + 4e-7f * (1.0f + fabsf(tau)); }
@@ -765,14 +777,19 @@ __global__ void __launch_bounds__(256) rerank_kernel(const RerankParams p) {
             ok = kth != KEY_SENTINEL && key_dist(kth) < tau - eps;
         }
         if (p.overflow[q]) ok = false;
+        // an element above the fp16 range became +-inf in the operand plane (|x_i| <= ||x||): no bound holds
+        if (p.f16_range && (p.qn2[q] >= 4.0e9f || __uint_as_float(*p.max_sqnorm_bits) >= 4.0e9f)) ok = false;
         p.flags[q] = ok ? 0 : 1;
         if (!ok) atomicAdd(p.n_flagged, 1);
     }
 }
 
-__global__ void f32_to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, size_t n) {
+// prepared fp32 queries [nq][ld] -> fp16 [nq][ld16] (ld16 <= ld; padding columns are zero)
+__global__ void f32_to_f16_kernel(const float* __restrict__ in, int ld, __half* __restrict__ out, int ld16, size_t nq) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i < n) out[i] = __float2half_rn(in[i]);
+    if (i >= nq * (size_t)ld16) return;
+    const size_t r = i / ld16, c = i - r * ld16;
+    out[i] = __float2half_rn(in[r * ld + c]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -909,23 +926,29 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
     if ((e = grow_dev(w->overflow, w->ovf_cap, a.nq)) != cudaSuccess) return e;
     if ((e = grow_dev(w->flags, w->flags_cap, a.nq)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(w->overflow, 0, a.nq * sizeof(int), st)) != cudaSuccess) return e;
+    // operand planes of the contraction: fp16 rows (fp16 shard, or the fp16 shadow of an fp32 shard) against
+    // fp16-rounded queries -> kind::f16; plain fp32 rows against fp32 queries -> kind::tf32
+    const bool g16 = a.f16 || a.shadow != nullptr;
+    const void* grows = a.f16 ? a.rows : (a.shadow ? a.shadow : a.rows);
+    const int gld = a.f16 ? a.ld : (a.shadow ? a.ld16 : a.ld);
+    const size_t gesz = g16 ? 2 : 4;
     const void* qa = a.q;
-    if (a.f16) {
-        if ((e = grow_dev(w->q16, w->q16_cap, a.nq * (size_t)a.ld)) != cudaSuccess) return e;
-        const size_t n = a.nq * (size_t)a.ld;
-        f32_to_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a.q, w->q16, n);
+    if (g16) {
+        if ((e = grow_dev(w->q16, w->q16_cap, a.nq * (size_t)gld)) != cudaSuccess) return e;
+        const size_t n = a.nq * (size_t)gld;
+        f32_to_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a.q, a.ld, w->q16, gld, a.nq);
         count_launch();
         qa = w->q16;
     }
     CUtensorMap tmA, tmB;
-    if (!make_tmap(&tmA, qa, a.f16, a.nq, (uint64_t)a.ld, GT_BM) || !make_tmap(&tmB, a.rows, a.f16, a.n_rows, (uint64_t)a.ld, GT_BN_HALF)) {
+    if (!make_tmap(&tmA, qa, g16, a.nq, (uint64_t)gld, GT_BM) || !make_tmap(&tmB, grows, g16, a.n_rows, (uint64_t)gld, GT_BN_HALF)) {
         err = "cuTensorMapEncodeTiled failed";
         return cudaErrorUnknown;
     }
     GemmParams gp{};
     gp.n_rows = a.n_rows; gp.nq = (uint32_t)a.nq;
-    gp.num_kb = (int)((size_t)a.ld * esz / GT_KB_BYTES);
-    gp.kb_elems = (int)(GT_KB_BYTES / esz);
+    gp.num_kb = (int)((size_t)gld * gesz / GT_KB_BYTES);
+    gp.kb_elems = (int)(GT_KB_BYTES / gesz);
     { const char* d = getenv("VDB_GEMM_DBG"); gp.dbg = d ? atoi(d) : 0; }
     gp.MB = MB; gp.n_tiles = n_tiles;
     gp.bits = 0;
@@ -967,7 +990,7 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
             if ((e = cudaMemsetAsync(w->buf, 0xFF, a.nq * (size_t)cap * sizeof(uint64_t), st)) != cudaSuccess) return e;
         }
         if (a.prof_begin) a.prof_begin(a.prof_ctx, st);
-        if (a.f16) e = l2 ? launch_gemm<true, true>(tmA, tmB, gp, grid, st) : launch_gemm<true, false>(tmA, tmB, gp, grid, st);
+        if (g16) e = l2 ? launch_gemm<true, true>(tmA, tmB, gp, grid, st) : launch_gemm<true, false>(tmA, tmB, gp, grid, st);
         else       e = l2 ? launch_gemm<false, true>(tmA, tmB, gp, grid, st) : launch_gemm<false, false>(tmA, tmB, gp, grid, st);
         if (a.prof_end) a.prof_end(a.prof_ctx, st);
         if (e != cudaSuccess) return e;
@@ -985,7 +1008,13 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
     rp.rows = a.rows; rp.row_bytes = (uint32_t)((size_t)a.ld * esz); rp.ld = a.ld;
     rp.labels = a.labels; rp.q = a.q; rp.qn2 = a.qn2; rp.max_sqnorm_bits = a.d_max_sqnorm_bits;
     rp.k = a.k; rp.metric = a.metric;
-    rp.eps_rel = a.f16 ? 6.5e-4f : 2.5e-3f;
+    // |approx dot - exact dot| <= eps_rel * ||q|| * ||d||  (+ eps_abs_unit * sqrt(dim) * (||q|| + ||d||) for fp16
+    // subnormal rounding).  fp16 shard: only the query is rounded (u = 2^-11 = 4.9e-4); shadow plane: query and
+    // row are rounded (2u + u^2 = 9.8e-4); tf32 operands are truncated to 10 mantissa bits (2 * 2^-10 = 1.95e-3).
+    // The rest is slack for the fp32 accumulation inside the tensor core.
+    rp.eps_rel = a.f16 ? 6.5e-4f : (a.shadow ? 1.3e-3f : 2.5e-3f);
+    rp.eps_abs = g16 ? 3.0e-8f * sqrtf((float)a.dim) : 0.0f;     // 2^-25 per element, Cauchy-Schwarz over dim
+    rp.f16_range = g16 ? 1 : 0;
     rp.out_ids = a.out_ids; rp.out_dist = a.out_dist; rp.out_counts = a.out_counts;
     rp.flags = w->flags; rp.n_flagged = w->n_flagged;
     e = a.f16 ? launch_rerank<__half>(kp, rp, a.nq, st) : launch_rerank<float>(kp, rp, a.nq, st);

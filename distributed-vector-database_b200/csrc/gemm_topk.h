@@ -16,6 +16,9 @@ struct GemmWorkspace {     // per in-flight call: candidate lists, thresholds, f
 
 struct GemmSearchArgs {
     const void* rows; int ld; int dim; bool f16; uint32_t n_rows;
+    // optional fp16 shadow plane of fp32 rows [n_rows][ld16]: when set, K2 contracts it (kind::f16) against
+    // fp16-rounded queries instead of the fp32 rows (kind::tf32); K4 always re-ranks from `rows`
+    const void* shadow = nullptr; int ld16 = 0;
     const float* sqnorm; const uint32_t* labels; const uint32_t* tomb;
     const float* q;        // prepared queries [nq][ld] fp32
     const float* qn2;      // [nq]

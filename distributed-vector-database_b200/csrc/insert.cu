@@ -70,6 +70,21 @@ __global__ void insert_rows_kernel(const float* __restrict__ src, size_t n, int 
     }
 }
 
+// fp16 shadow of fp32 shard rows [row0, row0+n): the operand plane of the batched tensor-core search
+// (kind::f16 runs at twice the tf32 rate; candidates are re-ranked from the fp32 rows, gemm_topk.cu).
+__global__ void shadow_rows_kernel(const float* __restrict__ rows, int ld, __half* __restrict__ shadow, int ld16,
+                                   size_t row0, size_t n) {
+    const size_t w = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = lane_id();
+    if (w >= n) return;
+    const float* src = rows + (row0 + w) * (size_t)ld;
+    __half2* dst = reinterpret_cast<__half2*>(shadow + (row0 + w) * (size_t)ld16);
+    for (int c = lane * 2; c < ld16; c += 64) {      // ld >= ld16, padding columns are zero
+        const float2 v = *reinterpret_cast<const float2*>(src + c);
+        dst[c >> 1] = __floats2half2_rn(v.x, v.y);
+    }
+}
+
 __global__ void synth_rows_kernel(uint64_t seed, uint64_t row_start, size_t n, int dim, float* __restrict__ out) {
     const size_t w = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
     const int lane = lane_id();
@@ -134,6 +149,13 @@ cudaError_t launch_insert_rows(const float* src, size_t n, int dim, int ld, bool
     else
         insert_rows_kernel<float><<<warp_grid(n, 256), 256, 0, st>>>(src, n, dim, ld, normalize, (float*)rows, sqnorm,
                                                                      row0, max_sqnorm_bits);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_shadow_rows(const float* rows, int ld, void* shadow, int ld16, size_t row0, size_t n, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    shadow_rows_kernel<<<warp_grid(n, 256), 256, 0, st>>>(rows, ld, (__half*)shadow, ld16, row0, n);
     count_launch();
     return cudaGetLastError();
 }

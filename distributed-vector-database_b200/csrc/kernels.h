@@ -55,6 +55,8 @@ cudaError_t launch_prepare_queries(const float* q, size_t nq, int dim, int ld, b
 // src [n][dim] fp32 -> shard rows [row0 .. row0+n) (T = f32/f16, stride ld), sqnorm, max norm.
 cudaError_t launch_insert_rows(const float* src, size_t n, int dim, int ld, bool normalize, bool f16, void* rows,
                                float* sqnorm, size_t row0, unsigned int* max_sqnorm_bits, cudaStream_t st);
+// fp32 rows [row0, row0+n) (stride ld) -> fp16 shadow plane (stride ld16 <= ld)
+cudaError_t launch_shadow_rows(const float* rows, int ld, void* shadow, int ld16, size_t row0, size_t n, cudaStream_t st);
 cudaError_t launch_synth_rows(uint64_t seed, uint64_t row_start, size_t n, int dim, float* out, cudaStream_t st);
 cudaError_t launch_set_bits(uint32_t* bitmap, const uint32_t* rows, size_t n, bool set, cudaStream_t st);
 cudaError_t launch_gather_rows(const void* rows, int ld, int dim, bool f16, const uint32_t* idx, size_t n, float* out,

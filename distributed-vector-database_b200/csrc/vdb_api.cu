@@ -103,6 +103,8 @@ struct vdb {
     std::atomic<size_t> count{0};
     size_t live = 0;
     void* rows = nullptr;
+    void* shadow = nullptr;           // fp16 copy of fp32 rows [capacity][ld16]: operand plane of the tensor path
+    int ld16 = 0;
     float* sqnorm = nullptr;
     uint32_t* labels = nullptr;
     uint32_t* tomb = nullptr;
@@ -125,6 +127,7 @@ struct vdb {
     // options / stats
     std::atomic<long> opt_path{0};          // 0 auto, 1 force scan, 2 force tensor
     std::atomic<long> opt_scan_batch{8};    // nq <= this takes the scan kernel in auto mode
+    std::atomic<long> opt_shadow{1};        // 1 = the tensor path contracts the fp16 shadow plane (fp32 shards)
     std::atomic<long> stat_fallback{0}, stat_tensor_batches{0}, stat_scan_passes{0};
     GemmPlan gemm_plan;
     // opt-in timing of the dominant kernel (scan or tensor) with CUDA events on the launching stream
@@ -157,6 +160,7 @@ int alloc_shard(vdb* db) {
     CU_TRY(cudaSetDevice(db->device));
     const size_t cap = std::max(db->capacity, (size_t)1);
     CU_TRY(cudaMalloc(&db->rows, cap * db->row_bytes()));
+    if (db->ld16) CU_TRY(cudaMalloc(&db->shadow, cap * (size_t)db->ld16 * 2));
     CU_TRY(cudaMalloc((void**)&db->sqnorm, cap * sizeof(float)));
     CU_TRY(cudaMalloc((void**)&db->labels, cap * sizeof(uint32_t)));
     const size_t words = (cap + 31) / 32 + 4;
@@ -326,6 +330,7 @@ int search_core(vdb* db, Workspace* ws, const float* d_q_raw, size_t nq, int k, 
     if (tensor) {
         GemmSearchArgs a{};
         a.rows = db->rows; a.ld = db->ld; a.dim = db->dim; a.f16 = f16; a.n_rows = (uint32_t)n;
+        if (db->shadow && db->opt_shadow.load()) { a.shadow = db->shadow; a.ld16 = db->ld16; }
         a.sqnorm = db->sqnorm; a.labels = db->labels; a.tomb = db->any_dead ? db->tomb : nullptr;
         a.q = ws->d_q; a.qn2 = ws->d_qn2; a.nq = nq; a.k = k;
         a.metric = db->metric == VDB_L2 ? 0 : 1;
@@ -409,6 +414,9 @@ int vdb_create(int dim, int metric, int store_dtype, size_t capacity, int device
     const int unit = store_dtype == VDB_F16 ? 256 : 128;   // one 512-byte warp load
     db->ld = (dim + unit - 1) / unit * unit;
     if (scan_max_k(1, db->ld, (uint32_t)db->row_bytes()) < 1) return fail(VDB_EINVAL, "dim too large for the scan kernel");
+    // fp32 shards keep an fp16 shadow plane for the batched tensor path (+50 % HBM); VDB_SHADOW=0 opts out
+    const char* sh = getenv("VDB_SHADOW");
+    if (store_dtype == VDB_F32 && !(sh && sh[0] == '0')) db->ld16 = (dim + 63) / 64 * 64;
     int rc = alloc_shard(db.get());
     if (rc != VDB_OK) {
         vdb_destroy(db.release());
@@ -427,6 +435,7 @@ void vdb_destroy(vdb_t* db) {
     for (auto& ev : db->prof_pool) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     gemm_plan_free(db->gemm_plan);
     if (db->rows) cudaFree(db->rows);
+    if (db->shadow) cudaFree(db->shadow);
     if (db->sqnorm) cudaFree(db->sqnorm);
     if (db->labels) cudaFree(db->labels);
     if (db->tomb) cudaFree(db->tomb);
@@ -528,6 +537,8 @@ static int add_impl(vdb* db, const float* rows, bool rows_on_device, const int64
         }
         CU_TRY(launch_insert_rows(src, m, db->dim, db->ld, db->metric == VDB_COSINE, db->dtype == VDB_F16, db->rows,
                                   db->sqnorm, row0 + off, db->d_max_sqnorm, db->wstream));
+        if (db->shadow)
+            CU_TRY(launch_shadow_rows((const float*)db->rows, db->ld, db->shadow, db->ld16, row0 + off, m, db->wstream));
         if (!rows_on_device) CU_TRY(cudaStreamSynchronize(db->wstream));   // staging buffer is reused
     }
     CU_TRY(cudaStreamSynchronize(db->wstream));
@@ -571,6 +582,8 @@ int vdb_add_synthetic(vdb_t* db, uint64_t seed, uint64_t row_start, size_t n, in
         CU_TRY(launch_synth_rows(seed, row_start + off, m, db->dim, db->d_stage, db->wstream));
         CU_TRY(launch_insert_rows(db->d_stage, m, db->dim, db->ld, db->metric == VDB_COSINE, db->dtype == VDB_F16,
                                   db->rows, db->sqnorm, row0 + off, db->d_max_sqnorm, db->wstream));
+        if (db->shadow)
+            CU_TRY(launch_shadow_rows((const float*)db->rows, db->ld, db->shadow, db->ld16, row0 + off, m, db->wstream));
     }
     CU_TRY(cudaStreamSynchronize(db->wstream));
     db->live += n;
@@ -679,6 +692,13 @@ int vdb_resize(vdb_t* db, size_t new_capacity) {
     CU_TRY(cudaMalloc((void**)&tomb, words * sizeof(uint32_t)));
     CU_TRY(cudaMemset(tomb, 0, words * sizeof(uint32_t)));
     CU_TRY(cudaMemcpy(rows, db->rows, n * db->row_bytes(), cudaMemcpyDeviceToDevice));
+    if (db->shadow) {
+        void* shadow = nullptr;
+        CU_TRY(cudaMalloc(&shadow, cap * (size_t)db->ld16 * 2));
+        CU_TRY(cudaMemcpy(shadow, db->shadow, n * (size_t)db->ld16 * 2, cudaMemcpyDeviceToDevice));
+        cudaFree(db->shadow);
+        db->shadow = shadow;
+    }
     CU_TRY(cudaMemcpy(sq, db->sqnorm, n * sizeof(float), cudaMemcpyDeviceToDevice));
     CU_TRY(cudaMemcpy(lab, db->labels, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
     CU_TRY(cudaMemcpy(tomb, db->tomb, std::min(words, old_words) * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
@@ -804,6 +824,14 @@ int vdb_load(const char* path, size_t capacity, int device, vdb_t** out) {
     fclose(f);
     if (!ok) { cudaGetLastError(); vdb_destroy(db); return fail(VDB_EIO, "snapshot truncated or copy failed"); }
     cudaMemcpy(db->d_max_sqnorm, &h.max_sqnorm_bits, 4, cudaMemcpyHostToDevice);
+    if (db->shadow && n) {   // derived data: rebuilt from the fp32 rows, not stored in the snapshot
+        if (launch_shadow_rows((const float*)db->rows, db->ld, db->shadow, db->ld16, 0, n, db->wstream) != cudaSuccess ||
+            cudaStreamSynchronize(db->wstream) != cudaSuccess) {
+            cudaGetLastError();
+            vdb_destroy(db);
+            return fail(VDB_ECUDA, "rebuilding the fp16 shadow plane failed");
+        }
+    }
     db->label_base = h.label_base;
     db->live = h.live;
     db->count.store(n);
@@ -854,6 +882,7 @@ int vdb_set_option(vdb_t* db, const char* name, long value) {
     if (!db || !name) return fail(VDB_EINVAL, "null argument");
     if (!strcmp(name, "path")) { db->opt_path.store(value); return VDB_OK; }
     if (!strcmp(name, "scan_batch")) { db->opt_scan_batch.store(value); return VDB_OK; }
+    if (!strcmp(name, "shadow")) { db->opt_shadow.store(value); return VDB_OK; }
     if (!strcmp(name, "profile")) { db->opt_profile.store(value); return VDB_OK; }
     return fail(VDB_EINVAL, std::string("unknown option ") + name);
 }
@@ -878,6 +907,7 @@ long vdb_get_stat(vdb_t* db, const char* name) {
         return (long)(total_ms * 1e6);
     }
     if (!strcmp(name, "ld")) return db->ld;
+    if (!strcmp(name, "shadow")) return db->shadow ? 1 : 0;
     return -1;
 }
 

@@ -193,18 +193,24 @@ def test_full_size_properties_1m(vdb):
 # batched tensor-core path (K2 + K5 + K4): forced with set_option("path", 2)
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("metric", ["l2", "ip", "cosine"])
-@pytest.mark.parametrize("store,dim", [("f32", 512), ("f16", 768)])
-def test_tensor_path_parity(vdb, metric, store, dim):
+@pytest.mark.parametrize("store,dim,shadow", [("f32", 512, 1), ("f32", 512, 0), ("f32", 100, 1), ("f16", 768, 1)])
+def test_tensor_path_parity(vdb, metric, store, dim, shadow):
+    """shadow=1: fp32 shard contracted through its fp16 shadow plane (kind::f16); shadow=0: the fp32 rows
+    themselves (kind::tf32); fp16 shards are contracted as stored."""
     ix, raw = build(vdb, metric, 6000, dim=dim, store=store, scale=1.3)
+    assert ix.get_stat("shadow") == (1 if store == "f32" else 0)
+    ix.set_option("shadow", shadow)
     ix.set_option("path", 2)
     q = R.synth_rows(R.SEED_QUERY, 0, 150, dim) * np.float32(0.8)
     assert_parity(ix, raw, metric, store, q, 10)
     assert ix.get_stat("tensor_batches") >= 1
 
 
+@pytest.mark.parametrize("shadow", [1, 0])
 @pytest.mark.parametrize("k", [1, 16, 17, 100, 128])
-def test_tensor_path_k_sizes(vdb, k):
+def test_tensor_path_k_sizes(vdb, k, shadow):
     ix, raw = build(vdb, "l2", 9000)
+    ix.set_option("shadow", shadow)
     ix.set_option("path", 2)
     q = R.synth_rows(R.SEED_QUERY, 3, 40, 512)
     assert_parity(ix, raw, "l2", "f32", q, k)
@@ -230,14 +236,46 @@ def test_tensor_path_tombstones(vdb):
 
 
 def test_tensor_path_equals_scan_path_bitwise(vdb):
-    """K4 re-ranks with the scan kernel's summation order: both paths return identical bits."""
+    """K4 re-ranks with the scan kernel's summation order: all paths return identical bits."""
     ix, raw = build(vdb, "cosine", 20000)
     q = R.synth_rows(R.SEED_QUERY, 0, 300, 512)
     ix.set_option("path", 1)
     a = ix.knn_query_padded(q, 10)
     ix.set_option("path", 2)
-    b = ix.knn_query_padded(q, 10)
-    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    for shadow in (1, 0):
+        ix.set_option("shadow", shadow)
+        b = ix.knn_query_padded(q, 10)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+
+
+def test_shadow_plane_follows_resize_save_load(vdb, tmp_path):
+    """the fp16 shadow plane is derived data: copied by resize, rebuilt by load, extended by later adds."""
+    ix, raw = build(vdb, "ip", 3000, cap=3000)
+    ix.resize_index(5000)
+    more = R.synth_rows(R.SEED_DB, 3000, 1500, 512)
+    ix.add_items(more, np.arange(3000, 4500))
+    allrows = np.concatenate([raw, more])
+    q = R.synth_rows(R.SEED_QUERY, 0, 64, 512)
+    ix.set_option("path", 2)
+    assert_parity(ix, allrows, "ip", "f32", q, 10)
+    path = str(tmp_path / "index.bin")
+    ix.save_index(path)
+    ix2 = vdb.Index("ip", 512)
+    ix2.load_index(path, max_elements=6000)
+    assert ix2.get_stat("shadow") == 1
+    ix2.set_option("path", 2)
+    assert_parity(ix2, allrows, "ip", "f32", q, 10)
+    assert ix2.get_stat("tensor_batches") >= 1 and ix2.get_stat("fallback_queries") == 0
+
+
+def test_shadow_plane_out_of_fp16_range_falls_back(vdb):
+    """rows with elements beyond the fp16 range turn into inf in the shadow plane: the certificate must
+    refuse and the exact scan must answer."""
+    ix, raw = build(vdb, "l2", 2000, scale=3.0e6)      # elements up to ~4e5 > 65504
+    ix.set_option("path", 2)
+    q = R.synth_rows(R.SEED_QUERY, 0, 12, 512) * np.float32(3.0e6)
+    assert_parity(ix, raw, "l2", "f32", q, 10)
+    assert ix.get_stat("fallback_queries") == 12
 
 
 def test_tensor_path_certificate_fallback_on_near_duplicates(vdb):
