@@ -5,7 +5,7 @@
 // Replaces hnswlib.Index.knn_query for nq > 8 (reference call site src/datanode/handler.py:364;
 // hnswlib accepts [nq, dim], the reference only ever passes one row).
 //
-// K2 (gemm_filter_kernel): persistent CTA PAIRS (cluster of 2, tcgen05 cta_group::2), 256 threads:
+// K2 (gemm_filter_kernel): persistent CTA PAIRS (cluster of 2, tcgen05 cta_group::2), 384 threads:
 //   warp 0   TMA producer: per k-block (128 bytes of every row) one 2-D tensor copy of this CTA's
 //            128 query rows (A) and of its half (128 rows) of the 256-row shard tile (B),
 //            SWIZZLE_128B, into a 4-stage shared-memory ring; completion bytes of both CTAs are
@@ -16,9 +16,9 @@
 //            smem stages / publishes accumulators
 //   warps 2-3 movers: drain the per-query key rings into the per-query candidate buffers in
 //            global memory (one atomicAdd reservation per query and round, lane-parallel)
-//   warps 4-7 epilogue: each thread owns one query (one TMEM lane): tcgen05.ld 32 columns at a
-//            time, turn the dot product into an approximate distance, keep the rows that beat the
-//            query's threshold (a key ring in shared memory; nothing else leaves the SM).
+//   warps 4-11 epilogue: two threads per query (one TMEM lane, columns 0-127 / 128-255): tcgen05.ld
+//            32 columns at a time, turn the dot product into an approximate distance, keep the rows
+//            that beat the query's threshold (a key ring in shared memory; nothing else leaves the SM).
 //   The [nq, n_rows] distance matrix never exists in memory.
 //
 // Thresholds come from LEVELS: the shard's 256-row tiles are visited in bit-reversed order, so
@@ -56,10 +56,11 @@ constexpr int GT_A_BYTES = GT_BM * GT_KB_BYTES;      // 16 KB
 constexpr int GT_B_BYTES = GT_BN_HALF * GT_KB_BYTES; // 16 KB (this CTA's half of the 256-row tile)
 constexpr int GT_STAGE_BYTES = GT_A_BYTES + GT_B_BYTES;
 constexpr int GT_STAGES = 5;
-constexpr int GT_THREADS = 256;
-constexpr int GT_RING = 48;                          // keys per query ring
-constexpr int GT_RING_STRIDE = 49;                   // padded: same-slot appends of a warp spread over banks
-constexpr int GT_EPI_THREADS = 128;
+constexpr int GT_THREADS = 384;                      // 12 warps: TMA, MMA, 2 movers, 8 epilogue
+constexpr int GT_RING = 24;                          // keys per ring (one ring per epilogue thread)
+constexpr int GT_RING_STRIDE = 25;                   // padded: same-slot appends of a warp spread over banks
+constexpr int GT_EPI_THREADS = 256;                  // 2 threads per query (TMEM lane): columns 0-127 / 128-255
+constexpr int GT_EPI_WARPS = GT_EPI_THREADS / 32;
 constexpr int GT_TMEM_COLS = 512;
 constexpr int GT_LEVEL_GROWTH = 8;                   // each level sees 8x the rows seen so far
 constexpr int GT_DENSE_TILES = 4;                    // level 0: 4 tiles = 1024 rows, everything kept
@@ -69,7 +70,8 @@ constexpr int GT_OFF_RING = GT_STAGES * GT_STAGE_BYTES;                         
 constexpr int GT_OFF_NORM = GT_OFF_RING + GT_EPI_THREADS * GT_RING_STRIDE * 8;    // + 50176
 constexpr int GT_OFF_BAR = GT_OFF_NORM + 2 * GT_BN * 4;                           // + 2048
 constexpr int GT_OFF_CTL = GT_OFF_BAR + 128;
-constexpr int GT_SMEM_BYTES_FILTER = GT_OFF_CTL + 1088 + 1024;
+constexpr int GT_CTL_BYTES = GT_EPI_THREADS * 8 + 64;                             // EpiCtl, checked below
+constexpr int GT_SMEM_BYTES_FILTER = GT_OFF_CTL + GT_CTL_BYTES + 1024;            // + slack for the 1024-byte alignment
 static_assert(GT_SMEM_BYTES_FILTER <= 232448, "shared memory budget");
 
 struct GemmParams {
@@ -210,9 +212,11 @@ __host__ __device__ __forceinline__ uint32_t bitrev(uint32_t x, int bits) {
 struct EpiCtl {
     uint32_t head_pub[GT_EPI_THREADS];   // keys appended so far (published by the epilogue thread)
     uint32_t tail[GT_EPI_THREADS];       // keys moved out so far
-    uint32_t qbase[4];                   // first query of each epilogue warp's current item
+    uint32_t qbase[GT_EPI_WARPS];        // first query of each epilogue warp's current item
     uint32_t done;                       // epilogue warps that have finished all items
 };
+
+static_assert(sizeof(EpiCtl) <= GT_CTL_BYTES, "EpiCtl outgrew its shared-memory slot");
 
 // item -> (slice, query block) and the slice's position range inside the level
 struct ItemRange { int mb, p0, p1; };
@@ -254,14 +258,14 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], 8);   // 4 epilogue warps x 2 CTAs arrive on the LEADER's barrier
+            mbar_init(&tmem_empty[a], 2 * GT_EPI_WARPS);   // 8 epilogue warps x 2 CTAs arrive on the LEADER's barrier
         }
         fence_barrier_init();
     }
     if (threadIdx.x < GT_EPI_THREADS) {
         ctl->head_pub[threadIdx.x] = 0;
         ctl->tail[threadIdx.x] = 0;
-        if (threadIdx.x < 4) ctl->qbase[threadIdx.x] = 0;
+        if (threadIdx.x < GT_EPI_WARPS) ctl->qbase[threadIdx.x] = 0;
         if (threadIdx.x == 0) ctl->done = 0;
     }
     if (warp == 2) tmem_alloc(tmem_ptr, GT_TMEM_COLS);
@@ -335,30 +339,30 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // Lane-parallel: each lane serves two queries; one atomicAdd reserves room for everything that is
         // waiting in a ring, so global-memory latency never sits on the TMEM-drain path of the epilogue.
         if (!p.dense) {
-            const int base = (warp - 2) * 64;    // warp 2 serves epilogue warps 4,5; warp 3 serves 6,7
+            const int base = (warp - 2) * (GT_EPI_THREADS / 2);    // each mover warp serves half of the rings
             volatile uint32_t* v_head = ctl->head_pub;
             volatile uint32_t* v_tail = ctl->tail;
             for (;;) {
-                const bool fin = *reinterpret_cast<volatile uint32_t*>(&ctl->done) == 4;
+                const bool fin = *reinterpret_cast<volatile uint32_t*>(&ctl->done) == GT_EPI_WARPS;
                 __threadfence_block();
                 bool moved = false;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int qi = base + h * 32 + lane;
-                    const uint32_t t = v_tail[qi];
-                    const uint32_t n = v_head[qi] - t;
+                for (int h = 0; h < GT_EPI_THREADS / 64; ++h) {
+                    const int ri = base + h * 32 + lane;          // ring == epilogue thread
+                    const uint32_t t = v_tail[ri];
+                    const uint32_t n = v_head[ri] - t;
                     if (n) {
                         __threadfence_block();
-                        const uint32_t q = *reinterpret_cast<volatile uint32_t*>(&ctl->qbase[qi >> 5]) + (qi & 31);
+                        const uint32_t q = *reinterpret_cast<volatile uint32_t*>(&ctl->qbase[ri >> 5]) + (ri & 31);
                         const int slot = atomicAdd(p.cnt + q, (int)n);
-                        const uint64_t* ring = ring_all + (size_t)qi * GT_RING_STRIDE;
+                        const uint64_t* ring = ring_all + (size_t)ri * GT_RING_STRIDE;
                         uint64_t* dst = p.buf + (size_t)q * p.cap;
                         for (uint32_t i = 0; i < n; ++i) {
                             const uint64_t key = *reinterpret_cast<const volatile uint64_t*>(ring + ((t + i) % GT_RING));
                             if (slot + (int)i < p.cap) dst[slot + i] = key;     // beyond cap: counted, flagged by K2s
                         }
                         __threadfence_block();
-                        v_tail[qi] = t + n;
+                        v_tail[ri] = t + n;
                         moved = true;
                     }
                 }
@@ -370,8 +374,15 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
     } else {
         // ================= epilogue: threshold filter (each CTA: its own 128 queries) =================
-        const int et = threadIdx.x - 128;                  // 0..127 == TMEM lane == query within this CTA's block
-        const int ew = et >> 5;                            // == warp % 4 : TMEM lane quadrant
+        // Two threads per query: warps 4-7 take columns 0-127 of the accumulator, warps 8-11 columns 128-255
+        // (a warp reaches the TMEM lane quadrant warp % 4).  Half the columns per thread halves the time an
+        // accumulator stays busy, which is what paces the MMA at the f16 rate.
+        const int et = threadIdx.x - 128;                  // 0..255: ring / epilogue thread
+        const int ew = et >> 5;                            // 0..7: epilogue warp
+        const int quad = warp & 3;                         // TMEM lane quadrant this warp may read
+        const int half = ew >> 2;                          // which 128 columns
+        const int ql = quad * 32 + lane;                   // TMEM lane == query within this CTA's block
+        const int col0 = half * (GT_BN / 2);
         const uint32_t my_ring_s = smem_u32(ring_all + (size_t)et * GT_RING_STRIDE);
         volatile uint32_t* my_tail = &ctl->tail[et];
         uint32_t head = 0, slot = 0;      // keys appended so far; slot == head % GT_RING
@@ -381,20 +392,21 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int item = pair; item < p.n_items; item += num_pairs) {
             const ItemRange ir = item_range(p, item);
             const uint32_t qbase = (uint32_t)ir.mb * (2 * GT_BM) + cta_rank * GT_BM;
-            const uint32_t q = qbase + et;
+            const uint32_t q = qbase + ql;
             const bool q_ok = q < p.nq;
             float thr = __int_as_float(0xff800000);        // -inf: nothing passes (padding queries)
             if (!p.dense) {
                 // the ring still holds keys of the previous item's query until the movers have drained it
                 while (*my_tail != head) __nanosleep(64);
+                tail_seen = head;
                 __syncwarp();
-                if (lane == 0) ctl->qbase[ew] = qbase + ew * 32;
+                if (lane == 0) ctl->qbase[ew] = qbase + quad * 32;
                 __threadfence_block();
                 if (q_ok) thr = p.thr[q];
             }
             const float nthr = -thr;
             uint64_t* dense_dst = p.buf + (size_t)(q_ok ? q : 0) * p.cap;
-            float n_next0 = 0.0f, n_next1 = 0.0f;
+            float n_next = 0.0f;
             bool first_tile = true;
 
             for (int pos = ir.p0; pos < ir.p1; ++pos) {
@@ -407,33 +419,30 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     // item: loaded here), published to the buffer the previous-but-one tile used
                     float* nsw = norm_s + acc * GT_BN;
                     if (first_tile) {
-                        const uint32_t r_a = row0 + et, r_b = row0 + 128 + et;
-                        n_next0 = r_a < p.n_rows ? p.sqnorm[r_a] : 0.0f;
-                        n_next1 = r_b < p.n_rows ? p.sqnorm[r_b] : 0.0f;
+                        const uint32_t r_a = row0 + et;
+                        n_next = r_a < p.n_rows ? p.sqnorm[r_a] : 0.0f;
                     }
-                    nsw[et] = n_next0;
-                    nsw[et + 128] = n_next1;
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    nsw[et] = n_next;
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
                     // next valid tile of this item
                     int np = pos + 1;
                     while (np < ir.p1 && (int)bitrev((uint32_t)np, p.bits) >= p.n_tiles) ++np;
                     if (np < ir.p1) {
-                        const uint32_t nr0 = bitrev((uint32_t)np, p.bits) * GT_BN;
-                        const uint32_t r_a = nr0 + et, r_b = nr0 + 128 + et;
-                        n_next0 = r_a < p.n_rows ? p.sqnorm[r_a] : 0.0f;
-                        n_next1 = r_b < p.n_rows ? p.sqnorm[r_b] : 0.0f;
+                        const uint32_t r_a = bitrev((uint32_t)np, p.bits) * GT_BN + et;
+                        n_next = r_a < p.n_rows ? p.sqnorm[r_a] : 0.0f;
                     }
                 }
                 first_tile = false;
                 mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * GT_BN;
-                const uint32_t ns_s = smem_u32(norm_s + acc * GT_BN);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * GT_BN + col0;
+                const uint32_t ns_s = smem_u32(norm_s + acc * GT_BN + col0);
+                constexpr int NCH = GT_BN / 2 / 32;            // 4 chunks of 32 columns per thread
                 if (p.dense) {
                     // level 0: every score of this tile is a candidate; position in the buffer is fixed
-                    uint64_t* dd = dense_dst + (size_t)(pos - p.pos_begin) * GT_BN;
+                    uint64_t* dd = dense_dst + (size_t)(pos - p.pos_begin) * GT_BN + col0;
 #pragma unroll 1
-                    for (int c = 0; c < GT_BN / 32; ++c) {
+                    for (int c = 0; c < NCH; ++c) {
                         uint32_t v[32];
                         float nv[32];
                         tmem_ld32(taddr + c * 32, v);
@@ -446,7 +455,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                                 float a;
                                 if constexpr (L2) a = fmaf(-2.0f, dot, nv[j]);
                                 else a = -dot;
-                                dd[c * 32 + j] = make_key(a, row0 + c * 32 + j);
+                                dd[c * 32 + j] = make_key(a, row0 + col0 + c * 32 + j);
                             }
                         }
                     }
@@ -461,7 +470,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 } else {
                     // TMEM reads are double-buffered: chunk c+1 is in flight while chunk c is filtered.
                     // Survivors are rare (about 1 score in 3000), so the common case of a chunk of 32 scores is a
-                    // min/max tree and ONE branch.  About a third of the warp-chunks hold a survivor in some lane:
+                    // min/max tree and ONE branch.  A fair share of the warp-chunks hold a survivor in some lane:
                     // that path walks the 8 group extrema of the tree and tests single scores only inside a
                     // group that has one.
                     auto filter_chunk = [&](const uint32_t (&v)[32], int c) {
@@ -486,46 +495,43 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         const float m = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])),
                                               fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
                         if (m > nthr) {
-                            // this chunk may append up to 32 keys: make sure the movers have left that much room
-                            // (tail_seen is a stale copy: the ring can only be emptier than it says)
-                            if (head - tail_seen > (uint32_t)(GT_RING - 32)) {
-                                if (dirty) { __threadfence_block(); ctl->head_pub[et] = head; dirty = false; }
-                                while (head - (tail_seen = *my_tail) > (uint32_t)(GT_RING - 32)) __nanosleep(32);
-                            }
 #pragma unroll
                             for (int gi = 0; gi < 8; ++gi) {
                                 if (g[gi] > nthr) {
+                                    // up to 4 appends: make room first (tail_seen is a stale copy: the ring can only
+                                    // be emptier than it says); publish what is pending before waiting for the movers
+                                    if (head - tail_seen > (uint32_t)(GT_RING - 4)) {
+                                        if (dirty) { __threadfence_block(); ctl->head_pub[et] = head; dirty = false; }
+                                        while (head - (tail_seen = *my_tail) > (uint32_t)(GT_RING - 4)) __nanosleep(32);
+                                    }
 #pragma unroll
                                     for (int e = 0; e < 4; ++e) {
                                         if (s[4 * gi + e] > nthr) {
-                                            st_shared_u64(my_ring_s + slot * 8, make_key(-s[4 * gi + e], row0 + c * 32 + 4 * gi + e));
+                                            st_shared_u64(my_ring_s + slot * 8,
+                                                          make_key(-s[4 * gi + e], row0 + col0 + c * 32 + 4 * gi + e));
                                             ++head;
                                             if (++slot == GT_RING) slot = 0;
                                         }
                                     }
+                                    dirty = true;
                                 }
                             }
-                            dirty = true;
                         }
                     };
-                    uint32_t v0[32], v1[32];
-                    tmem_ld32(taddr, v0);
-                    tmem_ld_wait();
+                    // single-buffered: the other epilogue warp of this sub-partition covers the TMEM latency
 #pragma unroll 1
-                    for (int c = 0; c < GT_BN / 32; c += 2) {
-                        tmem_ld32(taddr + (c + 1) * 32, v1);
-                        filter_chunk(v0, c);
+                    for (int c = 0; c < NCH; ++c) {
+                        uint32_t v[32];
+                        tmem_ld32(taddr + c * 32, v);
                         tmem_ld_wait();
-                        if (c + 2 < GT_BN / 32) {
-                            tmem_ld32(taddr + (c + 2) * 32, v0);
-                        } else {
-                            // the whole accumulator is in registers: hand it back before filtering the last chunk
+                        if (c == NCH - 1) {
+                            // this thread's share of the accumulator is in registers: hand it back before
+                            // filtering the last chunk
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[acc]), 0));
                         }
-                        filter_chunk(v1, c + 1);
-                        tmem_ld_wait();
+                        filter_chunk(v, c);
                     }
                     if (dirty) {    // publish this tile's keys to the movers (once per tile, not per chunk)
                         __threadfence_block();
