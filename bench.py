@@ -8,9 +8,12 @@ A "step" is one search of one batch of synthetic queries over the whole (sharded
 Workload at N=1 = BASELINE config[1]: 1M x 512 fp32 unit-norm rows, cosine, top-10.  `value` is
 the batched (batch 1024) queries/s with queries and results resident in HBM; the same line also
 carries the single-query (batch 1) scan numbers under "single_query", because config[1] names
-both.  N > 1 shards the SAME database by contiguous row ranges (strong scaling), every rank
-searches its shard and the per-rank top-k lists are all-gathered over NCCL and merged on the GPU
-(the coordinator's scatter-gather, src/coordinator/handler.py:191-216).
+both.  N > 1 shards the SAME database by contiguous row ranges; every rank searches its shard for
+the whole batch, the per-rank top-k lists are exchanged by query slice (all-to-all over
+NCCL/NVLink) and rank r merges the lists of its slice on the GPU (the coordinator's
+scatter-gather, src/coordinator/handler.py:191-216).  Default --scaling weak: the global batch is
+1024 x N, so the contraction work per GPU (batch x rows/N) is fixed as N grows -- the shape of
+BASELINE config[2] (10M rows over 8 GPUs, batch 4096); --scaling strong keeps the batch at 1024.
 
 Prints ONE JSON line (rank 0).  Inputs are larger than L2 (2 GB shard vs 126 MB), so no flush.
 """
@@ -106,7 +109,9 @@ def parse():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--metric", default="cosine", choices=["l2", "ip", "cosine"])
     ap.add_argument("--store", default="f32", choices=["f32", "f16"])
-    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--batch", type=int, default=1024, help="queries per step (per GPU under --scaling weak)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1: weak = global batch is batch x N (work per GPU fixed); strong = batch fixed")
     ap.add_argument("--single-steps", type=int, default=0, help="steps for the batch-1 leg (default: 5*steps)")
     ap.add_argument("--no-single", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -114,8 +119,12 @@ def parse():
     return ap.parse_args()
 
 
-def workload_name(a):
-    return f"{a.rows}x{a.dim} {a.store} {a.metric} top-{a.k}, batch {a.batch} (+ batch 1)"
+def global_batch(a, world):
+    return a.batch * world if a.scaling == "weak" else (a.batch + world - 1) // world * world
+
+
+def workload_name(a, world=1):
+    return f"{a.rows}x{a.dim} {a.store} {a.metric} top-{a.k}, batch {global_batch(a, world)} (+ batch 1)"
 
 
 # --------------------------------------------------------------------------------------------
@@ -143,6 +152,7 @@ def cpu_knn_qps(a, nq: int, rows_cap: int = 1_000_000, return_ids: bool = False)
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     nq = a.cpu_queries or 32
@@ -155,8 +165,11 @@ def run_reference(a):
     line = {
         "impl": "reference", "metric": "queries/sec exact top-k", "value": v, "unit": "queries/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * nq / v,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "inputs": "larger than L2/LLC (2 GB)"},
+        "higher_is_better": True, "scaling": a.scaling if world > 1 else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": workload_name(a, world), "global_batch": global_batch(a, world), "rows_total": a.rows,
+                   "inputs": "larger than L2/LLC (2 GB)",
+                   "note": "CPU exact scan of the same database; throughput does not depend on the batch size"},
         "cpu_baseline": {"value": v, "unit": "queries/s", "cores": cores, "kind": "port",
                          "sample": "per step: " + desc + " (oracle/knn_ref.c exact scan, OpenMP)"},
         "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -202,13 +215,31 @@ def run_ours(a):
         vdb._ffi.check(lib.vdb_synth_dev(SEED_QUERY, 0, nq, a.dim, q.data_ptr(), stream), "synth")
         return q
 
+    def exchange_buffers(nq):
+        """N>1: per-rank lists [nq,k] -> all-to-all by query slice -> [world, nq/world, k] on the owner of the slice"""
+        sl = nq // world
+        return (torch.empty((world, sl, a.k), dtype=torch.int64, device=dev),
+                torch.empty((world, sl, a.k), dtype=torch.float32, device=dev),
+                torch.empty((sl, a.k), dtype=torch.int64, device=dev),
+                torch.empty((sl, a.k), dtype=torch.float32, device=dev))
+
+    def exchange_and_merge(ids, dd, nq, bufs):
+        g_ids, g_dd, o_ids, o_dd = bufs
+        dist.all_to_all_single(g_ids.view(nq, a.k), ids)      # rank r receives every rank's lists for slice r
+        dist.all_to_all_single(g_dd.view(nq, a.k), dd)
+        vdb._ffi.check(lib.vdb_merge_topk(g_dd.data_ptr(), g_ids.data_ptr(), world, nq // world, a.k, a.k,
+                                          o_dd.data_ptr(), o_ids.data_ptr(), 1, local, stream), "merge")
+
     def device_leg(nq, steps, warmup):
         """queries + results resident in HBM; returns (seconds for `steps`, dominant-kernel ns, launches)"""
+        sharded = world > 1 and nq % world == 0
         q = make_queries(nq)
         ids = torch.empty((nq, a.k), dtype=torch.int64, device=dev)
         dd = torch.empty((nq, a.k), dtype=torch.float32, device=dev)
         cnt = torch.empty((nq,), dtype=torch.int32, device=dev)
-        if world > 1:
+        if sharded:
+            bufs = exchange_buffers(nq)
+        elif world > 1:     # a single query: all-gather the lists, every rank merges
             g_ids = torch.empty((world, nq, a.k), dtype=torch.int64, device=dev)
             g_dd = torch.empty((world, nq, a.k), dtype=torch.float32, device=dev)
             o_ids = torch.empty((nq, a.k), dtype=torch.int64, device=dev)
@@ -216,7 +247,9 @@ def run_ours(a):
 
         def step():
             ix.search_device(q.data_ptr(), nq, a.k, ids.data_ptr(), dd.data_ptr(), cnt.data_ptr(), stream)
-            if world > 1:
+            if sharded:
+                exchange_and_merge(ids, dd, nq, bufs)
+            elif world > 1:
                 dist.all_gather_into_tensor(g_ids, ids)
                 dist.all_gather_into_tensor(g_dd, dd)
                 vdb._ffi.check(lib.vdb_merge_topk(g_dd.data_ptr(), g_ids.data_ptr(), world, nq, a.k, a.k,
@@ -246,26 +279,33 @@ def run_ours(a):
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        final = (o_ids if world > 1 else ids)[:64].cpu().numpy()
+        final = (bufs[2] if sharded else (o_ids if world > 1 else ids))[:64].cpu().numpy()   # rank 0: queries 0..63
         return float(ms.item()) * 1e-3, kern_ns, nprof, launches, final
 
     def e2e_leg(nq, steps, warmup):
         """through the public host-buffer API: H2D of the queries and D2H of the results inside the timed region"""
+        sharded = world > 1 and nq % world == 0
         qh = make_queries(nq).cpu().numpy()          # host copy made outside the timed region
         if world > 1:
-            g_ids = torch.empty((world, nq, a.k), dtype=torch.int64, device=dev)
-            g_dd = torch.empty((world, nq, a.k), dtype=torch.float32, device=dev)
-            o_ids = torch.empty((nq, a.k), dtype=torch.int64, device=dev)
-            o_dd = torch.empty((nq, a.k), dtype=torch.float32, device=dev)
             pin_q = torch.from_numpy(qh).pin_memory()
+            if sharded:
+                bufs = exchange_buffers(nq)
+            else:
+                g_ids = torch.empty((world, nq, a.k), dtype=torch.int64, device=dev)
+                g_dd = torch.empty((world, nq, a.k), dtype=torch.float32, device=dev)
+                o_ids = torch.empty((nq, a.k), dtype=torch.int64, device=dev)
+                o_dd = torch.empty((nq, a.k), dtype=torch.float32, device=dev)
 
         def step():
             if world == 1:
                 return ix.knn_query_padded(qh, a.k)
-            qd = pin_q.to(dev, non_blocking=True)
+            qd = pin_q.to(dev, non_blocking=True)             # every rank needs the whole batch
             ids = torch.empty((nq, a.k), dtype=torch.int64, device=dev)
             dd = torch.empty((nq, a.k), dtype=torch.float32, device=dev)
             ix.search_device(qd.data_ptr(), nq, a.k, ids.data_ptr(), dd.data_ptr(), 0, stream)
+            if sharded:
+                exchange_and_merge(ids, dd, nq, bufs)
+                return bufs[2].cpu(), bufs[3].cpu()           # each rank returns the results of its slice
             dist.all_gather_into_tensor(g_ids, ids)
             dist.all_gather_into_tensor(g_dd, dd)
             vdb._ffi.check(lib.vdb_merge_topk(g_dd.data_ptr(), g_ids.data_ptr(), world, nq, a.k, a.k,
@@ -307,10 +347,21 @@ def run_ours(a):
             torch.backends.cuda.matmul.allow_tf32 = old
             del x, y
 
-    tf32_peak = cublas_tf32_tflops() if a.store == "f32" else None
+    shadow = a.store == "f32" and ix.get_stat("shadow") == 1       # fp32 rows contracted through their fp16 plane
+    tf32_path = a.store == "f32" and not shadow
+    tf32_peak = cublas_tf32_tflops() if tf32_path else None
+    dtype_name = ("f16 operands (shadow plane of f32 rows) / f32 accumulate, exact f32 re-rank" if shadow else
+                  "tf32 operands / f32 accumulate, exact f32 re-rank" if tf32_path else
+                  "f16-stored / f32 accumulate")
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")       # dram bytes per launch from the committed ncu captures
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f)
     with ClockSampler(local) as clk:
-        sec, kern_ns, nprof, launches, got_ids = device_leg(a.batch, a.steps, a.warmup)
-        e2e_sec = e2e_leg(a.batch, a.steps, a.warmup)
+        B = global_batch(a, world)
+        sec, kern_ns, nprof, launches, got_ids = device_leg(B, a.steps, a.warmup)
+        e2e_sec = e2e_leg(B, a.steps, a.warmup)
         single = None
         if not a.no_single:
             ss = a.single_steps or max(5 * a.steps, 50)
@@ -324,7 +375,8 @@ def run_ours(a):
                         "d2h_bytes_per_step": a.k * 12 + 4},
                 "roofline": {"bound": "hbm", "kernel": "scan_topk_kernel", "achieved": ach, "peak": peaks["hbm_gbs"],
                              "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "peak_source": peaks["source"],
-                             "algorithmic_bytes_per_launch": shard_bytes, "kernel_us": t_k * 1e6, "traffic": None},
+                             "algorithmic_bytes_per_launch": shard_bytes, "kernel_us": t_k * 1e6,
+                             "traffic": traffic.get(f"scan_topk_kernel|{a.rows}x{a.dim} {a.store}") if world == 1 else None},
                 "gpu_launches": s_launch,
             }
 
@@ -335,25 +387,28 @@ def run_ours(a):
     if tensor_batches > 0:
         # one search = `passes_per_step` launches of gemm_filter_kernel (one per threshold level) that together
         # contract every query with every row once: algorithmic flops per search / summed launch time
-        flops = 2.0 * a.batch * (hi - lo) * a.dim
+        flops = 2.0 * B * (hi - lo) * a.dim          # this rank's share: the whole batch against its rows
         t_step = kern_ns * 1e-9 / max(a.steps, 1)
         ach = flops / t_step / 1e12
-        tf32 = a.store == "f32"
-        peak = tf32_peak if tf32 else peaks["bf16_tflops"]
+        # kind::f16 against the measured bf16 burst peak (same tensor rate); kind::tf32 runs at half that rate
+        peak = peaks["bf16_tflops"] * (0.5 if tf32_path else 1.0)
         roof = {"bound": "tensor", "kernel": "gemm_filter_kernel", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak,
-                "peak_source": ("cuBLAS TF32 8192^3 measured in this run (fp32 rows use kind::tf32); "
-                                f"MEASURED_PEAKS bf16 = {peaks['bf16_tflops']:.0f} burst / {peaks['bf16_tflops_sustained']:.0f} sustained")
-                if tf32 else peaks["source"] + " bf16 burst (fp16 rows use kind::f16)",
-                "frac_of_measured_bf16": ach / peaks["bf16_tflops"],
+                "peak_source": peaks["source"] + (" bf16 burst x 0.5 (kind::tf32 runs at half the bf16 rate)" if tf32_path
+                                                  else " bf16 burst (kind::f16, same tensor rate)"),
+                "frac_of_measured_bf16_sustained": ach / (peaks["bf16_tflops_sustained"] * (0.5 if tf32_path else 1.0)),
                 "algorithmic_flops_per_step": flops, "kernel_us_per_step": t_step * 1e6,
-                "launches_per_step": passes_per_step, "traffic": None}
+                "launches_per_step": passes_per_step,
+                "traffic": traffic.get(f"gemm_filter_kernel|{workload_name(a, world)}")}
+        if tf32_peak:
+            roof["cublas_tf32_8192_tflops_this_run"] = tf32_peak
     else:
         ach = shard_bytes / t_kernel / 1e9
         roof = {"bound": "hbm", "kernel": "scan_topk_kernel", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / peaks["hbm_gbs"], "peak_source": peaks["source"],
                 "algorithmic_bytes_per_launch": shard_bytes, "kernel_us": t_kernel * 1e6,
-                "launches_per_step": passes_per_step, "traffic": None}
+                "launches_per_step": passes_per_step,
+                "traffic": traffic.get(f"scan_topk_kernel|{a.rows}x{a.dim} {a.store}")}
 
     if rank == 0:
         cpu = None
@@ -367,14 +422,17 @@ def run_ours(a):
                 hits = sum(len(set(got_ids[i].tolist()) & set(want_ids[i].tolist())) for i in range(m))
                 recall = hits / float(m * a.k)
         line = {
-            "metric": "queries/sec exact top-k", "value": a.batch * a.steps / sec, "unit": "queries/s",
+            "metric": "queries/sec exact top-k", "value": B * a.steps / sec, "unit": "queries/s",
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * sec / a.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32" if a.store == "f32" else "f16-stored/f32-accumulate", "data": "synthetic",
-            "config": {"workload": workload_name(a), "rows_per_gpu": hi - lo, "sharding": f"contiguous rows x{world}",
+            "higher_is_better": True, "scaling": a.scaling if world > 1 else "weak", "vs_baseline": None,
+            "dtype": dtype_name, "data": "synthetic",
+            "config": {"workload": workload_name(a, world), "global_batch": B, "rows_total": a.rows,
+                       "rows_per_gpu": hi - lo, "sharding": f"contiguous rows x{world}",
+                       "exchange": "none" if world == 1 else "all-to-all by query slice (NCCL) + GPU merge",
                        "l2": "inputs larger than L2 (no flush needed)", "path": "tensor" if tensor_batches > 0 else "scan"},
-            "e2e": {"value": a.batch * a.steps / e2e_sec, "unit": "queries/s",
-                    "h2d_bytes_per_step": a.batch * a.dim * 4, "d2h_bytes_per_step": a.batch * a.k * 12 + a.batch * 4},
+            "e2e": {"value": B * a.steps / e2e_sec, "unit": "queries/s",
+                    "h2d_bytes_per_step": world * B * a.dim * 4,
+                    "d2h_bytes_per_step": B * a.k * 12 + (B * 4 if world == 1 else 0)},
             "gpu_launches": launches,
             "roofline": roof,
             "cpu_baseline": cpu,

@@ -70,12 +70,15 @@ class LocalCoordinator:
 
 
 class ShardedSearcher:
-    """One rank per GPU (torch.distributed): every rank searches its shard, the per-rank top-k lists are
-    all-gathered (NCCL over NVLink on GPUs; gloo in the CPU tests) and merged by (distance, id) -- the GPU form
-    of coordinator/handler.py:191-216.
+    """One rank per GPU (torch.distributed): every rank searches its shard for the whole batch; the per-rank
+    top-k lists are exchanged BY QUERY SLICE (all-to-all: rank r receives every rank's lists for queries
+    [r*nq/G, (r+1)*nq/G)) and merged by (distance, id) on the owner of the slice -- the GPU form of
+    coordinator/handler.py:191-216 with the merge work and the exchanged bytes divided by G.  NCCL over NVLink
+    on GPUs; gloo in the CPU tests.  Batches that do not divide by G (a single query) are all-gathered and
+    merged on every rank.
 
     `local_search(queries[nq, dim], k) -> (ids int64 [nq,k] global ids, -1 padded; dist float32 [nq,k])`
-    `merge(dist [G,nq,k], ids [G,nq,k], k) -> (dist [nq,k], ids [nq,k])`   (the CUDA merge kernel in production)
+    `merge(dist [G,n,k], ids [G,n,k], k) -> (dist [n,k], ids [n,k])`   (the CUDA merge kernel in production)
     Tensors are torch tensors on the device of the process group's backend."""
 
     def __init__(self, local_search: Callable, merge: Callable, group=None):
@@ -85,10 +88,32 @@ class ShardedSearcher:
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
 
-    def search(self, queries, k: int):
+    def search_slice(self, queries, k: int):
+        """Results of this rank's query slice only: (dist [nq/G,k], ids [nq/G,k]); nq must divide by G."""
         import torch
         ids, dd = self.local_search(queries, k)
         nq = ids.shape[0]
+        if nq % self.world:
+            raise ValueError("search_slice needs a batch that divides by the world size")
+        g_ids = torch.empty_like(ids)
+        g_dd = torch.empty_like(dd)
+        self._dist.all_to_all_single(g_ids, ids.contiguous(), group=self.group)
+        self._dist.all_to_all_single(g_dd, dd.contiguous(), group=self.group)
+        sl = nq // self.world
+        return self.merge(g_dd.view(self.world, sl, -1), g_ids.view(self.world, sl, -1), k)
+
+    def search(self, queries, k: int):
+        """Full result on every rank: (dist [nq,k], ids [nq,k])."""
+        import torch
+        nq = queries.shape[0]
+        if nq % self.world == 0 and nq >= self.world:
+            dd, ids = self.search_slice(queries, k)
+            o_dd = torch.empty((nq,) + tuple(dd.shape[1:]), dtype=dd.dtype, device=dd.device)
+            o_ids = torch.empty((nq,) + tuple(ids.shape[1:]), dtype=ids.dtype, device=ids.device)
+            self._dist.all_gather_into_tensor(o_dd, dd.contiguous(), group=self.group)
+            self._dist.all_gather_into_tensor(o_ids, ids.contiguous(), group=self.group)
+            return o_dd, o_ids
+        ids, dd = self.local_search(queries, k)
         # concatenated along dim 0 (the layout both NCCL and gloo accept), viewed as [G, nq, k]
         g_ids = torch.empty((self.world * nq,) + tuple(ids.shape[1:]), dtype=ids.dtype, device=ids.device)
         g_dd = torch.empty((self.world * nq,) + tuple(dd.shape[1:]), dtype=dd.dtype, device=dd.device)

@@ -51,9 +51,10 @@ def _worker(rank, world, port, n, dim, nq, k, metric, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("metric", ["l2", "cosine"])
-def test_sharded_search_equals_single_shard(metric):
-    n, dim, nq, k, world = 1200, 64, 5, 10, 2
+@pytest.mark.parametrize("metric,nq", [("l2", 5), ("cosine", 5), ("l2", 6)])
+def test_sharded_search_equals_single_shard(metric, nq):
+    """nq = 5: does not divide by 2 -> all-gather + merge everywhere; nq = 6: all-to-all by query slice."""
+    n, dim, k, world = 1200, 64, 10, 2
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
