@@ -113,6 +113,8 @@ def parse():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = global batch is batch x N (work per GPU fixed); strong = batch fixed")
     ap.add_argument("--single-steps", type=int, default=0, help="steps for the batch-1 leg (default: 5*steps)")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: p2p = fused NVLink exchange+merge kernel (vdb_xchg_*), nccl = all-to-all + merge kernel")
     ap.add_argument("--no-single", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-queries", type=int, default=0)
@@ -223,8 +225,21 @@ def run_ours(a):
                 torch.empty((sl, a.k), dtype=torch.int64, device=dev),
                 torch.empty((sl, a.k), dtype=torch.float32, device=dev))
 
+    px = None
+    if world > 1 and a.exchange == "p2p":
+        def gather_handles(mine: bytes):
+            t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(dev)
+            o = torch.empty((world, 64), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(o, t)
+            return [o[r].cpu().numpy().tobytes() for r in range(world)]
+        px = vdb.PeerExchange(local, rank, world, max_slice=global_batch(a, world) // world, max_k=a.k,
+                              exchange_handles=gather_handles)
+
     def exchange_and_merge(ids, dd, nq, bufs):
         g_ids, g_dd, o_ids, o_dd = bufs
+        if px is not None:      # one kernel: peer stores over NVLink, flags, merge of the owned slice
+            px.merge(dd.data_ptr(), ids.data_ptr(), nq, a.k, o_dd.data_ptr(), o_ids.data_ptr(), stream)
+            return
         dist.all_to_all_single(g_ids.view(nq, a.k), ids)      # rank r receives every rank's lists for slice r
         dist.all_to_all_single(g_dd.view(nq, a.k), dd)
         vdb._ffi.check(lib.vdb_merge_topk(g_dd.data_ptr(), g_ids.data_ptr(), world, nq // world, a.k, a.k,
@@ -428,7 +443,9 @@ def run_ours(a):
             "dtype": dtype_name, "data": "synthetic",
             "config": {"workload": workload_name(a, world), "global_batch": B, "rows_total": a.rows,
                        "rows_per_gpu": hi - lo, "sharding": f"contiguous rows x{world}",
-                       "exchange": "none" if world == 1 else "all-to-all by query slice (NCCL) + GPU merge",
+                       "exchange": "none" if world == 1 else (
+                           "fused NVLink peer-store exchange + merge kernel, by query slice" if px is not None
+                           else "all-to-all by query slice (NCCL) + GPU merge"),
                        "l2": "inputs larger than L2 (no flush needed)", "path": "tensor" if tensor_batches > 0 else "scan"},
             "e2e": {"value": B * a.steps / e2e_sec, "unit": "queries/s",
                     "h2d_bytes_per_step": world * B * a.dim * 4,

@@ -120,3 +120,43 @@ class ShardedSearcher:
         self._dist.all_gather_into_tensor(g_ids, ids.contiguous(), group=self.group)
         self._dist.all_gather_into_tensor(g_dd, dd.contiguous(), group=self.group)
         return self.merge(g_dd.view(self.world, nq, -1), g_ids.view(self.world, nq, -1), k)
+
+
+class PeerExchange:
+    """Exchange + merge of the per-rank top-k lists in ONE CUDA kernel over NVLink peer memory (C ABI
+    vdb_xchg_*, kernel K5x in csrc/merge_topk.cu): the NCCL-free form of `ShardedSearcher.search_slice`'s
+    all-to-all + merge for the ranks of one box.
+
+    `exchange_handles(my_handle: bytes) -> list[bytes]` must return every rank's 64-byte handle in rank order
+    (e.g. an all-gather over the job's process group)."""
+
+    def __init__(self, device: int, rank: int, world: int, max_slice: int, max_k: int, exchange_handles: Callable):
+        import ctypes as C
+        from . import _ffi
+        self._ffi, self._C = _ffi, C
+        self.rank, self.world = rank, world
+        h = C.c_void_p()
+        buf = (C.c_ubyte * 64)()
+        _ffi.check(_ffi.lib().vdb_xchg_create(device, rank, world, max_slice, max_k, C.byref(h), buf), "xchg_create")
+        self._h = h.value
+        handles = exchange_handles(bytes(buf))
+        if len(handles) != world or any(len(x) != 64 for x in handles):
+            raise RuntimeError("exchange_handles must return one 64-byte handle per rank")
+        blob = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))
+        _ffi.check(_ffi.lib().vdb_xchg_connect(self._h, blob), "xchg_connect")
+
+    def merge(self, d_dist_ptr: int, d_ids_ptr: int, nq: int, k: int, o_dist_ptr: int, o_ids_ptr: int, stream: int = 0):
+        """Enqueue on `stream`: this rank's lists [nq,k] (device pointers) -> its slice's results [nq/world,k]."""
+        self._ffi.check(self._ffi.lib().vdb_xchg_merge_dev(self._h, d_dist_ptr, d_ids_ptr, nq, int(k), o_dist_ptr,
+                                                           o_ids_ptr, stream or None), "xchg_merge")
+
+    def close(self):
+        if self._h is not None:
+            self._ffi.lib().vdb_xchg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -36,7 +36,8 @@ struct MergeParams {
     // input mode B: (dist,id) lists laid out [G][nq][k_in]; id < 0 is padding
     const float* in_dist;
     const int64_t* in_ids;
-    int G, k_in;
+    int G, k_in;               // mode C: in_keys != null and G > 0: packed keys [G][key_stride_g] with query rows of k_in
+    size_t key_stride_g;
     size_t nq;
     int n_in;                  // keys per query (mode A) or G*k_in (mode B)
     int k_out;
@@ -46,6 +47,23 @@ struct MergeParams {
     int* out_counts;           // optional [nq]
 };
 cudaError_t launch_merge_topk(const MergeParams& p, cudaStream_t st);
+
+// ---- K5x exchange + merge over NVLink peer memory (merge_topk.cu) ---------------------------
+constexpr int XCHG_MAX_WORLD = 16;
+struct XchgParams {
+    int rank, world, parity;
+    uint32_t step;                 // 1, 2, 3, ... (flags start at 0)
+    size_t nq, slice;              // global batch, queries owned per rank (nq == slice * world)
+    int k;
+    const int64_t* ids;            // this rank's lists [nq][k] (id < 0 = padding)
+    const float* dist;
+    uint64_t* peer_buf[XCHG_MAX_WORLD];    // receive buffer of every rank: [2][world][stride_src] keys
+    uint32_t* peer_flag[XCHG_MAX_WORLD];   // flag words of every rank: [2][world]
+    const uint32_t* local_flag;
+    size_t stride_parity, stride_src;
+    unsigned int* done_counter;    // local, zeroed by the launcher
+};
+cudaError_t launch_exchange_merge(const XchgParams& x, const MergeParams& mp, int num_sms, cudaStream_t st);
 
 // ---- K0 / K3 / utilities (insert.cu) ------------------------------------------------------
 // queries [nq][dim] fp32 -> prepared [nq][ld] fp32 (normalised when cosine, zero padded),

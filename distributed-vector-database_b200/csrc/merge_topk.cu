@@ -5,6 +5,8 @@
 // Keys are (ordered fp32 distance << 32 | label), so one unsigned 64-bit bitonic sort gives
 // ascending (distance, label).  One CTA per query; inputs longer than the 2048-key shared
 // buffer are streamed through it, keeping the best k_out after each round.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -32,6 +34,10 @@ __device__ __forceinline__ void bitonic_sort_smem(uint64_t* buf, int n) {
 }
 
 __device__ __forceinline__ uint64_t merge_load(const MergeParams& p, size_t q, int idx) {
+    if (p.in_keys && p.G > 0) {   // packed keys laid out [G][nq][k_in] (the exchange buffer): L1-bypassing loads,
+        const int g = idx / p.k_in, j = idx - g * p.k_in;          // the lines were written by peer GPUs
+        return __ldcv(p.in_keys + ((size_t)g * p.key_stride_g + q * (size_t)p.k_in + j));
+    }
     if (p.in_keys) return p.in_keys[q * (size_t)p.n_in + idx];
     const int g = idx / p.k_in, j = idx - g * p.k_in;
     const size_t off = ((size_t)g * p.nq + q) * (size_t)p.k_in + j;
@@ -172,6 +178,65 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_select_kernel(const Merge
     __syncthreads();
     bitonic_sort_smem(buf, np);
     merge_emit(p, q, buf, np);
+}
+
+// ------------------------------------------------------------------------------------------
+// K5x: cross-GPU exchange fused with the merge, over NVLink peer memory (no NCCL call).
+//
+// GPU form of CoordinatorHandler.search's gather + merge (src/coordinator/handler.py:191-216) for G ranks of
+// one box.  Every rank has searched its shard for the whole batch; rank r owns the final answer of query slice
+// r.  One launch per rank:
+//   phase 1  pack (distance, id) into sortable keys and STORE each query's list straight into the owner's
+//            receive buffer (peer pointers opened with CUDA IPC; coalesced 8-byte stores over NVLink)
+//   phase 2  the last CTA to finish phase 1 publishes this step's number in every peer's flag word
+//            (system-scope fence + store)
+//   phase 3  wait until all G flags carry this step, then merge the G lists of each owned query
+// Receive buffers are double-buffered by step parity: a rank can only be two steps ahead of a peer after that
+// peer has pushed the step in between, which it does after finishing its merge of the older step.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MERGE_THREADS) exchange_merge_kernel(const XchgParams x, const MergeParams mp) {
+    __shared__ uint64_t buf[MERGE_BUF];
+    __shared__ int s_last;
+    const size_t total = x.nq * (size_t)x.k;
+    for (size_t i = blockIdx.x * (size_t)MERGE_THREADS + threadIdx.x; i < total; i += (size_t)gridDim.x * MERGE_THREADS) {
+        const size_t q = i / x.k;
+        const int j = (int)(i - q * x.k);
+        const int dst = (int)(q / x.slice);
+        const size_t ql = q - (size_t)dst * x.slice;
+        const int64_t id = x.ids[i];
+        const uint64_t key = id < 0 ? KEY_SENTINEL : make_key(x.dist[i], (uint32_t)id);
+        x.peer_buf[dst][(size_t)x.parity * x.stride_parity + (size_t)x.rank * x.stride_src + ql * x.k + j] = key;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(x.done_counter, 1u) == gridDim.x - 1 ? 1 : 0;
+    __syncthreads();
+    if (s_last) {
+        __threadfence_system();
+        if (threadIdx.x < x.world)
+            *reinterpret_cast<volatile uint32_t*>(x.peer_flag[threadIdx.x] + x.parity * x.world + x.rank) = x.step;
+    }
+    if (threadIdx.x < x.world) {
+        const volatile uint32_t* f = x.local_flag + x.parity * x.world + threadIdx.x;
+        while (*f < x.step) __nanosleep(200);
+    }
+    __threadfence_system();
+    __syncthreads();
+    for (size_t ql = blockIdx.x; ql < x.slice; ql += gridDim.x) {
+        merge_stream(mp, ql, buf);
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_exchange_merge(const XchgParams& x, const MergeParams& mp, int num_sms, cudaStream_t st) {
+    if (mp.k_out < 1 || mp.k_out > MERGE_BUF / 2) return cudaErrorInvalidValue;
+    cudaError_t e = cudaMemsetAsync(x.done_counter, 0, sizeof(unsigned int), st);
+    if (e != cudaSuccess) return e;
+    // every CTA waits for the peers in phase 3: keep the grid co-resident (no CTA may queue behind a waiting one)
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((size_t)num_sms * 2, std::max(x.slice, (x.nq * x.k + MERGE_THREADS - 1) / MERGE_THREADS)));
+    exchange_merge_kernel<<<grid, MERGE_THREADS, 0, st>>>(x, mp);
+    count_launch();
+    return cudaGetLastError();
 }
 
 cudaError_t launch_merge_topk(const MergeParams& p, cudaStream_t st) {

@@ -878,6 +878,109 @@ int vdb_merge_topk(const float* dist, const int64_t* ids, int G, size_t nq, int 
     return VDB_OK;
 }
 
+
+// ---- K5x: exchange + merge over NVLink peer memory -------------------------------------------
+struct vdb_xchg {
+    int device = 0, rank = 0, world = 1, num_sms = 148;
+    size_t max_slice = 0; int max_k = 0;
+    size_t stride_src = 0, stride_parity = 0, flag_bytes = 0, total_bytes = 0;
+    uint8_t* base = nullptr;                       // local allocation: [flags][keys]
+    uint8_t* peer_base[XCHG_MAX_WORLD] = {};       // peer mappings ([rank] == base)
+    bool connected = false;
+    unsigned int* done_counter = nullptr;
+    uint32_t step = 0;
+    std::mutex mu;
+};
+
+int vdb_xchg_create(int device, int rank, int world, size_t max_slice, int max_k, vdb_xchg_t** out, unsigned char* handle64) {
+    if (!out || !handle64) return fail(VDB_EINVAL, "null argument");
+    *out = nullptr;
+    if (world < 1 || world > XCHG_MAX_WORLD || rank < 0 || rank >= world) return fail(VDB_EINVAL, "bad rank/world (at most 16 ranks)");
+    if (max_slice < 1 || max_k < 1 || max_k > K_MAX) return fail(VDB_EINVAL, "bad max_slice/max_k");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CU_TRY(cudaSetDevice(device));
+    auto x = std::make_unique<vdb_xchg>();
+    x->device = device; x->rank = rank; x->world = world; x->max_slice = max_slice; x->max_k = max_k;
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    x->num_sms = prop.multiProcessorCount;
+    x->flag_bytes = 256;                                             // 2 * world u32, padded
+    x->stride_src = max_slice * (size_t)max_k;                       // keys per source rank
+    x->stride_parity = x->stride_src * world;
+    x->total_bytes = x->flag_bytes + 2 * x->stride_parity * sizeof(uint64_t);
+    CU_TRY(cudaMalloc((void**)&x->base, x->total_bytes));
+    CU_TRY(cudaMemset(x->base, 0, x->flag_bytes));
+    CU_TRY(cudaMalloc((void**)&x->done_counter, sizeof(unsigned int)));
+    CU_TRY(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    CU_TRY(cudaIpcGetMemHandle(&h, x->base));
+    memcpy(handle64, &h, 64);
+    x->peer_base[rank] = x->base;
+    *out = x.release();
+    return VDB_OK;
+}
+
+int vdb_xchg_connect(vdb_xchg_t* x, const unsigned char* handles) {
+    if (!x || !handles) return fail(VDB_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(x->mu);
+    if (x->connected) return VDB_OK;
+    CU_TRY(cudaSetDevice(x->device));
+    for (int r = 0; r < x->world; ++r) {
+        if (r == x->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + 64 * (size_t)r, 64);
+        void* p = nullptr;
+        CU_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        x->peer_base[r] = (uint8_t*)p;
+    }
+    x->connected = true;
+    return VDB_OK;
+}
+
+int vdb_xchg_merge_dev(vdb_xchg_t* x, const float* d_dist, const int64_t* d_ids, size_t nq, int k, float* o_dist,
+                       int64_t* o_ids, void* stream) {
+    if (!x || !d_dist || !d_ids || !o_dist || !o_ids) return fail(VDB_EINVAL, "null argument");
+    if (!x->connected && x->world > 1) return fail(VDB_EINVAL, "vdb_xchg_connect has not been called");
+    if (nq == 0 || nq % x->world) return fail(VDB_EINVAL, "the batch must divide by the number of ranks");
+    const size_t slice = nq / x->world;
+    if (slice > x->max_slice || k < 1 || k > x->max_k) return fail(VDB_EINVAL, "batch slice or k beyond what the exchange was created for");
+    std::lock_guard<std::mutex> lk(x->mu);
+    CU_TRY(cudaSetDevice(x->device));
+    XchgParams xp{};
+    xp.rank = x->rank; xp.world = x->world;
+    xp.step = ++x->step;
+    xp.parity = (int)(xp.step & 1);
+    xp.nq = nq; xp.slice = slice; xp.k = k;
+    xp.ids = d_ids; xp.dist = d_dist;
+    // strides follow this call's k and slice: every rank computes the same values from the same (nq, k)
+    xp.stride_src = slice * (size_t)k;
+    xp.stride_parity = x->stride_parity;
+    for (int r = 0; r < x->world; ++r) {
+        xp.peer_flag[r] = reinterpret_cast<uint32_t*>(x->peer_base[r]);
+        xp.peer_buf[r] = reinterpret_cast<uint64_t*>(x->peer_base[r] + x->flag_bytes);
+    }
+    xp.local_flag = reinterpret_cast<const uint32_t*>(x->base);
+    xp.done_counter = x->done_counter;
+    MergeParams mp{};
+    mp.in_keys = reinterpret_cast<const uint64_t*>(x->base + x->flag_bytes) + (size_t)xp.parity * x->stride_parity;
+    mp.G = x->world; mp.k_in = k; mp.key_stride_g = xp.stride_src;
+    mp.nq = slice; mp.n_in = x->world * k; mp.k_out = k;
+    mp.out_ids = o_ids; mp.out_dist = o_dist;
+    CU_TRY(launch_exchange_merge(xp, mp, x->num_sms, (cudaStream_t)stream));
+    return VDB_OK;
+}
+
+void vdb_xchg_destroy(vdb_xchg_t* x) {
+    if (!x) return;
+    cudaSetDevice(x->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < x->world; ++r)
+        if (r != x->rank && x->peer_base[r]) cudaIpcCloseMemHandle(x->peer_base[r]);
+    if (x->base) cudaFree(x->base);
+    if (x->done_counter) cudaFree(x->done_counter);
+    delete x;
+}
+
 int vdb_set_option(vdb_t* db, const char* name, long value) {
     if (!db || !name) return fail(VDB_EINVAL, "null argument");
     if (!strcmp(name, "path")) { db->opt_path.store(value); return VDB_OK; }

@@ -101,6 +101,23 @@ int vdb_load(const char *path, size_t capacity, int device, vdb_t **out);
 int vdb_merge_topk(const float *dist, const int64_t *ids, int G, size_t nq, int k_in, int k_out,
                    float *o_dist, int64_t *o_ids, int on_device, int device, void *stream);
 
+/* The same gather + merge (coordinator/handler.py:191-216) for G ranks of ONE box, fused into one kernel over
+ * NVLink peer memory instead of a collective library call: every rank has searched its shard for the whole
+ * batch; rank r owns the answers of queries [r*nq/G, (r+1)*nq/G).  The kernel stores each query's list into
+ * the owner's receive buffer (CUDA-IPC peer pointers), signals, waits for the G-1 peers and merges its slice.
+ *   create : allocates this rank's receive buffer, returns its 64-byte IPC handle
+ *   connect: takes all G handles (rank order; exchange them with any out-of-band channel, e.g. an all-gather)
+ *   merge  : d_dist/d_ids [nq,k] = this rank's lists (id < 0 = padding) -> o_dist/o_ids [nq/G,k], enqueued on
+ *            `stream`.  Collective: every rank must call it once per step with the same nq and k; one step in
+ *            flight per rank; nothing else may keep the GPU's SMs busy while it waits for its peers. */
+typedef struct vdb_xchg vdb_xchg_t;
+int vdb_xchg_create(int device, int rank, int world, size_t max_slice, int max_k, vdb_xchg_t **out,
+                    unsigned char *handle64);
+int vdb_xchg_connect(vdb_xchg_t *x, const unsigned char *handles /* world * 64 bytes */);
+int vdb_xchg_merge_dev(vdb_xchg_t *x, const float *d_dist, const int64_t *d_ids, size_t nq, int k,
+                       float *o_dist, int64_t *o_ids, void *stream);
+void vdb_xchg_destroy(vdb_xchg_t *x);
+
 /* Introspection for bench.py / tests */
 uint64_t vdb_launch_count(void);              /* kernels this library has launched so far   */
 int vdb_set_option(vdb_t *db, const char *name, long value);

@@ -1,0 +1,100 @@
+"""Two GPUs, one process each: the sharded search with the fused NVLink exchange + merge kernel (K5x,
+vdb_xchg_*) against (a) the same search with NCCL all-to-all + merge kernel and (b) the CPU oracle over the
+whole set.  Skipped on boxes with a single GPU (run with `gpurun --gpus 2`)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from oracle import cpu_ref as R
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, dim, nq, k, metric, steps, out):
+    import torch
+    import torch.distributed as dist
+    import dvdb_b200 as vdb
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        lib = vdb._ffi.lib()
+        lo, hi = vdb.sharding.contiguous_range(n, rank, world)
+        ix = vdb.Index(metric, dim, device=rank)
+        ix.init_index(hi - lo)
+        ix.add_items(R.synth_rows(R.SEED_DB, lo, hi - lo, dim), np.arange(lo, hi))
+        stream = torch.cuda.current_stream().cuda_stream
+
+        def gather_handles(mine: bytes):
+            t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(dev)
+            o = torch.empty((world, 64), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(o, t)
+            return [bytes(o[r].cpu().numpy().tobytes()) for r in range(world)]
+
+        px = vdb.PeerExchange(rank, rank, world, max_slice=nq // world, max_k=k, exchange_handles=gather_handles)
+        sl = nq // world
+        results = []
+        for step in range(steps):
+            q = torch.from_numpy(R.synth_rows(R.SEED_QUERY, 1000 * step, nq, dim)).to(dev)
+            ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+            dd = torch.empty((nq, k), dtype=torch.float32, device=dev)
+            ix.search_device(q.data_ptr(), nq, k, ids.data_ptr(), dd.data_ptr(), 0, stream)
+            # fused NVLink exchange + merge
+            o_ids = torch.empty((sl, k), dtype=torch.int64, device=dev)
+            o_dd = torch.empty((sl, k), dtype=torch.float32, device=dev)
+            px.merge(dd.data_ptr(), ids.data_ptr(), nq, k, o_dd.data_ptr(), o_ids.data_ptr(), stream)
+            # NCCL all-to-all + merge kernel
+            g_ids, g_dd = torch.empty_like(ids), torch.empty_like(dd)
+            dist.all_to_all_single(g_ids, ids)
+            dist.all_to_all_single(g_dd, dd)
+            n_ids = torch.empty((sl, k), dtype=torch.int64, device=dev)
+            n_dd = torch.empty((sl, k), dtype=torch.float32, device=dev)
+            vdb._ffi.check(lib.vdb_merge_topk(g_dd.data_ptr(), g_ids.data_ptr(), world, sl, k, k, n_dd.data_ptr(),
+                                              n_ids.data_ptr(), 1, rank, stream), "merge")
+            torch.cuda.synchronize()
+            assert torch.equal(o_ids, n_ids) and torch.equal(o_dd, n_dd), f"rank {rank} step {step}: p2p != nccl"
+            results.append((o_ids.cpu().numpy(), o_dd.cpu().numpy()))
+        out.put((rank, results))
+        dist.barrier()
+        px.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("metric,nq,k", [("cosine", 64, 10), ("l2", 6, 100)])
+def test_peer_exchange_equals_nccl_and_oracle(metric, nq, k):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    n, dim, world, steps = 4000, 512, 2, 3
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, dim, nq, k, metric, steps, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(out.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    stored = R.prepare_rows(R.synth_rows(R.SEED_DB, 0, n, dim), metric)
+    sl = nq // world
+    for step in range(steps):
+        q = R.synth_rows(R.SEED_QUERY, 1000 * step, nq, dim)
+        for r in range(world):
+            ids, dd = got[r][step]
+            for i in range(sl):
+                msg = R.check_topk(ids[i], dd[i], q[r * sl + i], stored, np.arange(n), k, metric, rtol=1e-5)
+                assert msg is None, f"step {step} rank {r} query {i}: {msg}"
