@@ -342,30 +342,48 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const int base = (warp - 2) * (GT_EPI_THREADS / 2);    // each mover warp serves half of the rings
             volatile uint32_t* v_head = ctl->head_pub;
             volatile uint32_t* v_tail = ctl->tail;
+            constexpr int RPL = GT_EPI_THREADS / 64;      // rings per lane
             for (;;) {
                 const bool fin = *reinterpret_cast<volatile uint32_t*>(&ctl->done) == GT_EPI_WARPS;
                 __threadfence_block();
+                // round: look at all rings of this lane, reserve room for all of them at once (the atomics'
+                // round trips overlap), then copy
+                uint32_t t[RPL], n[RPL], q[RPL];
+                int slot[RPL];
                 bool moved = false;
 #pragma unroll
-                for (int h = 0; h < GT_EPI_THREADS / 64; ++h) {
+                for (int h = 0; h < RPL; ++h) {
                     const int ri = base + h * 32 + lane;          // ring == epilogue thread
-                    const uint32_t t = v_tail[ri];
-                    const uint32_t n = v_head[ri] - t;
-                    if (n) {
-                        __threadfence_block();
-                        const uint32_t q = *reinterpret_cast<volatile uint32_t*>(&ctl->qbase[ri >> 5]) + (ri & 31);
-                        const int slot = atomicAdd(p.cnt + q, (int)n);
-                        const uint64_t* ring = ring_all + (size_t)ri * GT_RING_STRIDE;
-                        uint64_t* dst = p.buf + (size_t)q * p.cap;
-                        for (uint32_t i = 0; i < n; ++i) {
-                            const uint64_t key = *reinterpret_cast<const volatile uint64_t*>(ring + ((t + i) % GT_RING));
-                            if (slot + (int)i < p.cap) dst[slot + i] = key;     // beyond cap: counted, flagged by K2s
-                        }
-                        __threadfence_block();
-                        v_tail[ri] = t + n;
-                        moved = true;
+                    t[h] = v_tail[ri];
+                    n[h] = v_head[ri] - t[h];
+                    moved |= n[h] != 0;
+                }
+                __threadfence_block();
+#pragma unroll
+                for (int h = 0; h < RPL; ++h) {
+                    const int ri = base + h * 32 + lane;
+                    slot[h] = 0;
+                    if (n[h]) {
+                        q[h] = *reinterpret_cast<volatile uint32_t*>(&ctl->qbase[ri >> 5]) + (ri & 31);
+                        slot[h] = atomicAdd(p.cnt + q[h], (int)n[h]);
                     }
                 }
+#pragma unroll
+                for (int h = 0; h < RPL; ++h) {
+                    if (n[h]) {
+                        const int ri = base + h * 32 + lane;
+                        const uint64_t* ring = ring_all + (size_t)ri * GT_RING_STRIDE;
+                        uint64_t* dst = p.buf + (size_t)q[h] * p.cap;
+                        for (uint32_t i = 0; i < n[h]; ++i) {
+                            const uint64_t key = *reinterpret_cast<const volatile uint64_t*>(ring + ((t[h] + i) % GT_RING));
+                            if (slot[h] + (int)i < p.cap) dst[slot[h] + i] = key;     // beyond cap: counted, flagged by K2s
+                        }
+                    }
+                }
+                __threadfence_block();
+#pragma unroll
+                for (int h = 0; h < RPL; ++h)
+                    if (n[h]) v_tail[base + h * 32 + lane] = t[h] + n[h];
                 if (!__any_sync(0xffffffffu, moved)) {
                     if (fin) break;
                     __nanosleep(100);
