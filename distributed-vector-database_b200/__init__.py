@@ -7,11 +7,11 @@ name the build contract asks for.  Importing the package loads no native code; t
 from . import _ffi
 from .coordinator import LocalCoordinator, PeerExchange, ShardedSearcher, merge_search_results
 from .handler import GpuVectorNodeHandler
-from .index import Index, launch_count, merge_topk
+from .index import Index, launch_count, merge_topk, pinned_empty
 from .sharding import assign_shards_to_nodes, get_shard_id
 from .ttypes import Response, SearchRequest, SearchResult, VectorData
 from .wal import WALManager
 
-__all__ = ["Index", "merge_topk", "launch_count", "_ffi", "GpuVectorNodeHandler", "LocalCoordinator",
+__all__ = ["Index", "merge_topk", "pinned_empty", "launch_count", "_ffi", "GpuVectorNodeHandler", "LocalCoordinator",
            "ShardedSearcher", "PeerExchange", "merge_search_results", "WALManager", "get_shard_id", "assign_shards_to_nodes",
            "VectorData", "SearchRequest", "SearchResult", "Response"]

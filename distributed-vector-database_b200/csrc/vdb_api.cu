@@ -374,6 +374,16 @@ int search_core(vdb* db, Workspace* ws, const float* d_q_raw, size_t nq, int k, 
     return fail(VDB_ECUDA, "internal: unreachable search path");
 }
 
+bool is_pinned_host(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
 int check_k(const vdb* db, int k, size_t nq) {
     if (k < 1 || k > K_MAX) return fail(VDB_EINVAL, "k must be in [1, 1024]");
     const int nq_t = nq >= 8 ? 8 : nq >= 4 ? 4 : nq >= 2 ? 2 : 1;
@@ -636,21 +646,41 @@ int vdb_search(vdb_t* db, const float* queries, size_t nq, int k, int64_t* out_l
     CU_TRY(grow(ws->d_cnt, ws->cnt_cap, nq));
     const size_t out_bytes = nout * (sizeof(int64_t) + sizeof(float)) + nq * sizeof(int);
     CU_TRY(grow_host(ws->h_out, ws->h_out_cap, out_bytes));
-    memcpy(ws->h_q, queries, qelems * sizeof(float));
-    CU_TRY(cudaMemcpyAsync(ws->d_q_in, ws->h_q, qelems * sizeof(float), cudaMemcpyHostToDevice, st));
+    // caller buffers that are already page-locked (vdb_host_alloc, cudaHostAlloc/Register, torch pin_memory) are
+    // DMA'd directly; pageable ones go through the workspace's pinned staging buffers
+    const bool q_pinned = is_pinned_host(queries);
+    const bool out_pinned = is_pinned_host(out_labels) && is_pinned_host(out_dist) && (!out_counts || is_pinned_host(out_counts));
+    if (!q_pinned) memcpy(ws->h_q, queries, qelems * sizeof(float));
+    CU_TRY(cudaMemcpyAsync(ws->d_q_in, q_pinned ? queries : ws->h_q, qelems * sizeof(float), cudaMemcpyHostToDevice, st));
     rc = search_core(db, ws, ws->d_q_in, nq, k, ws->d_ids, ws->d_dist, ws->d_cnt, st, n);
     if (rc) { cudaStreamSynchronize(st); return rc; }
     int64_t* h_ids = reinterpret_cast<int64_t*>(ws->h_out);
     float* h_dist = reinterpret_cast<float*>(ws->h_out + nout * sizeof(int64_t));
     int* h_cnt = reinterpret_cast<int*>(ws->h_out + nout * (sizeof(int64_t) + sizeof(float)));
+    if (out_pinned) { h_ids = out_labels; h_dist = out_dist; h_cnt = out_counts; }
     CU_TRY(cudaMemcpyAsync(h_ids, ws->d_ids, nout * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaMemcpyAsync(h_dist, ws->d_dist, nout * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaMemcpyAsync(h_cnt, ws->d_cnt, nq * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (h_cnt) CU_TRY(cudaMemcpyAsync(h_cnt, ws->d_cnt, nq * sizeof(int), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
-    memcpy(out_labels, h_ids, nout * sizeof(int64_t));
-    memcpy(out_dist, h_dist, nout * sizeof(float));
-    if (out_counts) memcpy(out_counts, h_cnt, nq * sizeof(int));
+    if (!out_pinned) {
+        memcpy(out_labels, h_ids, nout * sizeof(int64_t));
+        memcpy(out_dist, h_dist, nout * sizeof(float));
+        if (out_counts) memcpy(out_counts, h_cnt, nq * sizeof(int));
+    }
     return VDB_OK;
+}
+
+void* vdb_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        fail(VDB_ENOMEM, "cudaMallocHost failed");
+        return nullptr;
+    }
+    return p;
+}
+void vdb_host_free(void* p) {
+    if (p) cudaFreeHost(p);
 }
 
 int vdb_search_dev(vdb_t* db, const float* d_queries, size_t nq, int k, int64_t* d_labels, float* d_dist, int* d_counts,

@@ -121,16 +121,24 @@ class Index:
             raise RuntimeError("Cannot return the results in a contiguous 2D array. Probably ef or M is too small")
         return labels.astype(np.uint64), dist
 
-    def knn_query_padded(self, data, k: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    def knn_query_padded(self, data, k: int, out=None) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
         """Exact search that does not fail on short results: labels int64 (-1 padded), distances
-        (+inf padded), counts int32 [nq]."""
+        (+inf padded), counts int32 [nq].  `out` = (labels, dist, counts) arrays to fill (e.g. page-locked
+        ones from `pinned_empty`, which the library reads and writes by DMA without a staging copy)."""
         h = self._handle()
         q = _as_f32_2d(data, self.dim, "query")
         nq = q.shape[0]
         k = int(k)
-        labels = np.empty((nq, k), dtype=np.int64)
-        dist = np.empty((nq, k), dtype=np.float32)
-        counts = np.empty((nq,), dtype=np.int32)
+        if out is not None:
+            labels, dist, counts = out
+            if (labels.shape != (nq, k) or dist.shape != (nq, k) or counts.shape != (nq,) or labels.dtype != np.int64
+                    or dist.dtype != np.float32 or counts.dtype != np.int32
+                    or not (labels.flags.c_contiguous and dist.flags.c_contiguous and counts.flags.c_contiguous)):
+                raise RuntimeError("out must be C-contiguous (int64 [nq,k], float32 [nq,k], int32 [nq])")
+        else:
+            labels = np.empty((nq, k), dtype=np.int64)
+            dist = np.empty((nq, k), dtype=np.float32)
+            counts = np.empty((nq,), dtype=np.int32)
         _ffi.check(_ffi.lib().vdb_search(h, q.ctypes.data_as(_ffi._f32p), nq, k, labels.ctypes.data_as(_ffi._i64p),
                                          dist.ctypes.data_as(_ffi._f32p), counts.ctypes.data_as(_ffi._i32p)),
                    "knn_query")
@@ -192,6 +200,36 @@ class Index:
 
     def get_stat(self, name: str) -> int:
         return int(_ffi.lib().vdb_get_stat(self._handle(), name.encode()))
+
+
+class _PinnedBlock:
+    def __init__(self, nbytes: int):
+        self.ptr = _ffi.lib().vdb_host_alloc(nbytes)
+        if not self.ptr:
+            raise RuntimeError(_ffi.last_error())
+
+    def __del__(self):
+        try:
+            _ffi.lib().vdb_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
+    """numpy array over page-locked host memory (vdb_host_alloc): query / result buffers that
+    `Index.knn_query_padded` moves by DMA with no staging copy.  Freed with the array."""
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
+    blk = _PinnedBlock(max(n * dt.itemsize, 1))
+    buf = (C.c_ubyte * max(n * dt.itemsize, 1)).from_address(blk.ptr)
+    arr = np.frombuffer(buf, dtype=dt, count=n).reshape(shape)
+    _keep_alive[id(buf)] = blk
+    import weakref
+    weakref.finalize(buf, _keep_alive.pop, id(buf), None)
+    return arr
+
+
+_keep_alive = {}
 
 
 def merge_topk(dist: np.ndarray, ids: np.ndarray, k: int, device: int = 0) -> Tuple[np.ndarray, np.ndarray]:

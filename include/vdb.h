@@ -72,6 +72,10 @@ int vdb_unmark_deleted(vdb_t *db, const int64_t *labels, size_t n);
  * fp32 re-rank. */
 int vdb_search(vdb_t *db, const float *queries, size_t nq, int k, int64_t *out_labels,
                float *out_dist, int *out_counts);
+/* Page-locked host buffers for queries / results: vdb_search moves them by DMA without the staging copy it
+ * needs for pageable memory (any page-locked buffer is recognised, these two are a convenience). */
+void *vdb_host_alloc(size_t bytes);
+void vdb_host_free(void *p);
 /* Same with DEVICE pointers, enqueued on `stream` (a cudaStream_t; NULL = default stream),
  * no host synchronisation. */
 int vdb_search_dev(vdb_t *db, const float *d_queries, size_t nq, int k, int64_t *d_labels,

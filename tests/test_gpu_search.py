@@ -137,6 +137,22 @@ def test_save_load_roundtrip(vdb, tmp_path):
         assert np.array_equal(x, y)
 
 
+def test_pinned_buffers_take_the_dma_path(vdb):
+    """page-locked query / result buffers (vdb_host_alloc) give the same answer as pageable ones."""
+    ix, raw = build(vdb, "cosine", 3000)
+    q = R.synth_rows(R.SEED_QUERY, 0, 40, 512)
+    a = ix.knn_query_padded(q, 10)
+    qp = vdb.pinned_empty((40, 512), np.float32)
+    qp[:] = q
+    outs = (vdb.pinned_empty((40, 10), np.int64), vdb.pinned_empty((40, 10), np.float32), vdb.pinned_empty((40,), np.int32))
+    b = ix.knn_query_padded(qp, 10, out=outs)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    assert b[0] is outs[0]
+    with pytest.raises(RuntimeError):
+        ix.knn_query_padded(qp, 10, out=(outs[0][:, :5], outs[1], outs[2]))
+
+
 def test_device_synthetic_rows_bit_identical(vdb):
     """the on-device generator == the oracle's generator, so 10M-row sets can be spot-checked."""
     ix = vdb.Index("ip", 512)
