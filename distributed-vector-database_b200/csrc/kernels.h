@@ -20,7 +20,7 @@ struct ScanParams {
     int nq;                  // 1..8
     int k;
     int metric;              // 0 = squared L2 (direct form), 1 = 1 - dot
-    int stages;              // filled by the launcher
+    int stages, ring;        // filled by the launcher (copy-ring stages, candidate-ring slots)
     int dbg;                 // experiments (VDB_SCAN_DBG): 1 = no FMA loop, 2 = no L2 policy hint, 4 = no select
     uint64_t* out_keys;      // [nq][grid][k]
 };

@@ -27,7 +27,9 @@ constexpr int SCAN_WARPS = 8;
 constexpr int SCAN_R = 2;                                  // rows per consumer warp per stage
 constexpr int SCAN_STAGE_ROWS = SCAN_WARPS * SCAN_R;       // 16
 constexpr int SCAN_THREADS = (SCAN_WARPS + 2) * 32;        // + producer warp + selector warp
-constexpr int SCAN_RING = 512;                             // candidate ring slots (power of two)
+constexpr int SCAN_RING_SMALL = 512;                       // candidate ring slots (power of two), k <= 32
+constexpr int SCAN_RING_LARGE = 4096;                      // k > 32: an insert costs O(k/32) and the first rounds of a
+                                                           // scan pass everything, so the ring must absorb a longer burst
 
 template <typename T> struct Elem;
 template <> struct Elem<float> {
@@ -94,17 +96,18 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_topk_kernel(const ScanPa
     uint8_t* stage_base = smem;
     float* qs = reinterpret_cast<float*>(smem + (size_t)stages * stage_bytes);          // [NQ][ld]
     uint64_t* lists = reinterpret_cast<uint64_t*>(qs + (size_t)NQ * p.ld);                // [NQ][k]
-    uint64_t* ring = lists + (size_t)NQ * p.k;                                            // [SCAN_RING]
-    uint64_t* full = ring + SCAN_RING;
+    const uint32_t ring_n = (uint32_t)p.ring, ring_mask = ring_n - 1;
+    uint64_t* ring = lists + (size_t)NQ * p.k;                                            // [ring_n]
+    uint64_t* full = ring + ring_n;
     uint64_t* empty = full + stages;
     ScanCtl* ctl = reinterpret_cast<ScanCtl*>(empty + stages);
-    uint8_t* ring_q = reinterpret_cast<uint8_t*>(ctl + 1);                                // [SCAN_RING]
+    uint8_t* ring_q = reinterpret_cast<uint8_t*>(ctl + 1);                                // [ring_n]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int k = p.k;
 
     for (int i = threadIdx.x; i < NQ * k; i += SCAN_THREADS) lists[i] = KEY_SENTINEL;
-    for (int i = threadIdx.x; i < SCAN_RING; i += SCAN_THREADS) ring[i] = KEY_SENTINEL;
+    for (int i = threadIdx.x; i < (int)ring_n; i += SCAN_THREADS) ring[i] = KEY_SENTINEL;
     if (threadIdx.x == 0) {
         ctl->tail = 0; ctl->head = 0; ctl->done = 0;
         for (int s = 0; s < stages; ++s) {
@@ -146,7 +149,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_topk_kernel(const ScanPa
         volatile ScanCtl* vctl = ctl;
         uint32_t head = 0;
         for (;;) {
-            const uint32_t slot = (head + lane) & (SCAN_RING - 1);
+            const uint32_t slot = (head + lane) & ring_mask;
             const uint64_t key = vring[slot];
             const uint32_t ready = __ballot_sync(0xffffffffu, key != KEY_SENTINEL);
             const int n = (ready == 0xffffffffu) ? 32 : __ffs(~ready) - 1;   // leading run of written slots
@@ -281,10 +284,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_topk_kernel(const ScanPa
                 uint32_t base = 0;
                 if (lane == leader) base = atomicAdd(&ctl->tail, (uint32_t)n);
                 base = __shfl_sync(0xffffffffu, base, leader);
-                while ((int)(base + n - vctl->head) > SCAN_RING) {
+                while ((int)(base + n - vctl->head) > (int)ring_n) {
                 }
                 if (pass) {
-                    const uint32_t slot = (base + __popc(m & ((1u << lane) - 1))) & (SCAN_RING - 1);
+                    const uint32_t slot = (base + __popc(m & ((1u << lane) - 1))) & ring_mask;
                     ring_q[slot] = (uint8_t)qi;
                     __threadfence_block();
                     reinterpret_cast<volatile uint64_t*>(ring)[slot] = make_key(dist, label);
@@ -304,8 +307,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_topk_kernel(const ScanPa
     }
 }
 
+static int scan_ring_slots(int k) { return k > 32 ? SCAN_RING_LARGE : SCAN_RING_SMALL; }
 static size_t scan_fixed_smem(int nq_t, int ld, int k, int stages) {
-    return (size_t)nq_t * ld * 4 + (size_t)nq_t * k * 8 + (size_t)SCAN_RING * 9 + (size_t)stages * 16 + 64 + 128;
+    return (size_t)nq_t * ld * 4 + (size_t)nq_t * k * 8 + (size_t)scan_ring_slots(k) * 9 + (size_t)stages * 16 + 64 + 128;
 }
 
 template <typename T, int NQ>
@@ -327,7 +331,8 @@ static cudaError_t launch_t(const ScanParams& p, int grid, size_t smem, cudaStre
 int scan_max_k(int nq_t, int ld, uint32_t row_bytes) {
     const size_t budget = 227 * 1024;
     const size_t min_stage = (size_t)2 * row_bytes * SCAN_STAGE_ROWS;
-    const size_t fixed0 = scan_fixed_smem(nq_t, ld, 0, 8);
+    // conservative: counted with the large candidate ring whatever k turns out to be
+    const size_t fixed0 = scan_fixed_smem(nq_t, ld, 0, 8) + (size_t)(SCAN_RING_LARGE - SCAN_RING_SMALL) * 9;
     if (min_stage + fixed0 >= budget) return 0;
     return (int)((budget - min_stage - fixed0) / ((size_t)nq_t * 8));
 }
@@ -371,6 +376,7 @@ cudaError_t launch_scan_topk(ScanParams p, bool f16, const ScanPlan& pl, cudaStr
     if (pl.grid == 0) return cudaErrorInvalidConfiguration;
     if (const char* e = getenv("VDB_SCAN_DBG")) p.dbg = atoi(e);
     p.stages = pl.stages;
+    p.ring = scan_ring_slots(p.k);
     const size_t smem = pl.smem;
     const int grid = pl.grid;
 #define VDB_SCAN_CASE(NQV)                                                        \
