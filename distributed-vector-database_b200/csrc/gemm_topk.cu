@@ -585,7 +585,8 @@ struct SelectParams {
 
 // Radix select on the 32 distance bits (4 passes of 8 bits): O(n) instead of a full sort.  Keys whose
 // distance bits equal the KP-th value are taken in arrival order until KP are kept.  Output unordered.
-__global__ void __launch_bounds__(256) select_kernel(const SelectParams p) {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) select_kernel(const SelectParams p) {
     extern __shared__ uint64_t sk[];
     __shared__ int hist[256];
     __shared__ uint32_t s_prefix, s_rank;
@@ -600,7 +601,7 @@ __global__ void __launch_bounds__(256) select_kernel(const SelectParams p) {
     if (threadIdx.x == 0) { s_valid = 0; s_c1 = 0; s_c2 = 0; s_prefix = 0; }
     __syncthreads();
     int my_valid = 0;
-    for (int i = threadIdx.x; i < n; i += 256) {
+    for (int i = threadIdx.x; i < n; i += THREADS) {
         uint64_t key = b[i];
         if (key != KEY_SENTINEL) {
             const uint32_t row = (uint32_t)key;
@@ -616,12 +617,12 @@ __global__ void __launch_bounds__(256) select_kernel(const SelectParams p) {
     __syncthreads();
     if (n_valid <= p.kp) {
         // everything valid is kept (no threshold yet)
-        for (int i = threadIdx.x; i < n; i += 256) {
+        for (int i = threadIdx.x; i < n; i += THREADS) {
             const uint64_t key = sk[i];
             if (key != KEY_SENTINEL) b[atomicAdd(&s_c1, 1)] = key;
         }
         __syncthreads();
-        for (int i = n_valid + threadIdx.x; i < p.kp; i += 256) b[i] = KEY_SENTINEL;
+        for (int i = n_valid + threadIdx.x; i < p.kp; i += THREADS) b[i] = KEY_SENTINEL;
         if (threadIdx.x == 0) {
             p.cnt[q] = p.kp;
             p.thr[q] = __int_as_float(0x7f800000);
@@ -632,10 +633,10 @@ __global__ void __launch_bounds__(256) select_kernel(const SelectParams p) {
     uint32_t mask = 0;
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = 24 - 8 * pass;
-        hist[threadIdx.x] = 0;
+        for (int i = threadIdx.x; i < 256; i += THREADS) hist[i] = 0;
         __syncthreads();
         const uint32_t prefix = s_prefix;
-        for (int i = threadIdx.x; i < n; i += 256) {
+        for (int i = threadIdx.x; i < n; i += THREADS) {
             const uint64_t key = sk[i];
             if (key != KEY_SENTINEL) {
                 const uint32_t hi = (uint32_t)(key >> 32);
@@ -674,7 +675,7 @@ __global__ void __launch_bounds__(256) select_kernel(const SelectParams p) {
     const uint32_t T = s_prefix;                  // distance bits of the KP-th best key
     const int need_eq = (int)s_rank;              // how many keys with exactly these bits to keep
     const int n_less = p.kp - need_eq;
-    for (int i = threadIdx.x; i < n; i += 256) {
+    for (int i = threadIdx.x; i < n; i += THREADS) {
         const uint64_t key = sk[i];
         if (key == KEY_SENTINEL) continue;
         const uint32_t hi = (uint32_t)(key >> 32);
@@ -986,7 +987,8 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
     sp.tomb = a.tomb; sp.n_rows = a.n_rows;
     static bool sel_configured = false;
     if (!sel_configured) {
-        if ((e = cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(select_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(select_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return e;
         sel_configured = true;
     }
     int sel_np = 2;
@@ -1019,7 +1021,10 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
         if (a.prof_end) a.prof_end(a.prof_ctx, st);
         if (e != cudaSuccess) return e;
         sp.dense_cnt = level == 0 ? (next - pos) * GT_BN : 0;
-        select_kernel<<<(unsigned)a.nq, 256, (size_t)sel_np * 8, st>>>(sp);
+        // one block per query; thousands of queries with a few hundred keys each: small blocks, so that more
+        // of them are resident and the barrier chain of a block is short
+        if (a.nq >= 4096 && cap <= 1024) select_kernel<64><<<(unsigned)a.nq, 64, (size_t)sel_np * 8, st>>>(sp);
+        else select_kernel<256><<<(unsigned)a.nq, 256, (size_t)sel_np * 8, st>>>(sp);
         count_launch();
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         pos = next;

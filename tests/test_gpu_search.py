@@ -333,3 +333,17 @@ def test_tensor_path_large_batch_vs_scan(vdb):
             bad += 1
     assert bad < 16          # only distance ties within tolerance may differ
     np.testing.assert_allclose(dt, want_d, rtol=RTOL, atol=RTOL)
+
+
+def test_tensor_path_batch_4096_small_blocks_select(vdb):
+    """batches of >= 4096 queries take the 64-thread threshold-selection blocks: tensor path == scan path."""
+    ix = vdb.Index("cosine", 512)
+    ix.init_index(30000)
+    ix.add_synthetic(R.SEED_DB, 0, 30000)
+    q = R.synth_rows(R.SEED_QUERY, 0, 4096, 512)
+    ix.set_option("path", 2)
+    a = ix.knn_query_padded(q, 10)
+    ix.set_option("path", 1)
+    b = ix.knn_query_padded(q[-200:], 10)
+    assert np.array_equal(a[0][-200:], b[0]) and np.array_equal(a[1][-200:], b[1])
+    assert ix.get_stat("fallback_queries") == 0
