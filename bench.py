@@ -219,7 +219,7 @@ def run_ours(a):
 
     def exchange_buffers(nq):
         """N>1: per-rank lists [nq,k] -> all-to-all by query slice -> [world, nq/world, k] on the owner of the slice"""
-        sl = nq // world
+        sl = (nq + world - 1) // world
         return (torch.empty((world, sl, a.k), dtype=torch.int64, device=dev),
                 torch.empty((world, sl, a.k), dtype=torch.float32, device=dev),
                 torch.empty((sl, a.k), dtype=torch.int64, device=dev),
@@ -247,7 +247,7 @@ def run_ours(a):
 
     def device_leg(nq, steps, warmup):
         """queries + results resident in HBM; returns (seconds for `steps`, dominant-kernel ns, launches)"""
-        sharded = world > 1 and nq % world == 0
+        sharded = world > 1 and (nq % world == 0 or px is not None)    # K5x takes ragged batches (a single query)
         q = make_queries(nq)
         ids = torch.empty((nq, a.k), dtype=torch.int64, device=dev)
         dd = torch.empty((nq, a.k), dtype=torch.float32, device=dev)
@@ -299,7 +299,7 @@ def run_ours(a):
 
     def e2e_leg(nq, steps, warmup):
         """through the public host-buffer API: H2D of the queries and D2H of the results inside the timed region"""
-        sharded = world > 1 and nq % world == 0
+        sharded = world > 1 and (nq % world == 0 or px is not None)
         qh = vdb.pinned_empty((nq, a.dim), np.float32)   # page-locked host buffers, filled outside the timed region
         qh[:] = make_queries(nq).cpu().numpy()
         outs = (vdb.pinned_empty((nq, a.k), np.int64), vdb.pinned_empty((nq, a.k), np.float32),

@@ -53,7 +53,7 @@ constexpr int XCHG_MAX_WORLD = 16;
 struct XchgParams {
     int rank, world, parity;
     uint32_t step;                 // 1, 2, 3, ... (flags start at 0)
-    size_t nq, slice;              // global batch, queries owned per rank (nq == slice * world)
+    size_t nq, slice, owned;       // global batch; slice = ceil(nq / world); queries this rank owns (<= slice)
     int k;
     const int64_t* ids;            // this rank's lists [nq][k] (id < 0 = padding)
     const float* dist;

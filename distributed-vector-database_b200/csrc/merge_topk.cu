@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) exchange_merge_kernel(const Xch
     }
     __threadfence_system();
     __syncthreads();
-    for (size_t ql = blockIdx.x; ql < x.slice; ql += gridDim.x) {
+    for (size_t ql = blockIdx.x; ql < x.owned; ql += gridDim.x) {   // queries this rank owns (ragged last slice)
         merge_stream(mp, ql, buf);
         __syncthreads();
     }

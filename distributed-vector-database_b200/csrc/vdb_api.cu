@@ -971,8 +971,8 @@ int vdb_xchg_merge_dev(vdb_xchg_t* x, const float* d_dist, const int64_t* d_ids,
                        int64_t* o_ids, void* stream) {
     if (!x || !d_dist || !d_ids || !o_dist || !o_ids) return fail(VDB_EINVAL, "null argument");
     if (!x->connected && x->world > 1) return fail(VDB_EINVAL, "vdb_xchg_connect has not been called");
-    if (nq == 0 || nq % x->world) return fail(VDB_EINVAL, "the batch must divide by the number of ranks");
-    const size_t slice = nq / x->world;
+    if (nq == 0) return fail(VDB_EINVAL, "empty batch");
+    const size_t slice = (nq + x->world - 1) / x->world;     // rank r owns queries [r*slice, min(nq, (r+1)*slice))
     if (slice > x->max_slice || k < 1 || k > x->max_k) return fail(VDB_EINVAL, "batch slice or k beyond what the exchange was created for");
     std::lock_guard<std::mutex> lk(x->mu);
     CU_TRY(cudaSetDevice(x->device));
@@ -981,6 +981,7 @@ int vdb_xchg_merge_dev(vdb_xchg_t* x, const float* d_dist, const int64_t* d_ids,
     xp.step = ++x->step;
     xp.parity = (int)(xp.step & 1);
     xp.nq = nq; xp.slice = slice; xp.k = k;
+    { const size_t lo = std::min(nq, (size_t)x->rank * slice), hi = std::min(nq, lo + slice); xp.owned = hi - lo; }
     xp.ids = d_ids; xp.dist = d_dist;
     // strides follow this call's k and slice: every rank computes the same values from the same (nq, k)
     xp.stride_src = slice * (size_t)k;
@@ -994,7 +995,7 @@ int vdb_xchg_merge_dev(vdb_xchg_t* x, const float* d_dist, const int64_t* d_ids,
     MergeParams mp{};
     mp.in_keys = reinterpret_cast<const uint64_t*>(x->base + x->flag_bytes) + (size_t)xp.parity * x->stride_parity;
     mp.G = x->world; mp.k_in = k; mp.key_stride_g = xp.stride_src;
-    mp.nq = slice; mp.n_in = x->world * k; mp.k_out = k;
+    mp.nq = xp.owned; mp.n_in = x->world * k; mp.k_out = k;
     mp.out_ids = o_ids; mp.out_dist = o_dist;
     CU_TRY(launch_exchange_merge(xp, mp, x->num_sms, (cudaStream_t)stream));
     return VDB_OK;

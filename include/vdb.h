@@ -111,8 +111,9 @@ int vdb_merge_topk(const float *dist, const int64_t *ids, int G, size_t nq, int 
  * the owner's receive buffer (CUDA-IPC peer pointers), signals, waits for the G-1 peers and merges its slice.
  *   create : allocates this rank's receive buffer, returns its 64-byte IPC handle
  *   connect: takes all G handles (rank order; exchange them with any out-of-band channel, e.g. an all-gather)
- *   merge  : d_dist/d_ids [nq,k] = this rank's lists (id < 0 = padding) -> o_dist/o_ids [nq/G,k], enqueued on
- *            `stream`.  Collective: every rank must call it once per step with the same nq and k; one step in
+ *   merge  : d_dist/d_ids [nq,k] = this rank's lists (id < 0 = padding) -> o_dist/o_ids [slice,k] with
+ *            slice = ceil(nq/G) (rank r owns queries [r*slice, min(nq,(r+1)*slice)); rows beyond what it owns
+ *            are left untouched), enqueued on `stream`.  Collective: every rank must call it once per step with the same nq and k; one step in
  *            flight per rank; nothing else may keep the GPU's SMs busy while it waits for its peers. */
 typedef struct vdb_xchg vdb_xchg_t;
 int vdb_xchg_create(int device, int rank, int world, size_t max_slice, int max_k, vdb_xchg_t **out,

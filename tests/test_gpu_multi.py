@@ -72,6 +72,79 @@ def _worker(rank, world, port, n, dim, nq, k, metric, steps, out):
         dist.destroy_process_group()
 
 
+def _worker_ragged(rank, world, port, n, dim, k, out):
+    """a single query (and 3 queries) through K5x: rank 0 owns query 0, ragged slices elsewhere"""
+    import torch
+    import torch.distributed as dist
+    import dvdb_b200 as vdb
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        lo, hi = vdb.sharding.contiguous_range(n, rank, world)
+        ix = vdb.Index("l2", dim, device=rank)
+        ix.init_index(hi - lo)
+        ix.add_items(R.synth_rows(R.SEED_DB, lo, hi - lo, dim), np.arange(lo, hi))
+        stream = torch.cuda.current_stream().cuda_stream
+
+        def gather_handles(mine: bytes):
+            t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(dev)
+            o = torch.empty((world, 64), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(o, t)
+            return [bytes(o[r].cpu().numpy().tobytes()) for r in range(world)]
+
+        px = vdb.PeerExchange(rank, rank, world, max_slice=2, max_k=k, exchange_handles=gather_handles)
+        res = {}
+        for nq in (1, 3, 1):
+            sl = (nq + world - 1) // world
+            q = torch.from_numpy(R.synth_rows(R.SEED_QUERY, 7 * nq, nq, dim)).to(dev)
+            ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+            dd = torch.empty((nq, k), dtype=torch.float32, device=dev)
+            ix.search_device(q.data_ptr(), nq, k, ids.data_ptr(), dd.data_ptr(), 0, stream)
+            o_ids = torch.full((sl, k), -7, dtype=torch.int64, device=dev)
+            o_dd = torch.zeros((sl, k), dtype=torch.float32, device=dev)
+            px.merge(dd.data_ptr(), ids.data_ptr(), nq, k, o_dd.data_ptr(), o_ids.data_ptr(), stream)
+            torch.cuda.synchronize()
+            res[nq] = (o_ids.cpu().numpy(), o_dd.cpu().numpy())
+        out.put((rank, res))
+        dist.barrier()
+        px.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_exchange_ragged_batches():
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    n, dim, k, world = 3000, 512, 10, 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_ragged, args=(r, world, port, n, dim, k, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(out.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    stored = R.prepare_rows(R.synth_rows(R.SEED_DB, 0, n, dim), "l2")
+    for nq in (1, 3):
+        sl = (nq + world - 1) // world
+        q = R.synth_rows(R.SEED_QUERY, 7 * nq, nq, dim)
+        for r in range(world):
+            ids, dd = got[r][nq]
+            for i in range(sl):
+                qi = r * sl + i
+                if qi < nq:
+                    msg = R.check_topk(ids[i], dd[i], q[qi], stored, np.arange(n), k, "l2", rtol=1e-5)
+                    assert msg is None, f"nq {nq} rank {r} query {qi}: {msg}"
+                else:
+                    assert (ids[i] == -7).all()          # rows a rank does not own stay untouched
+
+
 @pytest.mark.parametrize("metric,nq,k", [("cosine", 64, 10), ("l2", 6, 100)])
 def test_peer_exchange_equals_nccl_and_oracle(metric, nq, k):
     import torch
