@@ -928,15 +928,35 @@ static int choose_slices(int MB, int n_pos, int num_pairs) {
     return best;
 }
 
+static cudaError_t ensure_ws(GemmWorkspace& ws) {
+    if (ws.impl) return cudaSuccess;
+    auto* w = new GemmWsImpl();
+    cudaError_t e = cudaMalloc((void**)&w->n_flagged, sizeof(int));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&w->h_n_flagged, sizeof(int));
+    if (e != cudaSuccess) { delete w; return e; }
+    ws.impl = w;
+    return cudaSuccess;
+}
+
+cudaError_t gemm_topk_prep_targets(GemmWorkspace& ws, const GemmSearchArgs& a, GemmPrepTargets* out) {
+    cudaError_t e = ensure_ws(ws);
+    if (e != cudaSuccess) return e;
+    auto* w = static_cast<GemmWsImpl*>(ws.impl);
+    const bool g16 = a.f16 || a.shadow != nullptr;
+    const int gld = a.f16 ? a.ld : (a.shadow ? a.ld16 : a.ld);
+    if ((e = grow_dev(w->overflow, w->ovf_cap, a.nq)) != cudaSuccess) return e;
+    if (g16 && (e = grow_dev(w->q16, w->q16_cap, a.nq * (size_t)gld)) != cudaSuccess) return e;
+    out->q16 = g16 ? w->q16 : nullptr;
+    out->gld = gld;
+    out->overflow = w->overflow;
+    out->n_flagged = w->n_flagged;
+    return cudaSuccess;
+}
+
 cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearchArgs& a, cudaStream_t st, std::string& err) {
     if (!plan.impl) plan.impl = new GemmPlanImpl();
-    if (!ws.impl) {
-        auto* w = new GemmWsImpl();
-        cudaError_t e = cudaMalloc((void**)&w->n_flagged, sizeof(int));
-        if (e == cudaSuccess) e = cudaMallocHost((void**)&w->h_n_flagged, sizeof(int));
-        if (e != cudaSuccess) { delete w; return e; }
-        ws.impl = w;
-    }
+    cudaError_t e0 = ensure_ws(ws);
+    if (e0 != cudaSuccess) return e0;
     auto* w = static_cast<GemmWsImpl*>(ws.impl);
     const int kp = kp_for_k(a.k);
     const int cap = cap_for_kp(kp);
@@ -950,7 +970,7 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
     if ((e = grow_dev(w->thr, w->thr_cap, a.nq)) != cudaSuccess) return e;
     if ((e = grow_dev(w->overflow, w->ovf_cap, a.nq)) != cudaSuccess) return e;
     if ((e = grow_dev(w->flags, w->flags_cap, a.nq)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(w->overflow, 0, a.nq * sizeof(int), st)) != cudaSuccess) return e;
+    if (!a.prepped && (e = cudaMemsetAsync(w->overflow, 0, a.nq * sizeof(int), st)) != cudaSuccess) return e;
     // operand planes of the contraction: fp16 rows (fp16 shard, or the fp16 shadow of an fp32 shard) against
     // fp16-rounded queries -> kind::f16; plain fp32 rows against fp32 queries -> kind::tf32
     const bool g16 = a.f16 || a.shadow != nullptr;
@@ -960,9 +980,11 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
     const void* qa = a.q;
     if (g16) {
         if ((e = grow_dev(w->q16, w->q16_cap, a.nq * (size_t)gld)) != cudaSuccess) return e;
-        const size_t n = a.nq * (size_t)gld;
-        f32_to_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a.q, a.ld, w->q16, gld, a.nq);
-        count_launch();
+        if (!a.prepped) {
+            const size_t n = a.nq * (size_t)gld;
+            f32_to_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a.q, a.ld, w->q16, gld, a.nq);
+            count_launch();
+        }
         qa = w->q16;
     }
     CUtensorMap tmA, tmB;
@@ -1012,8 +1034,11 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
         gp.n_items = MB * gp.S;
         const int grid = 2 * std::min(gp.n_items, num_pairs_max);   // whole CTA pairs
         if (level == 0) {
-            // dense level writes fixed positions; positions whose tile is past the end stay sentinel
-            if ((e = cudaMemsetAsync(w->buf, 0xFF, a.nq * (size_t)cap * sizeof(uint64_t), st)) != cudaSuccess) return e;
+            // dense level writes fixed positions; positions whose tile is past the end must read as sentinel:
+            // fill the buffer only when there is such a position (never for shards of a few thousand rows or more)
+            bool all_valid = true;
+            for (int pp = pos; pp < next; ++pp) all_valid = all_valid && (int)bitrev((uint32_t)pp, gp.bits) < n_tiles;
+            if (!all_valid && (e = cudaMemsetAsync(w->buf, 0xFF, a.nq * (size_t)cap * sizeof(uint64_t), st)) != cudaSuccess) return e;
         }
         if (a.prof_begin) a.prof_begin(a.prof_ctx, st);
         if (g16) e = l2 ? launch_gemm<true, true>(tmA, tmB, gp, grid, st) : launch_gemm<true, false>(tmA, tmB, gp, grid, st);
@@ -1031,7 +1056,7 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
         ++level;
     }
 
-    if ((e = cudaMemsetAsync(w->n_flagged, 0, sizeof(int), st)) != cudaSuccess) return e;
+    if (!a.prepped && (e = cudaMemsetAsync(w->n_flagged, 0, sizeof(int), st)) != cudaSuccess) return e;
     RerankParams rp{};
     rp.approx = w->buf; rp.stride = (size_t)cap; rp.overflow = w->overflow; rp.tau = w->thr;
     rp.rows = a.rows; rp.row_bytes = (uint32_t)((size_t)a.ld * esz); rp.ld = a.ld;

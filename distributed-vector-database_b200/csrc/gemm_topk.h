@@ -20,6 +20,7 @@ struct GemmSearchArgs {
     // fp16-rounded queries instead of the fp32 rows (kind::tf32); K4 always re-ranks from `rows`
     const void* shadow = nullptr; int ld16 = 0;
     const float* sqnorm; const uint32_t* labels; const uint32_t* tomb;
+    bool prepped = false;  // the caller filled gemm_topk_prep_targets() while preparing the queries
     const float* q;        // prepared queries [nq][ld] fp32
     const float* qn2;      // [nq]
     size_t nq; int k; int metric;   // 0 = L2, 1 = 1 - dot
@@ -31,6 +32,12 @@ struct GemmSearchArgs {
     void (*prof_end)(void* ctx, cudaStream_t st) = nullptr;
     void* prof_ctx = nullptr;
 };
+
+// Buffers of the workspace that the caller's query-preparation kernel fills / clears for the next
+// gemm_topk_search (saves a conversion kernel and two memsets per batch): fp16 query plane [nq][gld] when the
+// contraction runs in kind::f16, the per-query overflow flags and the flagged-query counter.
+struct GemmPrepTargets { void* q16 = nullptr; int gld = 0; int* overflow = nullptr; int* n_flagged = nullptr; };
+cudaError_t gemm_topk_prep_targets(GemmWorkspace& ws, const struct GemmSearchArgs& a, GemmPrepTargets* out);
 
 bool gemm_topk_supported(int dim, int ld, bool f16, int k, size_t n_rows);
 cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearchArgs& a, cudaStream_t st, std::string& err);

@@ -11,10 +11,15 @@
 namespace vdbk {
 
 __global__ void prepare_queries_kernel(const float* __restrict__ q, size_t nq, int dim, int ld, bool normalize,
-                                       float* __restrict__ out, float* __restrict__ qn2) {
+                                       float* __restrict__ out, float* __restrict__ qn2, __half* __restrict__ out16,
+                                       int ld16, int* __restrict__ zero_per_query, int* __restrict__ zero_one) {
     const size_t w = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
     const int lane = lane_id();
     if (w >= nq) return;
+    if (lane == 0) {      // per-batch flags of the tensor path, cleared here instead of by separate memsets
+        if (zero_per_query) zero_per_query[w] = 0;
+        if (zero_one && w == 0) *zero_one = 0;
+    }
     const float* src = q + w * (size_t)dim;
     float scale = 1.0f;
     if (normalize) {
@@ -27,6 +32,7 @@ __global__ void prepare_queries_kernel(const float* __restrict__ q, size_t nq, i
         for (int e = 0; e < 4; ++e) {
             const float v = (c + e < dim) ? src[c + e] * scale : 0.0f;
             out[w * (size_t)ld + c + e] = v;
+            if (out16 && c + e < ld16) out16[w * (size_t)ld16 + c + e] = __float2half_rn(v);   // fp16 operand copy
             a = fmaf(v, v, a);
         }
     }
@@ -133,9 +139,10 @@ static inline unsigned warp_grid(size_t n_warps, int threads) {
 }
 
 cudaError_t launch_prepare_queries(const float* q, size_t nq, int dim, int ld, bool normalize, float* out, float* qn2,
-                                   cudaStream_t st) {
+                                   cudaStream_t st, void* out16, int ld16, int* zero_per_query, int* zero_one) {
     if (!nq) return cudaSuccess;
-    prepare_queries_kernel<<<warp_grid(nq, 256), 256, 0, st>>>(q, nq, dim, ld, normalize, out, qn2);
+    prepare_queries_kernel<<<warp_grid(nq, 256), 256, 0, st>>>(q, nq, dim, ld, normalize, out, qn2, (__half*)out16, ld16,
+                                                              zero_per_query, zero_one);
     count_launch();
     return cudaGetLastError();
 }

@@ -67,9 +67,11 @@ cudaError_t launch_exchange_merge(const XchgParams& x, const MergeParams& mp, in
 
 // ---- K0 / K3 / utilities (insert.cu) ------------------------------------------------------
 // queries [nq][dim] fp32 -> prepared [nq][ld] fp32 (normalised when cosine, zero padded),
-// qn2[nq] = sum of squares of the prepared query.
+// qn2[nq] = sum of squares of the prepared query.  Optional: fp16 copy [nq][ld16] (operand of the kind::f16
+// contraction) and two flag arrays to clear (zero_per_query[nq], *zero_one).
 cudaError_t launch_prepare_queries(const float* q, size_t nq, int dim, int ld, bool normalize, float* out,
-                                   float* qn2, cudaStream_t st);
+                                   float* qn2, cudaStream_t st, void* out16 = nullptr, int ld16 = 0,
+                                   int* zero_per_query = nullptr, int* zero_one = nullptr);
 // src [n][dim] fp32 -> shard rows [row0 .. row0+n) (T = f32/f16, stride ld), sqnorm, max norm.
 cudaError_t launch_insert_rows(const float* src, size_t n, int dim, int ld, bool normalize, bool f16, void* rows,
                                float* sqnorm, size_t row0, unsigned int* max_sqnorm_bits, cudaStream_t st);

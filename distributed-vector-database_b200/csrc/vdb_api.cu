@@ -326,7 +326,6 @@ int search_core(vdb* db, Workspace* ws, const float* d_q_raw, size_t nq, int k, 
 
     CU_TRY(grow(ws->d_q, ws->q_cap, nq * (size_t)db->ld));
     CU_TRY(grow(ws->d_qn2, ws->qn2_cap, nq));
-    CU_TRY(launch_prepare_queries(d_q_raw, nq, db->dim, db->ld, db->metric == VDB_COSINE, ws->d_q, ws->d_qn2, st));
     if (tensor) {
         GemmSearchArgs a{};
         a.rows = db->rows; a.ld = db->ld; a.dim = db->dim; a.f16 = f16; a.n_rows = (uint32_t)n;
@@ -337,6 +336,13 @@ int search_core(vdb* db, Workspace* ws, const float* d_q_raw, size_t nq, int k, 
         a.d_max_sqnorm_bits = db->d_max_sqnorm;
         a.num_sms = db->num_sms;
         a.out_ids = d_ids; a.out_dist = d_dist; a.out_counts = d_cnt;
+        // one kernel prepares the queries (pad / normalise / norms), writes their fp16 operand copy and clears
+        // the per-batch flags of the tensor path
+        GemmPrepTargets pt;
+        CU_TRY(gemm_topk_prep_targets(ws->gemm, a, &pt));
+        CU_TRY(launch_prepare_queries(d_q_raw, nq, db->dim, db->ld, db->metric == VDB_COSINE, ws->d_q, ws->d_qn2, st,
+                                      pt.q16, pt.gld, pt.overflow, pt.n_flagged));
+        a.prepped = true;
         std::string err;
         ProfScope prof(db, st, true);       // one event pair per launch of the tensor-core kernel
         a.prof_begin = prof_begin_cb; a.prof_end = prof_end_cb; a.prof_ctx = &prof;
