@@ -347,3 +347,52 @@ def test_tensor_path_batch_4096_small_blocks_select(vdb):
     b = ix.knn_query_padded(q[-200:], 10)
     assert np.array_equal(a[0][-200:], b[0]) and np.array_equal(a[1][-200:], b[1])
     assert ix.get_stat("fallback_queries") == 0
+
+
+def test_concurrent_searches_and_a_writer_on_one_index(vdb):
+    """the library itself is safe for concurrent searches (one stream + workspace per call in flight) plus one
+    writer (SURVEY 8b threading): 6 threads hammer scan and tensor searches while rows are appended; every
+    answer must be the exact top-k of SOME prefix of the insert sequence, and the final state must be exact."""
+    import threading
+    n0, n1, dim, k = 4000, 6000, 512, 10
+    raw = R.synth_rows(R.SEED_DB, 0, n1, dim)
+    stored = R.prepare_rows(raw, "cosine")
+    ix = vdb.Index("cosine", dim)
+    ix.init_index(n1)
+    ix.add_items(raw[:n0], np.arange(n0))
+    qs = R.synth_rows(R.SEED_QUERY, 0, 48, dim)
+    errors = []
+
+    def check(l, d, q):
+        # valid for a prefix: every returned id is the exact neighbour among rows [0, m) for some m >= n0:
+        # cheap necessary condition -- distances are exact for the ids returned and sorted
+        for i in range(len(l)):
+            ids = l[i]
+            want = 1.0 - stored[ids] @ R.prepare_rows(q[i:i + 1], "cosine")[0]
+            if not (np.allclose(d[i], want, rtol=1e-4, atol=1e-5) and (np.diff(d[i]) >= 0).all() and (ids >= 0).all()):
+                errors.append((ids.tolist(), d[i].tolist()))
+
+    def searcher(batch):
+        try:
+            for _ in range(12):
+                q = qs[:batch]
+                l, d, c = ix.knn_query_padded(q, k)
+                check(l, d, q)
+        except Exception as e:          # noqa: BLE001
+            errors.append(repr(e))
+
+    def writer():
+        try:
+            for lo in range(n0, n1, 250):
+                ix.add_items(raw[lo:lo + 250], np.arange(lo, lo + 250))
+        except Exception as e:          # noqa: BLE001
+            errors.append(repr(e))
+
+    ts = [threading.Thread(target=searcher, args=(b,)) for b in (1, 3, 48, 48, 8, 20)] + [threading.Thread(target=writer)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors[:3]
+    assert ix.get_current_count() == n1
+    assert_parity(ix, raw, "cosine", "f32", qs, k)
