@@ -37,6 +37,15 @@ __host__ __device__ __forceinline__ uint32_t key_label(uint64_t key) { return ui
 #ifdef __CUDACC__
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+// Programmatic dependent launch: every kernel of the search chain starts with this.  launch_dependents lets the
+// NEXT kernel of the stream be set up (and its CTAs placed where resources allow) while this one runs; wait
+// blocks until the PREVIOUS kernel has completed and its writes are visible.  Placed before the first global
+// access, so the chain behaves exactly like plain stream order minus the launch gaps.
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // Canonical cross-lane sum: butterfly xor 16,8,4,2,1.  Every kernel that reports a distance
 // uses this tree on per-lane partials built in the same element order, so the scan kernel and
 // the re-rank kernel return bit-identical distances for the same (query,row).
@@ -161,5 +170,24 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
     return p;
 }
 #endif  // __CUDACC__
+
+#ifdef __CUDACC__
+// Host: launch `kern` with programmatic stream serialisation allowed (VDB_PDL=0 falls back to a plain launch).
+bool pdl_enabled();
+template <typename... P, typename... A>
+inline cudaError_t launch_pdl(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...);
+}
+#endif
 
 }  // namespace vdbk

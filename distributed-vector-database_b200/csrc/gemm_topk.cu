@@ -236,6 +236,7 @@ __device__ __forceinline__ ItemRange item_range(const GemmParams& p, int item) {
 template <bool F16, bool L2>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GT_THREADS, 1)
 gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    pdl_prologue();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* ring_all = reinterpret_cast<uint64_t*>(smem + GT_OFF_RING);
@@ -587,6 +588,7 @@ struct SelectParams {
 // distance bits equal the KP-th value are taken in arrival order until KP are kept.  Output unordered.
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) select_kernel(const SelectParams p) {
+    pdl_prologue();
     extern __shared__ uint64_t sk[];
     __shared__ int hist[256];
     __shared__ uint32_t s_prefix, s_rank;
@@ -715,6 +717,7 @@ struct RerankParams {
 
 template <typename T, int KP>
 __global__ void __launch_bounds__(256) rerank_kernel(const RerankParams p) {
+    pdl_prologue();
     __shared__ uint64_t ek[KP];
     const int q = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t* ap = p.approx + (size_t)q * p.stride;
@@ -895,22 +898,23 @@ static cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, c
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    gemm_filter_kernel<F16, L2><<<grid, GT_THREADS, GT_SMEM_BYTES_FILTER, st>>>(tmA, tmB, gp);
+    cudaError_t e = launch_pdl(gemm_filter_kernel<F16, L2>, dim3(grid), dim3(GT_THREADS), GT_SMEM_BYTES_FILTER, st, tmA, tmB, gp);
     count_launch();
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 template <typename T>
 static cudaError_t launch_rerank(int kp, const RerankParams& rp, size_t nq, cudaStream_t st) {
+    cudaError_t le = cudaSuccess;
     switch (kp) {
-        case 32: rerank_kernel<T, 32><<<(unsigned)nq, 256, 0, st>>>(rp); break;
-        case 64: rerank_kernel<T, 64><<<(unsigned)nq, 256, 0, st>>>(rp); break;
-        case 128: rerank_kernel<T, 128><<<(unsigned)nq, 256, 0, st>>>(rp); break;
-        case 256: rerank_kernel<T, 256><<<(unsigned)nq, 256, 0, st>>>(rp); break;
+        case 32: le = launch_pdl(rerank_kernel<T, 32>, dim3((unsigned)nq), dim3(256), 0, st, rp); break;
+        case 64: le = launch_pdl(rerank_kernel<T, 64>, dim3((unsigned)nq), dim3(256), 0, st, rp); break;
+        case 128: le = launch_pdl(rerank_kernel<T, 128>, dim3((unsigned)nq), dim3(256), 0, st, rp); break;
+        case 256: le = launch_pdl(rerank_kernel<T, 256>, dim3((unsigned)nq), dim3(256), 0, st, rp); break;
         default: return cudaErrorInvalidValue;
     }
     count_launch();
-    return cudaGetLastError();
+    return le != cudaSuccess ? le : cudaGetLastError();
 }
 
 // slices of a level's position range: fill the pairs in whole waves, prefer few slices
@@ -1048,10 +1052,10 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
         sp.dense_cnt = level == 0 ? (next - pos) * GT_BN : 0;
         // one block per query; thousands of queries with a few hundred keys each: small blocks, so that more
         // of them are resident and the barrier chain of a block is short
-        if (a.nq >= 4096 && cap <= 1024) select_kernel<64><<<(unsigned)a.nq, 64, (size_t)sel_np * 8, st>>>(sp);
-        else select_kernel<256><<<(unsigned)a.nq, 256, (size_t)sel_np * 8, st>>>(sp);
+        if (a.nq >= 4096 && cap <= 1024) e = launch_pdl(select_kernel<64>, dim3((unsigned)a.nq), dim3(64), (size_t)sel_np * 8, st, sp);
+        else e = launch_pdl(select_kernel<256>, dim3((unsigned)a.nq), dim3(256), (size_t)sel_np * 8, st, sp);
         count_launch();
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) return e;
         pos = next;
         ++level;
     }

@@ -13,6 +13,7 @@ namespace vdbk {
 __global__ void prepare_queries_kernel(const float* __restrict__ q, size_t nq, int dim, int ld, bool normalize,
                                        float* __restrict__ out, float* __restrict__ qn2, __half* __restrict__ out16,
                                        int ld16, int* __restrict__ zero_per_query, int* __restrict__ zero_one) {
+    pdl_prologue();
     const size_t w = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
     const int lane = lane_id();
     if (w >= nq) return;
@@ -141,10 +142,10 @@ static inline unsigned warp_grid(size_t n_warps, int threads) {
 cudaError_t launch_prepare_queries(const float* q, size_t nq, int dim, int ld, bool normalize, float* out, float* qn2,
                                    cudaStream_t st, void* out16, int ld16, int* zero_per_query, int* zero_one) {
     if (!nq) return cudaSuccess;
-    prepare_queries_kernel<<<warp_grid(nq, 256), 256, 0, st>>>(q, nq, dim, ld, normalize, out, qn2, (__half*)out16, ld16,
-                                                              zero_per_query, zero_one);
+    cudaError_t e = launch_pdl(prepare_queries_kernel, dim3(warp_grid(nq, 256)), dim3(256), 0, st, q, nq, dim, ld, normalize, out,
+                               qn2, (__half*)out16, ld16, zero_per_query, zero_one);
     count_launch();
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t launch_insert_rows(const float* src, size_t n, int dim, int ld, bool normalize, bool f16, void* rows,

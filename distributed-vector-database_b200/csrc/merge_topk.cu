@@ -92,6 +92,7 @@ __device__ __forceinline__ void merge_stream(const MergeParams& p, size_t q, uin
 }
 
 __global__ void __launch_bounds__(MERGE_THREADS) merge_topk_kernel(const MergeParams p) {
+    pdl_prologue();
     __shared__ uint64_t buf[MERGE_BUF];
     merge_stream(p, blockIdx.x, buf);
 }
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_topk_kernel(const MergePa
 // k-th distance in 4 passes over the keys, only keys at or below it are sorted.  Falls back to the streaming
 // path when exact distance ties make more than MERGE_BUF keys qualify.
 __global__ void __launch_bounds__(MERGE_THREADS) merge_select_kernel(const MergeParams p) {
+    pdl_prologue();
     __shared__ uint64_t buf[MERGE_BUF];
     __shared__ int hist[256];
     __shared__ uint32_t s_prefix, s_rank;
@@ -242,10 +244,11 @@ cudaError_t launch_exchange_merge(const XchgParams& x, const MergeParams& mp, in
 cudaError_t launch_merge_topk(const MergeParams& p, cudaStream_t st) {
     if (p.nq == 0) return cudaSuccess;
     if (p.k_out < 1 || p.k_out > MERGE_BUF / 2) return cudaErrorInvalidValue;
-    if (p.n_in >= 512 && p.n_in >= 8 * p.k_out) merge_select_kernel<<<(unsigned)p.nq, MERGE_THREADS, 0, st>>>(p);
-    else merge_topk_kernel<<<(unsigned)p.nq, MERGE_THREADS, 0, st>>>(p);
+    cudaError_t e;
+    if (p.n_in >= 512 && p.n_in >= 8 * p.k_out) e = launch_pdl(merge_select_kernel, dim3((unsigned)p.nq), dim3(MERGE_THREADS), 0, st, p);
+    else e = launch_pdl(merge_topk_kernel, dim3((unsigned)p.nq), dim3(MERGE_THREADS), 0, st, p);
     count_launch();
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace vdbk

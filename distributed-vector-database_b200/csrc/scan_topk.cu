@@ -86,6 +86,7 @@ struct ScanCtl {            // shared-memory control block of the candidate ring
 
 template <typename T, int NQ>
 __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_topk_kernel(const ScanParams p) {
+    pdl_prologue();
     constexpr int PER16 = Elem<T>::PER16;
     constexpr int VS = SCAN_R * NQ;   // (row, query) values a warp produces per stage
     constexpr int G = 32 / VS;        // stages whose partial sums are reduced together
@@ -323,9 +324,9 @@ static cudaError_t launch_t(const ScanParams& p, int grid, size_t smem, cudaStre
         if (e != cudaSuccess) return e;
         configured[dev & 63] = true;
     }
-    scan_topk_kernel<T, NQ><<<grid, SCAN_THREADS, smem, st>>>(p);
+    cudaError_t e = launch_pdl(scan_topk_kernel<T, NQ>, dim3(grid), dim3(SCAN_THREADS), smem, st, p);
     count_launch();
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 int scan_max_k(int nq_t, int ld, uint32_t row_bytes) {

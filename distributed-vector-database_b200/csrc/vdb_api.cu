@@ -380,6 +380,15 @@ int search_core(vdb* db, Workspace* ws, const float* d_q_raw, size_t nq, int k, 
     return fail(VDB_ECUDA, "internal: unreachable search path");
 }
 
+}  // namespace
+namespace vdbk {
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("VDB_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+}  // namespace vdbk
+namespace {
+
 bool is_pinned_host(const void* p) {
     if (!p) return false;
     cudaPointerAttributes a{};
