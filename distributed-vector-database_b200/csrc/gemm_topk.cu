@@ -1080,21 +1080,31 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
     return cudaSuccess;
 }
 
-// After gemm_topk_search: how many queries failed the certificate (synchronises `st`), and which.
-cudaError_t gemm_topk_flagged(GemmWorkspace& ws, size_t nq, std::vector<int>& flagged, cudaStream_t st) {
+// After gemm_topk_search: how many queries failed the certificate, and which.  Split in two so that a caller
+// that synchronises the stream anyway (vdb_search copies the results to the host) pays no extra round trip:
+//   _enqueue: async copy of the counter to pinned host memory on `st`
+//   _collect: after `st` has been synchronised; lists the flagged queries (one more copy only when there are any)
+cudaError_t gemm_topk_flagged_enqueue(GemmWorkspace& ws, cudaStream_t st) {
+    auto* w = static_cast<GemmWsImpl*>(ws.impl);
+    return cudaMemcpyAsync(w->h_n_flagged, w->n_flagged, sizeof(int), cudaMemcpyDeviceToHost, st);
+}
+cudaError_t gemm_topk_flagged_collect(GemmWorkspace& ws, size_t nq, std::vector<int>& flagged, cudaStream_t st) {
     auto* w = static_cast<GemmWsImpl*>(ws.impl);
     flagged.clear();
-    cudaError_t e = cudaMemcpyAsync(w->h_n_flagged, w->n_flagged, sizeof(int), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) return e;
     if (*w->h_n_flagged == 0) return cudaSuccess;
     std::vector<int> f(nq);
-    e = cudaMemcpyAsync(f.data(), w->flags, nq * sizeof(int), cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaMemcpyAsync(f.data(), w->flags, nq * sizeof(int), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return e;
     for (size_t i = 0; i < nq; ++i)
         if (f[i]) flagged.push_back((int)i);
     return cudaSuccess;
+}
+cudaError_t gemm_topk_flagged(GemmWorkspace& ws, size_t nq, std::vector<int>& flagged, cudaStream_t st) {
+    cudaError_t e = gemm_topk_flagged_enqueue(ws, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return e;
+    return gemm_topk_flagged_collect(ws, nq, flagged, st);
 }
 
 void gemm_plan_note_fallbacks(GemmPlan& plan, long n) {

@@ -43,6 +43,9 @@ bool gemm_topk_supported(int dim, int ld, bool f16, int k, size_t n_rows);
 cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearchArgs& a, cudaStream_t st, std::string& err);
 // after gemm_topk_search: synchronises `st` and lists the queries whose certificate failed
 cudaError_t gemm_topk_flagged(GemmWorkspace& ws, size_t nq, std::vector<int>& flagged, cudaStream_t st);
+// the same in two halves for callers that synchronise `st` themselves between them
+cudaError_t gemm_topk_flagged_enqueue(GemmWorkspace& ws, cudaStream_t st);
+cudaError_t gemm_topk_flagged_collect(GemmWorkspace& ws, size_t nq, std::vector<int>& flagged, cudaStream_t st);
 void gemm_plan_note_fallbacks(GemmPlan& plan, long n);
 void gemm_plan_free(GemmPlan& plan);
 void gemm_workspace_free(GemmWorkspace& ws);
