@@ -126,7 +126,10 @@ struct vdb {
     std::vector<Workspace*> ws_free;
     // options / stats
     std::atomic<long> opt_path{0};          // 0 auto, 1 force scan, 2 force tensor
-    std::atomic<long> opt_scan_batch{8};    // nq <= this takes the scan kernel in auto mode
+    // nq <= this takes the scan kernel in auto mode.  Measured on 1M x 512 (tools/small_batch.py): one scan pass
+    // of 1/2/4/8 fp32 queries costs 297/300/341/570 us (beyond 4 queries the pass is LDS-bound, not HBM-bound),
+    // the tensor path ~320 us for any small batch -> 4 for fp32 rows; fp16 rows do twice the work per byte -> 2
+    std::atomic<long> opt_scan_batch{4};
     std::atomic<long> opt_shadow{1};        // 1 = the tensor path contracts the fp16 shadow plane (fp32 shards)
     std::atomic<long> stat_fallback{0}, stat_tensor_batches{0}, stat_scan_passes{0};
     GemmPlan gemm_plan;
@@ -449,6 +452,7 @@ int vdb_create(int dim, int metric, int store_dtype, size_t capacity, int device
     db->dtype = store_dtype;
     db->device = device;
     db->capacity = capacity;
+    db->opt_scan_batch.store(store_dtype == VDB_F16 ? 2 : 4);
     const int unit = store_dtype == VDB_F16 ? 256 : 128;   // one 512-byte warp load
     db->ld = (dim + unit - 1) / unit * unit;
     if (scan_max_k(1, db->ld, (uint32_t)db->row_bytes()) < 1) return fail(VDB_EINVAL, "dim too large for the scan kernel");

@@ -68,7 +68,7 @@ int vdb_unmark_deleted(vdb_t *db, const int64_t *labels, size_t n);
  *                                                              handler.py:364
  * Exact over all live rows.  Rows with fewer than k live neighbours are padded with label -1
  * and distance +inf; out_counts[q] (optional) is the number of real results.
- * nq <= 8..16 takes the HBM-streaming scan kernel, larger nq the tcgen05 kernel + exact
+ * nq <= 4 (2 for fp16 rows) takes the HBM-streaming scan kernel, larger nq the tcgen05 kernel + exact
  * fp32 re-rank. */
 int vdb_search(vdb_t *db, const float *queries, size_t nq, int k, int64_t *out_labels,
                float *out_dist, int *out_counts);
