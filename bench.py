@@ -166,7 +166,7 @@ def run_reference(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    nq = a.cpu_queries or 32
+    nq = a.cpu_queries or 256         # per step: ~1 s of CPU work on all host threads (x (warmup + steps) steps)
     vals, desc, cores = [], "", 1
     for i in range(a.warmup + a.steps):
         qps, cores, desc = cpu_knn_qps(a, nq)
@@ -303,7 +303,7 @@ def run_ours(a):
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        final = (bufs[2] if sharded else (o_ids if world > 1 else ids))[:64].cpu().numpy()   # rank 0: queries 0..63
+        final = (bufs[2] if sharded else (o_ids if world > 1 else ids))[:4096].cpu().numpy()   # rank 0: the first queries of the batch (its slice when sharded)
         return float(ms.item()) * 1e-3, kern_ns, nprof, launches, final
 
     def e2e_leg(nq, steps, warmup):
@@ -314,7 +314,18 @@ def run_ours(a):
         outs = (vdb.pinned_empty((nq, a.k), np.int64), vdb.pinned_empty((nq, a.k), np.float32),
                 vdb.pinned_empty((nq,), np.int32))
         if world > 1:
-            pin_q = torch.from_numpy(qh).pin_memory()
+            # the batch arrives split over the ranks' hosts: each rank uploads ITS slice of the queries and the
+            # slices are all-gathered over NVLink (every rank needs the whole batch); results of the rank's
+            # slice go back to its page-locked host buffers
+            even = nq % world == 0
+            sl = nq // world if even else nq
+            pin_q = torch.from_numpy(qh[rank * sl:(rank + 1) * sl] if even else qh).pin_memory()
+            qd = torch.empty((nq, a.dim), dtype=torch.float32, device=dev)
+            ids = torch.empty((nq, a.k), dtype=torch.int64, device=dev)
+            dd = torch.empty((nq, a.k), dtype=torch.float32, device=dev)
+            n_out = (nq + world - 1) // world if sharded else nq
+            h_ids = torch.empty((n_out, a.k), dtype=torch.int64).pin_memory()
+            h_dd = torch.empty((n_out, a.k), dtype=torch.float32).pin_memory()
             if sharded:
                 bufs = exchange_buffers(nq)
             else:
@@ -326,18 +337,25 @@ def run_ours(a):
         def step():
             if world == 1:
                 return ix.knn_query_padded(qh, a.k, out=outs)
-            qd = pin_q.to(dev, non_blocking=True)             # every rank needs the whole batch
-            ids = torch.empty((nq, a.k), dtype=torch.int64, device=dev)
-            dd = torch.empty((nq, a.k), dtype=torch.float32, device=dev)
+            if even:
+                qd[rank * sl:(rank + 1) * sl].copy_(pin_q, non_blocking=True)
+                dist.all_gather_into_tensor(qd, qd[rank * sl:(rank + 1) * sl])
+            else:
+                qd.copy_(pin_q, non_blocking=True)            # a single query: every rank uploads it
             ix.search_device(qd.data_ptr(), nq, a.k, ids.data_ptr(), dd.data_ptr(), 0, stream)
             if sharded:
                 exchange_and_merge(ids, dd, nq, bufs)
-                return bufs[2].cpu(), bufs[3].cpu()           # each rank returns the results of its slice
-            dist.all_gather_into_tensor(g_ids, ids)
-            dist.all_gather_into_tensor(g_dd, dd)
-            vdb._ffi.check(lib.vdb_merge_topk(g_dd.data_ptr(), g_ids.data_ptr(), world, nq, a.k, a.k,
-                                              o_dd.data_ptr(), o_ids.data_ptr(), 1, local, stream), "merge")
-            return o_ids.cpu(), o_dd.cpu()
+                h_ids.copy_(bufs[2], non_blocking=True)       # each rank returns the results of its slice
+                h_dd.copy_(bufs[3], non_blocking=True)
+            else:
+                dist.all_gather_into_tensor(g_ids, ids)
+                dist.all_gather_into_tensor(g_dd, dd)
+                vdb._ffi.check(lib.vdb_merge_topk(g_dd.data_ptr(), g_ids.data_ptr(), world, nq, a.k, a.k,
+                                                  o_dd.data_ptr(), o_ids.data_ptr(), 1, local, stream), "merge")
+                h_ids.copy_(o_ids, non_blocking=True)
+                h_dd.copy_(o_dd, non_blocking=True)
+            torch.cuda.current_stream().synchronize()         # the caller holds its results when step() returns
+            return h_ids, h_dd
 
         for _ in range(warmup):
             step()
@@ -441,7 +459,12 @@ def run_ours(a):
         cpu = None
         recall = None
         if not a.no_cpu and world == 1:
-            qps, cores, desc, want_ids = cpu_knn_qps(a, a.cpu_queries or 64, return_ids=True)
+            # bounded sample of the same workload, sized from a short probe to ~12 s of CPU work on all host threads
+            nq_cpu = a.cpu_queries
+            if not nq_cpu:
+                probe_qps = cpu_knn_qps(a, 64)[0]
+                nq_cpu = int(min(B * 8, max(64, 64 * round(12.0 * probe_qps / 64))))
+            qps, cores, desc, want_ids = cpu_knn_qps(a, nq_cpu, return_ids=True)
             cpu = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
                    "sample": desc + " (oracle/knn_ref.c exact scan, OpenMP)"}
             if want_ids is not None and a.rows <= 1_000_000:
@@ -460,7 +483,7 @@ def run_ours(a):
                            else "all-to-all by query slice (NCCL) + GPU merge"),
                        "l2": "inputs larger than L2 (no flush needed)", "path": "tensor" if tensor_batches > 0 else "scan"},
             "e2e": {"value": B * a.steps / e2e_sec, "unit": "queries/s",
-                    "h2d_bytes_per_step": world * B * a.dim * 4,
+                    "h2d_bytes_per_step": B * a.dim * 4,
                     "d2h_bytes_per_step": B * a.k * 12 + (B * 4 if world == 1 else 0)},
             "gpu_launches": launches,
             "roofline": roof,

@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectParams p) {
     pdl_prologue();
     extern __shared__ uint64_t sk[];
     __shared__ int hist[256];
-    __shared__ uint32_t s_prefix, s_rank;
+    __shared__ uint32_t s_prefix, s_rank, s_min, s_max;
     __shared__ int s_valid, s_c1, s_c2;
     const size_t q = blockIdx.x;
     uint64_t* b = p.buf + q * (size_t)p.cap;
@@ -600,9 +600,10 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectParams p) {
         if (threadIdx.x == 0) p.overflow[q] = 1;
         n = p.cap;
     }
-    if (threadIdx.x == 0) { s_valid = 0; s_c1 = 0; s_c2 = 0; s_prefix = 0; }
+    if (threadIdx.x == 0) { s_valid = 0; s_c1 = 0; s_c2 = 0; s_prefix = 0; s_min = 0xFFFFFFFFu; s_max = 0u; }
     __syncthreads();
     int my_valid = 0;
+    uint32_t vlo = 0xFFFFFFFFu, vhi = 0u;
     for (int i = threadIdx.x; i < n; i += THREADS) {
         uint64_t key = b[i];
         if (key != KEY_SENTINEL) {
@@ -610,10 +611,15 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectParams p) {
             if (row >= p.n_rows || (p.tomb && ((p.tomb[row >> 5] >> (row & 31)) & 1u))) key = KEY_SENTINEL;
         }
         sk[i] = key;
-        my_valid += key != KEY_SENTINEL;
+        if (key != KEY_SENTINEL) {
+            ++my_valid;
+            vlo = min(vlo, (uint32_t)(key >> 32)); vhi = max(vhi, (uint32_t)(key >> 32));
+        }
     }
     my_valid = warp_sum_int(my_valid);
-    if ((threadIdx.x & 31) == 0 && my_valid) atomicAdd(&s_valid, my_valid);
+    vlo = __reduce_min_sync(0xffffffffu, vlo);
+    vhi = __reduce_max_sync(0xffffffffu, vhi);
+    if ((threadIdx.x & 31) == 0 && my_valid) { atomicAdd(&s_valid, my_valid); atomicMin(&s_min, vlo); atomicMax(&s_max, vhi); }
     __syncthreads();
     const int n_valid = s_valid;
     __syncthreads();
@@ -631,9 +637,17 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectParams p) {
         }
         return;
     }
-    if (threadIdx.x == 0) s_rank = (uint32_t)p.kp;     // 1-based rank of the key we are looking for
-    uint32_t mask = 0;
-    for (int pass = 0; pass < 4; ++pass) {
+    // The passes start at the highest byte in which the values differ: the bytes above it (sign, exponent) are
+    // common to all keys and would send every atomicAdd of a pass to ONE histogram bin.
+    const uint32_t diff = s_min ^ s_max;
+    const int first_pass = diff ? 3 - ((31 - __clz(diff)) >> 3) : 4;     // all values equal: no pass
+    uint32_t mask = first_pass == 0 ? 0u : (first_pass == 4 ? 0xFFFFFFFFu : ~((1u << (32 - 8 * first_pass)) - 1u));
+    if (threadIdx.x == 0) {
+        s_rank = (uint32_t)p.kp;                       // 1-based rank of the key we are looking for
+        s_prefix = s_min & mask;
+    }
+    __syncthreads();
+    for (int pass = first_pass; pass < 4; ++pass) {
         const int shift = 24 - 8 * pass;
         for (int i = threadIdx.x; i < 256; i += THREADS) hist[i] = 0;
         __syncthreads();
@@ -713,7 +727,132 @@ struct RerankParams {
     int64_t* out_ids; float* out_dist; int* out_counts;
     int* flags;               // [nq] 1 = certificate failed
     int* n_flagged;
+    // window kernel only: the level buffers as the last level left them (no final select)
+    const int* cnt;           // [nq] keys in the buffer (may exceed cap: overflow)
+    int cap;
+    const uint32_t* tomb; uint32_t n_rows;
 };
+
+// exact fp32 distance of (query, row) in the scan kernel's summation order -> sortable key; whole warp
+template <typename T>
+__device__ __forceinline__ uint64_t exact_key(const RerankParams& p, const float* qv, uint32_t row, int lane) {
+    const int nld16 = p.row_bytes / 512;
+    constexpr int PER16 = 16 / sizeof(T);
+    const uint8_t* rp = reinterpret_cast<const uint8_t*>(p.rows) + (size_t)row * p.row_bytes;
+    float acc = 0.0f;
+    for (int ch = 0; ch < nld16; ++ch) {
+        float dv[PER16], qq[PER16];
+        if constexpr (sizeof(T) == 4) {
+            const float4 t = *reinterpret_cast<const float4*>(rp + (size_t)(ch * 32 + lane) * 16);
+            dv[0] = t.x; dv[1] = t.y; dv[2] = t.z; dv[3] = t.w;
+        } else {
+            const uint4 t = *reinterpret_cast<const uint4*>(rp + (size_t)(ch * 32 + lane) * 16);
+            const __half2* h = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(h[i]);
+                dv[2 * i] = f.x; dv[2 * i + 1] = f.y;
+            }
+        }
+        const float* qp = qv + (size_t)(ch * 32 + lane) * PER16;
+#pragma unroll
+        for (int e = 0; e < PER16; e += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(qp + e);
+            qq[e] = t.x; qq[e + 1] = t.y; qq[e + 2] = t.z; qq[e + 3] = t.w;
+        }
+        if (p.metric == 0) {
+#pragma unroll
+            for (int e = 0; e < PER16; ++e) {
+                const float t = dv[e] - qq[e];
+                acc = fmaf(t, t, acc);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < PER16; ++e) acc = fmaf(dv[e], qq[e], acc);
+        }
+    }
+    acc = warp_sum_butterfly(acc);
+    const float dist = p.metric == 0 ? acc : 1.0f - acc;
+    return make_key(dist, p.labels[row]);
+}
+
+// Same arithmetic for NR rows at once: the loads of all rows (4 lane chunks each) are issued before the first FMA,
+// so a warp keeps NR x 4 x 16 bytes in flight per lane instead of 16 (the window re-rank reads a handful of rows
+// per query: its time is memory latency, not bandwidth).
+template <typename T, int NR>
+__device__ __forceinline__ void exact_keys(const RerankParams& p, const float* qs, const uint32_t (&row)[NR], int lane,
+                                           uint64_t (&out)[NR]) {
+    const int nld16 = p.row_bytes / 512;
+    constexpr int PER16 = 16 / sizeof(T);
+    constexpr int U = 4;
+    const uint8_t* rp[NR];
+    float acc[NR];
+    uint32_t label[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        rp[r] = reinterpret_cast<const uint8_t*>(p.rows) + (size_t)row[r] * p.row_bytes + (size_t)lane * 16;
+        acc[r] = 0.0f;
+        label[r] = __ldg(p.labels + row[r]);
+    }
+    for (int ch0 = 0; ch0 < nld16; ch0 += U) {
+        uint4 raw[NR][U];
+#pragma unroll
+        for (int r = 0; r < NR; ++r)
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (ch0 + u < nld16) raw[r][u] = __ldg(reinterpret_cast<const uint4*>(rp[r] + (size_t)(ch0 + u) * 512));
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (ch0 + u < nld16) {
+                float qq[PER16];
+                const float* qp = qs + (size_t)((ch0 + u) * 32 + lane) * PER16;
+#pragma unroll
+                for (int e = 0; e < PER16; e += 4) {
+                    const float4 t = *reinterpret_cast<const float4*>(qp + e);
+                    qq[e] = t.x; qq[e + 1] = t.y; qq[e + 2] = t.z; qq[e + 3] = t.w;
+                }
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                    float dv[PER16];
+                    if constexpr (sizeof(T) == 4) {
+                        dv[0] = __uint_as_float(raw[r][u].x); dv[1] = __uint_as_float(raw[r][u].y);
+                        dv[2] = __uint_as_float(raw[r][u].z); dv[3] = __uint_as_float(raw[r][u].w);
+                    } else {
+                        const __half2* h = reinterpret_cast<const __half2*>(&raw[r][u]);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float2 f = __half22float2(h[i]);
+                            dv[2 * i] = f.x; dv[2 * i + 1] = f.y;
+                        }
+                    }
+                    if (p.metric == 0) {
+#pragma unroll
+                        for (int e = 0; e < PER16; ++e) {
+                            const float t = dv[e] - qq[e];
+                            acc[r] = fmaf(t, t, acc[r]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < PER16; ++e) acc[r] = fmaf(dv[e], qq[e], acc[r]);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const float a = warp_sum_butterfly(acc[r]);
+        out[r] = make_key(p.metric == 0 ? a : 1.0f - a, label[r]);
+    }
+}
+
+// error bound of the approximate values of query q (approximate-value units: ||d||^2 - 2 q.d for L2, -q.d otherwise):
+// |approximate + offset - exact| <= eps for every row, offset = ||q||^2 (L2) / 1 (ip, cosine); `at` = the value
+// (offset included) whose magnitude scales the fp32 slack
+__device__ __forceinline__ float approx_eps(const RerankParams& p, float qn2, float dmax2, float at) {
+    const float eb = p.eps_rel * sqrtf(qn2) * sqrtf(dmax2) + p.eps_abs * (sqrtf(qn2) + sqrtf(dmax2));
+    return p.metric == 0 ? 2.0f * eb + 4e-7f * (qn2 + dmax2 + fabsf(at)) : eb + 4e-7f * (1.0f + fabsf(at));
+}
 
 template <typename T, int KP>
 __global__ void __launch_bounds__(256) rerank_kernel(const RerankParams p) {
@@ -722,50 +861,9 @@ __global__ void __launch_bounds__(256) rerank_kernel(const RerankParams p) {
     const int q = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t* ap = p.approx + (size_t)q * p.stride;
     const float* qv = p.q + (size_t)q * p.ld;
-    const int nld16 = p.row_bytes / 512;
-    constexpr int PER16 = 16 / sizeof(T);
     for (int c = warp; c < KP; c += 8) {
         const uint64_t key = ap[c];
-        uint64_t out = KEY_SENTINEL;
-        if (key != KEY_SENTINEL) {
-            const uint32_t row = (uint32_t)key;
-            const uint8_t* rp = reinterpret_cast<const uint8_t*>(p.rows) + (size_t)row * p.row_bytes;
-            float acc = 0.0f;
-            for (int ch = 0; ch < nld16; ++ch) {
-                float dv[PER16], qq[PER16];
-                if constexpr (sizeof(T) == 4) {
-                    const float4 t = *reinterpret_cast<const float4*>(rp + (size_t)(ch * 32 + lane) * 16);
-                    dv[0] = t.x; dv[1] = t.y; dv[2] = t.z; dv[3] = t.w;
-                } else {
-                    const uint4 t = *reinterpret_cast<const uint4*>(rp + (size_t)(ch * 32 + lane) * 16);
-                    const __half2* h = reinterpret_cast<const __half2*>(&t);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float2 f = __half22float2(h[i]);
-                        dv[2 * i] = f.x; dv[2 * i + 1] = f.y;
-                    }
-                }
-                const float* qp = qv + (size_t)(ch * 32 + lane) * PER16;
-#pragma unroll
-                for (int e = 0; e < PER16; e += 4) {
-                    const float4 t = *reinterpret_cast<const float4*>(qp + e);
-                    qq[e] = t.x; qq[e + 1] = t.y; qq[e + 2] = t.z; qq[e + 3] = t.w;
-                }
-                if (p.metric == 0) {
-#pragma unroll
-                    for (int e = 0; e < PER16; ++e) {
-                        const float t = dv[e] - qq[e];
-                        acc = fmaf(t, t, acc);
-                    }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < PER16; ++e) acc = fmaf(dv[e], qq[e], acc);
-                }
-            }
-            acc = warp_sum_butterfly(acc);
-            const float dist = p.metric == 0 ? acc : 1.0f - acc;
-            out = make_key(dist, p.labels[row]);
-        }
+        const uint64_t out = key != KEY_SENTINEL ? exact_key<T>(p, qv, (uint32_t)key, lane) : KEY_SENTINEL;
         if (lane == 0) ek[c] = out;
     }
     __syncthreads();
@@ -807,6 +905,217 @@ __global__ void __launch_bounds__(256) rerank_kernel(const RerankParams p) {
         if (p.overflow[q]) ok = false;
         // an element above the fp16 range became +-inf in the operand plane (|x_i| <= ||x||): no bound holds
         if (p.f16_range && (p.qn2[q] >= 4.0e9f || __uint_as_float(*p.max_sqnorm_bits) >= 4.0e9f)) ok = false;
+        p.flags[q] = ok ? 0 : 1;
+        if (!ok) atomicAdd(p.n_flagged, 1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4w: K4 straight from the level buffers -- no select after the last level, and only the candidates that can
+// still reach the exact top-k are re-ranked.
+//   Buffer of query q after the last level: the k' keys the previous select carried over + every row of the last
+//   level whose approximate value beat that level's threshold thr.  Every row that is NOT in the buffer failed a
+//   threshold >= thr (thresholds only tighten) or was dropped by a select at a value >= thr: approximate >= thr.
+//   With |approximate + offset - exact| <= eps for every row:
+//   (1) window: let a_k = k-th smallest approximate value in the buffer.  k rows have exact <= a_k + offset + eps,
+//       so a row with approximate > a_k + 2 eps (exact > a_k + offset + eps) is strictly worse than k rows: only
+//       the keys at or below a_k + 2 eps (a handful beyond k) are read back from the fp32 rows;
+//   (2) certificate: k-th exact distance < thr + offset - eps  =>  no row outside the buffer can enter the top-k.
+// ------------------------------------------------------------------------------------------
+// One block of 128 threads per query; six short stages, a barrier between them:
+//   1. a' = k-th smallest of the k' carried keys (rank by counting): a' >= a_k
+//   2. list = buffer keys at or below a' + 2 eps (expected ~8k of them: a' is the k-th best of 1/8 of the rows)
+//   3. a_k = k-th smallest of the list (radix select over the bits in which the list's values differ)
+//   4. window = list keys at or below a_k + 2 eps
+//   5. exact distances, two rows in flight per warp   6. results written at their rank (by counting), certificate
+constexpr int RW_THREADS = 128;
+
+// value bits of the `rank`-th smallest (1-based) of the n > = rank real keys in sk[] (no sentinels).  Radix select
+// from the highest byte in which the values differ: the bytes above it are common to all keys and would send every
+// atomicAdd of a pass to ONE histogram bin.  Stops as soon as the bin that holds the rank has a single key.
+__device__ __forceinline__ uint32_t block_kth_bits(const uint64_t* sk, int n, int rank, int* hist, uint32_t* sh) {
+    // sh[0] = min, sh[1] = max, sh[2] = prefix, sh[3] = rank, sh[4] = count in the chosen bin
+    const int tid = threadIdx.x;
+    if (tid == 0) { sh[0] = 0xFFFFFFFFu; sh[1] = 0u; }
+    __syncthreads();
+    uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+    for (int i = tid; i < n; i += RW_THREADS) {
+        const uint32_t v = (uint32_t)(sk[i] >> 32);
+        lo = min(lo, v); hi = max(hi, v);
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((tid & 31) == 0) { atomicMin(&sh[0], lo); atomicMax(&sh[1], hi); }
+    __syncthreads();
+    lo = sh[0]; hi = sh[1];
+    if (lo == hi) return lo;
+    int shift = ((31 - __clz(lo ^ hi)) >> 3) << 3;          // byte of the highest differing bit
+    uint32_t mask = shift == 24 ? 0u : ~((1u << (shift + 8)) - 1u);
+    if (tid == 0) { sh[2] = lo & mask; sh[3] = (uint32_t)rank; sh[4] = 0u; }
+    for (; shift >= 0; shift -= 8) {
+        for (int i = tid; i < 256; i += RW_THREADS) hist[i] = 0;
+        __syncthreads();
+        const uint32_t prefix = sh[2];
+        for (int i = tid; i < n; i += RW_THREADS) {
+            const uint32_t v = (uint32_t)(sk[i] >> 32);
+            if ((v & mask) == prefix) atomicAdd(&hist[(v >> shift) & 255], 1);
+        }
+        __syncthreads();
+        if (tid < 32) {
+            int local[8], sum = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { local[i] = hist[tid * 8 + i]; sum += local[i]; }
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (tid >= o) incl += t;
+            }
+            const int excl = incl - sum;
+            const int r = (int)sh[3];
+            if (r > excl && r <= incl) {
+                int run = excl;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (r > run && r <= run + local[i]) {
+                        sh[2] = prefix | ((uint32_t)(tid * 8 + i) << shift);
+                        sh[3] = (uint32_t)(r - run);
+                        sh[4] = (uint32_t)local[i];
+                    }
+                    run += local[i];
+                }
+            }
+        }
+        mask |= 0xFFu << shift;
+        __syncthreads();
+        if (sh[4] == 1u && shift > 0) {            // one key left under this prefix: it is the answer
+            const uint32_t prefix1 = sh[2];
+            __syncthreads();
+            for (int i = tid; i < n; i += RW_THREADS) {
+                const uint32_t v = (uint32_t)(sk[i] >> 32);
+                if ((v & mask) == prefix1) sh[2] = v;
+            }
+            __syncthreads();
+            break;
+        }
+    }
+    return sh[2];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(RW_THREADS) rerank_window_kernel(const RerankParams p, const int kp) {
+    pdl_prologue();
+    extern __shared__ uint64_t wsm[];
+    uint64_t* sk = wsm;                // [cap] buffer keys; from stage 4 the window keys
+    uint64_t* lk = wsm + p.cap;        // [cap] list; from stage 5 the exact keys
+    __shared__ int hist[256];
+    __shared__ uint32_t sh[8];
+    __shared__ uint32_t s_a1;
+    __shared__ int s_m1, s_m;
+    __shared__ float s_kth;
+    __shared__ int s_have_kth;
+    const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int k = p.k;
+    const uint64_t* b = p.approx + (size_t)q * p.stride;
+    int n = p.cnt[q];
+    bool ok = !(n > p.cap || p.overflow[q] != 0);
+    n = min(n, p.cap);
+    const float qn2 = p.qn2[q];
+    const float dmax2 = __uint_as_float(*p.max_sqnorm_bits);
+    const float off = p.metric == 0 ? qn2 : 1.0f;
+    const float INF = __int_as_float(0x7f800000);
+    // value bits of a_x + 2 eps (with a margin for the rounding of the sum); non-finite: keep everything
+    auto window_bits = [&](uint32_t a_bits) -> uint32_t {
+        const float a = ordered_to_float(a_bits);
+        const float wv = a + 2.25f * approx_eps(p, qn2, dmax2, a + off);
+        return (wv == wv && fabsf(wv) < INF) ? float_to_ordered(wv) : 0xFFFFFFFFu;
+    };
+    if (tid == 0) { s_a1 = 0xFFFFFFFFu; s_m1 = 0; s_m = 0; s_kth = INF; s_have_kth = 0; }
+    // ---- 0. the buffer; padding rows of the last tile and tombstoned rows drop out
+    for (int i = tid; i < n; i += RW_THREADS) {
+        uint64_t key = b[i];
+        if (key != KEY_SENTINEL) {
+            const uint32_t row = (uint32_t)key;
+            if (row >= p.n_rows || (p.tomb && ((p.tomb[row >> 5] >> (row & 31)) & 1u))) key = KEY_SENTINEL;
+        }
+        sk[i] = key;
+    }
+    __syncthreads();
+    // ---- 1. bound from the carried keys (sentinels sort last: fewer than k real ones -> keep everything)
+    const int nc = min(n, kp);
+    for (int t = tid; t < nc; t += RW_THREADS) {
+        const uint64_t key = sk[t];
+        int rank = 0;
+        for (int j = 0; j < nc; ++j) rank += sk[j] < key;
+        if (rank == k - 1) s_a1 = (uint32_t)(key >> 32);      // keys are distinct (rows are), sentinels are not:
+    }                                                          // a sentinel of rank k-1 writes 0xFFFFFFFF as well
+    __syncthreads();
+    // ---- 2. the keys that can still matter
+    const uint32_t w1 = s_a1 == 0xFFFFFFFFu ? 0xFFFFFFFFu : window_bits(s_a1);
+    for (int i0 = 0; i0 < n; i0 += RW_THREADS) {
+        const int i = i0 + tid;
+        const uint64_t key = i < n ? sk[i] : KEY_SENTINEL;
+        const bool pass = key != KEY_SENTINEL && (uint32_t)(key >> 32) <= w1;
+        const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+        int base = 0;
+        if (lane == 0 && bal) base = atomicAdd(&s_m1, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (pass) lk[base + __popc(bal & ((1u << lane) - 1u))] = key;
+    }
+    __syncthreads();
+    const int m1 = s_m1;
+    // ---- 3. a_k and the final window
+    uint32_t w2 = w1;
+    if (m1 > k) w2 = min(w1, window_bits(block_kth_bits(lk, m1, k, hist, sh)));
+    // ---- 4. window keys -> sk (stage 2 has finished reading it: barriers above)
+    for (int i0 = 0; i0 < m1; i0 += RW_THREADS) {
+        const int i = i0 + tid;
+        const uint64_t key = i < m1 ? lk[i] : KEY_SENTINEL;
+        const bool pass = i < m1 && (uint32_t)(key >> 32) <= w2;
+        const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+        int base = 0;
+        if (lane == 0 && bal) base = atomicAdd(&s_m, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (pass) sk[base + __popc(bal & ((1u << lane) - 1u))] = key;
+    }
+    __syncthreads();
+    int m = s_m;
+    // ---- 5. exact distances -> lk
+    const float* qv = p.q + (size_t)q * p.ld;
+    for (int c = 2 * warp; c < m; c += 2 * (RW_THREADS / 32)) {     // an odd tail repeats its row (result discarded)
+        const uint32_t rows[2] = {(uint32_t)sk[c], (uint32_t)sk[min(c + 1, m - 1)]};
+        uint64_t out[2];
+        exact_keys<T, 2>(p, qv, rows, lane, out);
+        if (lane == 0) lk[c] = out[0];
+        if (lane == 1 && c + 1 < m) lk[c + 1] = out[1];
+    }
+    __syncthreads();
+    // ---- 6. results at their rank (keys are distinct: labels are), certificate
+    if (m > 2048) { ok = false; m = 0; }            // degenerate (thousands of near-ties): leave it to the scan
+    for (int i = tid; i < m; i += RW_THREADS) {
+        const uint64_t key = lk[i];
+        int rank = 0;
+        for (int j = 0; j < m; ++j) rank += lk[j] < key;
+        if (rank < k) {
+            p.out_ids[(size_t)q * k + rank] = (int64_t)key_label(key);
+            p.out_dist[(size_t)q * k + rank] = key_dist(key);
+            if (rank == k - 1) { s_kth = key_dist(key); s_have_kth = 1; }
+        }
+    }
+    for (int i = m + tid; i < k; i += RW_THREADS) {
+        p.out_ids[(size_t)q * k + i] = -1;
+        p.out_dist[(size_t)q * k + i] = INF;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (p.out_counts) p.out_counts[q] = min(m, k);
+        const float a_tau = p.tau[q];
+        if (a_tau < INF) {                          // rows outside the buffer exist: prove they cannot matter
+            const float tau = a_tau + off;
+            ok = ok && s_have_kth && s_kth < tau - approx_eps(p, qn2, dmax2, tau);
+        }
+        // an element above the fp16 range became +-inf in the operand plane (|x_i| <= ||x||): no bound holds
+        if (p.f16_range && (qn2 >= 4.0e9f || dmax2 >= 4.0e9f)) ok = false;
         p.flags[q] = ok ? 0 : 1;
         if (!ok) atomicAdd(p.n_flagged, 1);
     }
@@ -901,6 +1210,20 @@ static cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, c
     cudaError_t e = launch_pdl(gemm_filter_kernel<F16, L2>, dim3(grid), dim3(GT_THREADS), GT_SMEM_BYTES_FILTER, st, tmA, tmB, gp);
     count_launch();
     return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+template <typename T>
+static cudaError_t launch_rerank_window(int kp, const RerankParams& rp, size_t nq, cudaStream_t st) {
+    const size_t smem = 2 * (size_t)rp.cap * sizeof(uint64_t);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(rerank_window_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    cudaError_t le = launch_pdl(rerank_window_kernel<T>, dim3((unsigned)nq), dim3(RW_THREADS), smem, st, rp, kp);
+    count_launch();
+    return le != cudaSuccess ? le : cudaGetLastError();
 }
 
 template <typename T>
@@ -1022,6 +1345,8 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
 
     // levels over positions: [0, d0) dense, then each level GT_LEVEL_GROWTH x what has been seen, the last one
     // takes what is left if that is at most 1.5 x the growth
+    // VDB_WINDOW=0: the previous chain (select after every level, re-rank of all k' candidates)
+    static const bool window = [] { const char* v = getenv("VDB_WINDOW"); return !(v && atoi(v) == 0); }();
     int pos = 0;
     int level = 0;
     while (pos < n_pos) {
@@ -1050,6 +1375,8 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
         if (a.prof_end) a.prof_end(a.prof_ctx, st);
         if (e != cudaSuccess) return e;
         sp.dense_cnt = level == 0 ? (next - pos) * GT_BN : 0;
+        // the window re-rank reads the last level's buffer as it is (the dense level's buffer has no count)
+        if (window && next == n_pos && level > 0) break;
         // one block per query; thousands of queries with a few hundred keys each: small blocks, so that more
         // of them are resident and the barrier chain of a block is short
         if (a.nq >= 4096 && cap <= 1024) e = launch_pdl(select_kernel<64>, dim3((unsigned)a.nq), dim3(64), (size_t)sel_np * 8, st, sp);
@@ -1075,7 +1402,9 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
     rp.f16_range = g16 ? 1 : 0;
     rp.out_ids = a.out_ids; rp.out_dist = a.out_dist; rp.out_counts = a.out_counts;
     rp.flags = w->flags; rp.n_flagged = w->n_flagged;
-    e = a.f16 ? launch_rerank<__half>(kp, rp, a.nq, st) : launch_rerank<float>(kp, rp, a.nq, st);
+    rp.cnt = w->cnt; rp.cap = cap; rp.tomb = a.tomb; rp.n_rows = a.n_rows;
+    if (window) e = a.f16 ? launch_rerank_window<__half>(kp, rp, a.nq, st) : launch_rerank_window<float>(kp, rp, a.nq, st);
+    else e = a.f16 ? launch_rerank<__half>(kp, rp, a.nq, st) : launch_rerank<float>(kp, rp, a.nq, st);
     if (e != cudaSuccess) return e;
     return cudaSuccess;
 }
