@@ -582,6 +582,8 @@ struct SelectParams {
     float* thr; int* overflow;
     const uint32_t* tomb; uint32_t n_rows;
     int dense_cnt;            // > 0: level 0 wrote this many keys per query at fixed positions
+    int thr_rank;             // the next level's threshold = the thr_rank-th best kept value (<= kp)
+    int np2;                  // keys the shared array sk[] holds (>= cap); kept[kp] lies behind it
 };
 
 // Radix select on the 32 distance bits (4 passes of 8 bits): O(n) instead of a full sort.  Keys whose
@@ -633,7 +635,9 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectParams p) {
         for (int i = n_valid + threadIdx.x; i < p.kp; i += THREADS) b[i] = KEY_SENTINEL;
         if (threadIdx.x == 0) {
             p.cnt[q] = p.kp;
-            p.thr[q] = __int_as_float(0x7f800000);
+            // level 0: nothing has been dropped yet.  Later levels: rows dropped so far are >= the current
+            // threshold and nothing tighter is known: it stays
+            if (p.dense_cnt > 0) p.thr[q] = __int_as_float(0x7f800000);
         }
         return;
     }
@@ -691,19 +695,37 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectParams p) {
     const uint32_t T = s_prefix;                  // distance bits of the KP-th best key
     const int need_eq = (int)s_rank;              // how many keys with exactly these bits to keep
     const int n_less = p.kp - need_eq;
+    uint64_t* kept = sk + p.np2;                  // [kp] behind the key array
+    const bool tighter = p.thr_rank < p.kp;
     for (int i = threadIdx.x; i < n; i += THREADS) {
         const uint64_t key = sk[i];
         if (key == KEY_SENTINEL) continue;
         const uint32_t hi = (uint32_t)(key >> 32);
-        if (hi < T) b[atomicAdd(&s_c1, 1)] = key;
+        int dst = -1;
+        if (hi < T) dst = atomicAdd(&s_c1, 1);
         else if (hi == T) {
             const int s = atomicAdd(&s_c2, 1);
-            if (s < need_eq) b[n_less + s] = key;
+            if (s < need_eq) dst = n_less + s;
+        }
+        if (dst >= 0) {
+            b[dst] = key;
+            if (tighter) kept[dst] = key;
         }
     }
-    if (threadIdx.x == 0) {
-        p.cnt[q] = p.kp;
-        p.thr[q] = ordered_to_float(T);
+    if (threadIdx.x == 0) p.cnt[q] = p.kp;
+    if (!tighter) {
+        if (threadIdx.x == 0) p.thr[q] = ordered_to_float(T);
+        return;
+    }
+    // The kp best stay candidates; the threshold is the thr_rank-th best of them.  While only a small part of the
+    // shard has been seen the kp-th best of the sample is far looser than the certificate needs, and every row
+    // that passes it costs a trip through the key rings (rank by counting: keys are distinct).
+    __syncthreads();
+    for (int t = threadIdx.x; t < p.kp; t += THREADS) {
+        const uint64_t key = kept[t];
+        int rank = 0;
+        for (int j = 0; j < p.kp; ++j) rank += kept[j] < key;
+        if (rank == p.thr_rank - 1) p.thr[q] = ordered_to_float((uint32_t)(key >> 32));
     }
 }
 
@@ -1342,11 +1364,17 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
     }
     int sel_np = 2;
     while (sel_np < cap) sel_np <<= 1;
+    sp.np2 = sel_np;
+    const size_t sel_smem = ((size_t)sel_np + kp) * 8;
 
     // levels over positions: [0, d0) dense, then each level GT_LEVEL_GROWTH x what has been seen, the last one
     // takes what is left if that is at most 1.5 x the growth
     // VDB_WINDOW=0: the previous chain (select after every level, re-rank of all k' candidates)
     static const bool window = [] { const char* v = getenv("VDB_WINDOW"); return !(v && atoi(v) == 0); }();
+    // (only with the window re-rank, whose certificate uses the last level's threshold; the previous chain's
+    // certificate assumes that threshold is the k'-th best)
+    static const bool tight_rank = window && [] { const char* v = getenv("VDB_TIGHT"); return !(v && atoi(v) == 0); }();
+    const int kq = std::max(kp / 2, std::min(kp, (16 * a.k + 9) / 10));
     int pos = 0;
     int level = 0;
     while (pos < n_pos) {
@@ -1375,12 +1403,14 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
         if (a.prof_end) a.prof_end(a.prof_ctx, st);
         if (e != cudaSuccess) return e;
         sp.dense_cnt = level == 0 ? (next - pos) * GT_BN : 0;
+        // threshold rank: while at most a quarter of the shard has been seen, a tighter rank than k' (see K2s)
+        sp.thr_rank = (tight_rank && 4L * next <= n_pos) ? kq : kp;
         // the window re-rank reads the last level's buffer as it is (the dense level's buffer has no count)
         if (window && next == n_pos && level > 0) break;
         // one block per query; thousands of queries with a few hundred keys each: small blocks, so that more
         // of them are resident and the barrier chain of a block is short
-        if (a.nq >= 4096 && cap <= 1024) e = launch_pdl(select_kernel<64>, dim3((unsigned)a.nq), dim3(64), (size_t)sel_np * 8, st, sp);
-        else e = launch_pdl(select_kernel<256>, dim3((unsigned)a.nq), dim3(256), (size_t)sel_np * 8, st, sp);
+        if (a.nq >= 4096 && cap <= 1024) e = launch_pdl(select_kernel<64>, dim3((unsigned)a.nq), dim3(64), sel_smem, st, sp);
+        else e = launch_pdl(select_kernel<256>, dim3((unsigned)a.nq), dim3(256), sel_smem, st, sp);
         count_launch();
         if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) return e;
         pos = next;
