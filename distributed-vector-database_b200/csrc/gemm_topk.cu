@@ -63,7 +63,7 @@ constexpr int GT_EPI_THREADS = 256;                  // 2 threads per query (TME
 constexpr int GT_EPI_WARPS = GT_EPI_THREADS / 32;
 constexpr int GT_TMEM_COLS = 512;
 constexpr int GT_LEVEL_GROWTH = 8;                   // each level sees 8x the rows seen so far
-constexpr int GT_DENSE_TILES = 4;                    // level 0: 4 tiles = 1024 rows, everything kept
+constexpr int GT_PROBE_TILES = 16;                   // probe level: 16 tiles = 4096 rows, 128 chunk minima per query
 
 // dynamic shared memory map (base aligned to 1024)
 constexpr int GT_OFF_RING = GT_STAGES * GT_STAGE_BYTES;                           // 163840
@@ -84,10 +84,11 @@ struct GemmParams {
     int n_tiles;             // 256-row tiles of the shard
     int bits;                // tile order = bit reversal over `bits` bits
     int pos_begin, pos_end;  // this level's positions in that order
-    int dense;               // level 0: keep every score
+    int probe;               // level 0: one key per 32-score chunk (its best live row), at fixed positions
     int dbg;                 // experiments only: 2 = epilogue releases TMEM at once, 8 = TMEM reads but no filtering
     const float* sqnorm;     // [n_rows] (L2 only)
-    const float* thr;        // [nq] threshold of this level (approximate distance); unused when dense
+    const float* thr;        // [nq] threshold of this level (approximate distance); unused by the probe
+    const uint32_t* tomb;    // tombstone bitmap (probe only: a dead row must not stand for its chunk)
     uint64_t* buf;           // [nq][cap] candidate keys (approximate distance bits << 32 | row)
     int* cnt;                // [nq] keys in buf
     int cap;
@@ -339,7 +340,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // ================= movers: key rings -> per-query candidate buffers in global memory =================
         // Lane-parallel: each lane serves two queries; one atomicAdd reserves room for everything that is
         // waiting in a ring, so global-memory latency never sits on the TMEM-drain path of the epilogue.
-        if (!p.dense) {
+        if (!p.probe) {
             const int base = (warp - 2) * (GT_EPI_THREADS / 2);    // each mover warp serves half of the rings
             volatile uint32_t* v_head = ctl->head_pub;
             volatile uint32_t* v_tail = ctl->tail;
@@ -414,7 +415,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const uint32_t q = qbase + ql;
             const bool q_ok = q < p.nq;
             float thr = __int_as_float(0xff800000);        // -inf: nothing passes (padding queries)
-            if (!p.dense) {
+            if (!p.probe) {
                 // the ring still holds keys of the previous item's query until the movers have drained it
                 while (*my_tail != head) __nanosleep(64);
                 tail_seen = head;
@@ -457,25 +458,40 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * GT_BN + col0;
                 const uint32_t ns_s = smem_u32(norm_s + acc * GT_BN + col0);
                 constexpr int NCH = GT_BN / 2 / 32;            // 4 chunks of 32 columns per thread
-                if (p.dense) {
-                    // level 0: every score of this tile is a candidate; position in the buffer is fixed
-                    uint64_t* dd = dense_dst + (size_t)(pos - p.pos_begin) * GT_BN + col0;
+                if (p.probe) {
+                    // probe level: per 32-score chunk only its best live row is written (fixed position: 8 keys
+                    // per tile and query).  The r-th smallest of those chunk minima is the value of a real row with
+                    // at least r rows at or below it: a valid threshold for the levels that follow, which visit
+                    // these tiles again.
+                    uint64_t* dd = dense_dst + (size_t)(pos - p.pos_begin) * 8 + half * NCH;
 #pragma unroll 1
                     for (int c = 0; c < NCH; ++c) {
                         uint32_t v[32];
-                        float nv[32];
                         tmem_ld32(taddr + c * 32, v);
-                        if constexpr (L2) lds_f32x32(ns_s + c * 128, nv);
                         tmem_ld_wait();
                         if (q_ok) {
+                            const uint32_t r0 = row0 + col0 + c * 32;        // multiple of 32: one tombstone word
+                            uint32_t dead = p.tomb ? p.tomb[r0 >> 5] : 0u;
+                            if (r0 + 32 > p.n_rows) dead |= r0 >= p.n_rows ? 0xFFFFFFFFu : ~((1u << (p.n_rows - r0)) - 1u);
+                            float s[32];
+                            if constexpr (L2) {
+                                float nv[32];
+                                lds_f32x32(ns_s + c * 128, nv);
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) s[j] = fmaf(2.0f, __uint_as_float(v[j]), -nv[j]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) s[j] = __uint_as_float(v[j]);
+                            }
+                            float m = __int_as_float(0xff800000);
+                            int jm = -1;
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
-                                const float dot = __uint_as_float(v[j]);
-                                float a;
-                                if constexpr (L2) a = fmaf(-2.0f, dot, nv[j]);
-                                else a = -dot;
-                                dd[c * 32 + j] = make_key(a, row0 + col0 + c * 32 + j);
+                                const bool better = !((dead >> j) & 1u) && s[j] > m;     // NaN never wins
+                                m = better ? s[j] : m;
+                                jm = better ? j : jm;
                             }
+                            dd[c] = jm >= 0 ? make_key(-m, r0 + jm) : KEY_SENTINEL;
                         }
                     }
                     // all TMEM reads of this accumulator are done: one arrive per warp on the LEADER's barrier
@@ -581,7 +597,8 @@ struct SelectParams {
     uint64_t* buf; int* cnt; int cap; int kp;
     float* thr; int* overflow;
     const uint32_t* tomb; uint32_t n_rows;
-    int dense_cnt;            // > 0: level 0 wrote this many keys per query at fixed positions
+    int probe_cnt;            // > 0: the probe level wrote this many keys per query at fixed positions; they only
+                              // yield the first threshold (the levels that follow visit the probed tiles again)
     int thr_rank;             // the next level's threshold = the thr_rank-th best kept value (<= kp)
     int np2;                  // keys the shared array sk[] holds (>= cap); kept[kp] lies behind it
 };
@@ -597,7 +614,7 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectParams p) {
     __shared__ int s_valid, s_c1, s_c2;
     const size_t q = blockIdx.x;
     uint64_t* b = p.buf + q * (size_t)p.cap;
-    int n = p.dense_cnt > 0 ? p.dense_cnt : p.cnt[q];
+    int n = p.probe_cnt > 0 ? p.probe_cnt : p.cnt[q];
     if (n > p.cap) {
         if (threadIdx.x == 0) p.overflow[q] = 1;
         n = p.cap;
@@ -625,20 +642,22 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectParams p) {
     __syncthreads();
     const int n_valid = s_valid;
     __syncthreads();
-    if (n_valid <= p.kp) {
-        // everything valid is kept (no threshold yet)
+    const bool probe = p.probe_cnt > 0;
+    const int want = probe ? p.thr_rank : p.kp;   // 1-based rank of the key we are looking for
+    if (probe && n_valid < want) {
+        if (threadIdx.x == 0) { p.cnt[q] = 0; p.thr[q] = __int_as_float(0x7f800000); }   // too few live rows probed
+        return;
+    }
+    if (!probe && n_valid <= p.kp) {
+        // everything valid is kept
         for (int i = threadIdx.x; i < n; i += THREADS) {
             const uint64_t key = sk[i];
             if (key != KEY_SENTINEL) b[atomicAdd(&s_c1, 1)] = key;
         }
         __syncthreads();
         for (int i = n_valid + threadIdx.x; i < p.kp; i += THREADS) b[i] = KEY_SENTINEL;
-        if (threadIdx.x == 0) {
-            p.cnt[q] = p.kp;
-            // level 0: nothing has been dropped yet.  Later levels: rows dropped so far are >= the current
-            // threshold and nothing tighter is known: it stays
-            if (p.dense_cnt > 0) p.thr[q] = __int_as_float(0x7f800000);
-        }
+        // rows dropped so far are >= the current threshold and nothing tighter is known: it stays
+        if (threadIdx.x == 0) p.cnt[q] = p.kp;
         return;
     }
     // The passes start at the highest byte in which the values differ: the bytes above it (sign, exponent) are
@@ -647,7 +666,7 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectParams p) {
     const int first_pass = diff ? 3 - ((31 - __clz(diff)) >> 3) : 4;     // all values equal: no pass
     uint32_t mask = first_pass == 0 ? 0u : (first_pass == 4 ? 0xFFFFFFFFu : ~((1u << (32 - 8 * first_pass)) - 1u));
     if (threadIdx.x == 0) {
-        s_rank = (uint32_t)p.kp;                       // 1-based rank of the key we are looking for
+        s_rank = (uint32_t)want;
         s_prefix = s_min & mask;
     }
     __syncthreads();
@@ -692,7 +711,11 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectParams p) {
         mask |= 0xFFu << shift;
         __syncthreads();
     }
-    const uint32_t T = s_prefix;                  // distance bits of the KP-th best key
+    const uint32_t T = s_prefix;                  // distance bits of the want-th best key
+    if (probe) {
+        if (threadIdx.x == 0) { p.cnt[q] = 0; p.thr[q] = ordered_to_float(T); }
+        return;
+    }
     const int need_eq = (int)s_rank;              // how many keys with exactly these bits to keep
     const int n_less = p.kp - need_eq;
     uint64_t* kept = sk + p.np2;                  // [kp] behind the key array
@@ -755,50 +778,8 @@ struct RerankParams {
     const uint32_t* tomb; uint32_t n_rows;
 };
 
-// exact fp32 distance of (query, row) in the scan kernel's summation order -> sortable key; whole warp
-template <typename T>
-__device__ __forceinline__ uint64_t exact_key(const RerankParams& p, const float* qv, uint32_t row, int lane) {
-    const int nld16 = p.row_bytes / 512;
-    constexpr int PER16 = 16 / sizeof(T);
-    const uint8_t* rp = reinterpret_cast<const uint8_t*>(p.rows) + (size_t)row * p.row_bytes;
-    float acc = 0.0f;
-    for (int ch = 0; ch < nld16; ++ch) {
-        float dv[PER16], qq[PER16];
-        if constexpr (sizeof(T) == 4) {
-            const float4 t = *reinterpret_cast<const float4*>(rp + (size_t)(ch * 32 + lane) * 16);
-            dv[0] = t.x; dv[1] = t.y; dv[2] = t.z; dv[3] = t.w;
-        } else {
-            const uint4 t = *reinterpret_cast<const uint4*>(rp + (size_t)(ch * 32 + lane) * 16);
-            const __half2* h = reinterpret_cast<const __half2*>(&t);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 f = __half22float2(h[i]);
-                dv[2 * i] = f.x; dv[2 * i + 1] = f.y;
-            }
-        }
-        const float* qp = qv + (size_t)(ch * 32 + lane) * PER16;
-#pragma unroll
-        for (int e = 0; e < PER16; e += 4) {
-            const float4 t = *reinterpret_cast<const float4*>(qp + e);
-            qq[e] = t.x; qq[e + 1] = t.y; qq[e + 2] = t.z; qq[e + 3] = t.w;
-        }
-        if (p.metric == 0) {
-#pragma unroll
-            for (int e = 0; e < PER16; ++e) {
-                const float t = dv[e] - qq[e];
-                acc = fmaf(t, t, acc);
-            }
-        } else {
-#pragma unroll
-            for (int e = 0; e < PER16; ++e) acc = fmaf(dv[e], qq[e], acc);
-        }
-    }
-    acc = warp_sum_butterfly(acc);
-    const float dist = p.metric == 0 ? acc : 1.0f - acc;
-    return make_key(dist, p.labels[row]);
-}
-
-// Same arithmetic for NR rows at once: the loads of all rows (4 lane chunks each) are issued before the first FMA,
+// Exact fp32 distances of (query, row) in the scan kernel's summation order -> sortable keys; whole warp, NR rows
+// at once: the loads of all rows (4 lane chunks each) are issued before the first FMA,
 // so a warp keeps NR x 4 x 16 bytes in flight per lane instead of 16 (the window re-rank reads a handful of rows
 // per query: its time is memory latency, not bandwidth).
 template <typename T, int NR>
@@ -874,62 +855,6 @@ __device__ __forceinline__ void exact_keys(const RerankParams& p, const float* q
 __device__ __forceinline__ float approx_eps(const RerankParams& p, float qn2, float dmax2, float at) {
     const float eb = p.eps_rel * sqrtf(qn2) * sqrtf(dmax2) + p.eps_abs * (sqrtf(qn2) + sqrtf(dmax2));
     return p.metric == 0 ? 2.0f * eb + 4e-7f * (qn2 + dmax2 + fabsf(at)) : eb + 4e-7f * (1.0f + fabsf(at));
-}
-
-template <typename T, int KP>
-__global__ void __launch_bounds__(256) rerank_kernel(const RerankParams p) {
-    pdl_prologue();
-    __shared__ uint64_t ek[KP];
-    const int q = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint64_t* ap = p.approx + (size_t)q * p.stride;
-    const float* qv = p.q + (size_t)q * p.ld;
-    for (int c = warp; c < KP; c += 8) {
-        const uint64_t key = ap[c];
-        const uint64_t out = key != KEY_SENTINEL ? exact_key<T>(p, qv, (uint32_t)key, lane) : KEY_SENTINEL;
-        if (lane == 0) ek[c] = out;
-    }
-    __syncthreads();
-    // bitonic sort of KP keys by 256 threads
-    for (int size = 2; size <= KP; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int t = threadIdx.x; t < KP / 2; t += 256) {
-                const int i = 2 * t - (t & (stride - 1)), j = i + stride;
-                const bool asc = (i & size) == 0;
-                const uint64_t a = ek[i], b = ek[j];
-                if ((a > b) == asc) { ek[i] = b; ek[j] = a; }
-            }
-            __syncthreads();
-        }
-    }
-    const int k = p.k;
-    for (int i = threadIdx.x; i < k; i += 256) {
-        const uint64_t key = ek[i];
-        const bool real = key != KEY_SENTINEL;
-        p.out_ids[(size_t)q * k + i] = real ? (int64_t)key_label(key) : -1;
-        p.out_dist[(size_t)q * k + i] = real ? key_dist(key) : __int_as_float(0x7f800000);
-    }
-    if (threadIdx.x == 0) {
-        int cnt = 0;
-        for (int i = 0; i < k; ++i) cnt += ek[i] != KEY_SENTINEL;
-        if (p.out_counts) p.out_counts[q] = cnt;
-        bool ok = true;
-        const float a_tau = p.tau[q];
-        if (a_tau < __int_as_float(0x7f800000)) {   // candidate list full: rows outside it exist, prove they cannot matter
-            const float qn2 = p.qn2[q];
-            const float dmax2 = __uint_as_float(*p.max_sqnorm_bits);
-            const float eb = p.eps_rel * sqrtf(qn2) * sqrtf(dmax2) + p.eps_abs * (sqrtf(qn2) + sqrtf(dmax2));
-            float tau, eps;
-            if (p.metric == 0) { tau = a_tau + qn2; eps = 2.0f * eb + 4e-7f * (qn2 + dmax2 + fabsf(tau)); }
-            else               { tau = 1.0f + a_tau; eps = eb + 4e-7f * (1.0f + fabsf(tau)); }
-            const uint64_t kth = ek[k - 1];
-            ok = kth != KEY_SENTINEL && key_dist(kth) < tau - eps;
-        }
-        if (p.overflow[q]) ok = false;
-        // an element above the fp16 range became +-inf in the operand plane (|x_i| <= ||x||): no bound holds
-        if (p.f16_range && (p.qn2[q] >= 4.0e9f || __uint_as_float(*p.max_sqnorm_bits) >= 4.0e9f)) ok = false;
-        p.flags[q] = ok ? 0 : 1;
-        if (!ok) atomicAdd(p.n_flagged, 1);
-    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1201,7 +1126,15 @@ static int kp_for_k(int k) {
     while (kp < 2 * k) kp <<= 1;
     return kp;
 }
-static int cap_for_kp(int kp) { return std::max(16 * kp, GT_DENSE_TILES * GT_BN); }
+static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
+// probe tiles: 8 chunk minima per tile and query; with 4x as many chunks as the threshold rank the rank-th chunk
+// minimum is close to the rank-th best probed row (VDB_PROBE_TILES / VDB_GROWTH: sweeps, tools/level_sweep.sh)
+static int probe_tiles(int rank) {
+    static const int v = env_int("VDB_PROBE_TILES", 0);
+    return std::max(v > 0 ? v : GT_PROBE_TILES, (rank + 1) / 2);
+}
+static int level_growth() { static const int v = std::max(2, env_int("VDB_GROWTH", GT_LEVEL_GROWTH)); return v; }
+static int cap_for_kp(int kp) { return 16 * kp; }
 
 bool gemm_topk_supported(int dim, int ld, bool f16, int k, size_t n_rows) {
     (void)dim;
@@ -1244,20 +1177,6 @@ static cudaError_t launch_rerank_window(int kp, const RerankParams& rp, size_t n
         configured = smem;
     }
     cudaError_t le = launch_pdl(rerank_window_kernel<T>, dim3((unsigned)nq), dim3(RW_THREADS), smem, st, rp, kp);
-    count_launch();
-    return le != cudaSuccess ? le : cudaGetLastError();
-}
-
-template <typename T>
-static cudaError_t launch_rerank(int kp, const RerankParams& rp, size_t nq, cudaStream_t st) {
-    cudaError_t le = cudaSuccess;
-    switch (kp) {
-        case 32: le = launch_pdl(rerank_kernel<T, 32>, dim3((unsigned)nq), dim3(256), 0, st, rp); break;
-        case 64: le = launch_pdl(rerank_kernel<T, 64>, dim3((unsigned)nq), dim3(256), 0, st, rp); break;
-        case 128: le = launch_pdl(rerank_kernel<T, 128>, dim3((unsigned)nq), dim3(256), 0, st, rp); break;
-        case 256: le = launch_pdl(rerank_kernel<T, 256>, dim3((unsigned)nq), dim3(256), 0, st, rp); break;
-        default: return cudaErrorInvalidValue;
-    }
     count_launch();
     return le != cudaSuccess ? le : cudaGetLastError();
 }
@@ -1350,7 +1269,7 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
     gp.bits = 0;
     while ((1 << gp.bits) < n_tiles) ++gp.bits;
     const int n_pos = 1 << gp.bits;          // positions in bit-reversed order; those mapping past n_tiles are skipped
-    gp.sqnorm = a.sqnorm; gp.thr = w->thr; gp.buf = w->buf; gp.cnt = w->cnt; gp.cap = cap;
+    gp.sqnorm = a.sqnorm; gp.thr = w->thr; gp.buf = w->buf; gp.cnt = w->cnt; gp.cap = cap; gp.tomb = a.tomb;
     const bool l2 = a.metric == 0;
 
     SelectParams sp{};
@@ -1367,54 +1286,57 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
     sp.np2 = sel_np;
     const size_t sel_smem = ((size_t)sel_np + kp) * 8;
 
-    // levels over positions: [0, d0) dense, then each level GT_LEVEL_GROWTH x what has been seen, the last one
-    // takes what is left if that is at most 1.5 x the growth
-    // VDB_WINDOW=0: the previous chain (select after every level, re-rank of all k' candidates)
-    static const bool window = [] { const char* v = getenv("VDB_WINDOW"); return !(v && atoi(v) == 0); }();
-    // (only with the window re-rank, whose certificate uses the last level's threshold; the previous chain's
-    // certificate assumes that threshold is the k'-th best)
-    static const bool tight_rank = window && [] { const char* v = getenv("VDB_TIGHT"); return !(v && atoi(v) == 0); }();
+    // Level plan over positions (bit-reversed tile order).  Probe: the first P positions, chunk minima only ->
+    // first threshold.  Then levels from position 0 on, each covering level_growth() x the positions that informed
+    // its threshold; the last one takes what is left if that is at most 1.5 x the growth.  A select follows every
+    // level but the last (the window re-rank reads the last level's buffer as it is).
+    // Threshold rank: while at most a quarter of the shard has been seen, max(k'/2, 1.6 k) instead of k' -- the
+    // sample's k'-th best is then far looser than the certificate needs, and every row that passes costs a trip
+    // through the key rings.  The k' best stay candidates either way.
     const int kq = std::max(kp / 2, std::min(kp, (16 * a.k + 9) / 10));
-    int pos = 0;
-    int level = 0;
-    while (pos < n_pos) {
-        int next;
-        if (level == 0) next = std::min(n_pos, GT_DENSE_TILES);
-        else {
-            // positions scale with tiles by n_pos / n_tiles (< 2): use positions directly
-            long want = (long)pos * GT_LEVEL_GROWTH;
-            next = (int)std::min<long>(n_pos, pos + want);
-            if ((long)(n_pos - pos) <= want + want / 2) next = n_pos;
-        }
-        gp.pos_begin = pos; gp.pos_end = next; gp.dense = level == 0 ? 1 : 0;
-        gp.S = choose_slices(MB, next - pos, num_pairs_max);
+    auto rank_after = [&](int seen) { return 4L * seen <= n_pos ? kq : kp; };
+    auto run_level = [&](int p0, int p1, bool probe) -> cudaError_t {
+        gp.pos_begin = p0; gp.pos_end = p1; gp.probe = probe ? 1 : 0;
+        gp.S = choose_slices(MB, p1 - p0, num_pairs_max);
         gp.n_items = MB * gp.S;
         const int grid = 2 * std::min(gp.n_items, num_pairs_max);   // whole CTA pairs
-        if (level == 0) {
-            // dense level writes fixed positions; positions whose tile is past the end must read as sentinel:
-            // fill the buffer only when there is such a position (never for shards of a few thousand rows or more)
-            bool all_valid = true;
-            for (int pp = pos; pp < next; ++pp) all_valid = all_valid && (int)bitrev((uint32_t)pp, gp.bits) < n_tiles;
-            if (!all_valid && (e = cudaMemsetAsync(w->buf, 0xFF, a.nq * (size_t)cap * sizeof(uint64_t), st)) != cudaSuccess) return e;
-        }
+        cudaError_t le;
         if (a.prof_begin) a.prof_begin(a.prof_ctx, st);
-        if (g16) e = l2 ? launch_gemm<true, true>(tmA, tmB, gp, grid, st) : launch_gemm<true, false>(tmA, tmB, gp, grid, st);
-        else       e = l2 ? launch_gemm<false, true>(tmA, tmB, gp, grid, st) : launch_gemm<false, false>(tmA, tmB, gp, grid, st);
+        if (g16) le = l2 ? launch_gemm<true, true>(tmA, tmB, gp, grid, st) : launch_gemm<true, false>(tmA, tmB, gp, grid, st);
+        else       le = l2 ? launch_gemm<false, true>(tmA, tmB, gp, grid, st) : launch_gemm<false, false>(tmA, tmB, gp, grid, st);
         if (a.prof_end) a.prof_end(a.prof_ctx, st);
-        if (e != cudaSuccess) return e;
-        sp.dense_cnt = level == 0 ? (next - pos) * GT_BN : 0;
-        // threshold rank: while at most a quarter of the shard has been seen, a tighter rank than k' (see K2s)
-        sp.thr_rank = (tight_rank && 4L * next <= n_pos) ? kq : kp;
-        // the window re-rank reads the last level's buffer as it is (the dense level's buffer has no count)
-        if (window && next == n_pos && level > 0) break;
+        return le;
+    };
+    auto run_select = [&](int probe_cnt, int thr_rank) -> cudaError_t {
+        sp.probe_cnt = probe_cnt; sp.thr_rank = thr_rank;
         // one block per query; thousands of queries with a few hundred keys each: small blocks, so that more
         // of them are resident and the barrier chain of a block is short
-        if (a.nq >= 4096 && cap <= 1024) e = launch_pdl(select_kernel<64>, dim3((unsigned)a.nq), dim3(64), sel_smem, st, sp);
-        else e = launch_pdl(select_kernel<256>, dim3((unsigned)a.nq), dim3(256), sel_smem, st, sp);
+        cudaError_t le;
+        if (a.nq >= 4096 && cap <= 1024) le = launch_pdl(select_kernel<64>, dim3((unsigned)a.nq), dim3(64), sel_smem, st, sp);
+        else le = launch_pdl(select_kernel<256>, dim3((unsigned)a.nq), dim3(256), sel_smem, st, sp);
         count_launch();
-        if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) return e;
-        pos = next;
-        ++level;
+        return le != cudaSuccess ? le : cudaGetLastError();
+    };
+    {
+        const int P = std::min(n_pos, probe_tiles(kq));
+        // the probe writes fixed positions; positions whose tile is past the end must read as sentinel: fill the
+        // buffer only when there is such a position (never for shards of a few thousand rows or more)
+        bool all_valid = true;
+        for (int pp = 0; pp < P; ++pp) all_valid = all_valid && (int)bitrev((uint32_t)pp, gp.bits) < n_tiles;
+        if (!all_valid && (e = cudaMemsetAsync(w->buf, 0xFF, a.nq * (size_t)cap * sizeof(uint64_t), st)) != cudaSuccess) return e;
+        if ((e = run_level(0, P, true)) != cudaSuccess) return e;
+        if ((e = run_select(P * 8, rank_after(P))) != cudaSuccess) return e;
+        int seen = P, pos = 0;
+        while (pos < n_pos) {
+            // positions scale with tiles by n_pos / n_tiles (< 2): use positions directly
+            const long want = (long)seen * level_growth();
+            int next = (int)std::min<long>(n_pos, pos + want);
+            if ((long)(n_pos - pos) <= want + want / 2) next = n_pos;
+            if ((e = run_level(pos, next, false)) != cudaSuccess) return e;
+            if (next == n_pos) break;
+            if ((e = run_select(0, rank_after(next))) != cudaSuccess) return e;
+            seen = pos = next;
+        }
     }
 
     if (!a.prepped && (e = cudaMemsetAsync(w->n_flagged, 0, sizeof(int), st)) != cudaSuccess) return e;
@@ -1433,8 +1355,7 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
     rp.out_ids = a.out_ids; rp.out_dist = a.out_dist; rp.out_counts = a.out_counts;
     rp.flags = w->flags; rp.n_flagged = w->n_flagged;
     rp.cnt = w->cnt; rp.cap = cap; rp.tomb = a.tomb; rp.n_rows = a.n_rows;
-    if (window) e = a.f16 ? launch_rerank_window<__half>(kp, rp, a.nq, st) : launch_rerank_window<float>(kp, rp, a.nq, st);
-    else e = a.f16 ? launch_rerank<__half>(kp, rp, a.nq, st) : launch_rerank<float>(kp, rp, a.nq, st);
+    e = a.f16 ? launch_rerank_window<__half>(kp, rp, a.nq, st) : launch_rerank_window<float>(kp, rp, a.nq, st);
     if (e != cudaSuccess) return e;
     return cudaSuccess;
 }
