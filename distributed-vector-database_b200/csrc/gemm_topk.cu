@@ -88,7 +88,7 @@ struct GemmParams {
     int dbg;                 // experiments only: 2 = epilogue releases TMEM at once, 8 = TMEM reads but no filtering
     const float* sqnorm;     // [n_rows] (L2 only)
     const float* thr;        // [nq] threshold of this level (approximate distance); unused by the probe
-    const uint32_t* tomb;    // tombstone bitmap (probe only: a dead row must not stand for its chunk)
+    const uint32_t* tomb;    // tombstone bitmap or null: dead rows neither stand for a probe chunk nor pass a level
     uint64_t* buf;           // [nq][cap] candidate keys (approximate distance bits << 32 | row)
     int* cnt;                // [nq] keys in buf
     int cap;
@@ -530,6 +530,10 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         const float m = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])),
                                               fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
                         if (m > nthr) {
+                            // deleted rows stop here (p.tomb is null while the shard has none): a shard that is
+                            // mostly tombstones would otherwise fill the level buffers with dead survivors.
+                            // The chunk's 32 rows share one bitmap word.
+                            const uint32_t dead = p.tomb ? __ldg(p.tomb + ((row0 + col0 + c * 32) >> 5)) : 0u;
 #pragma unroll
                             for (int gi = 0; gi < 8; ++gi) {
                                 if (g[gi] > nthr) {
@@ -541,7 +545,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                                     }
 #pragma unroll
                                     for (int e = 0; e < 4; ++e) {
-                                        if (s[4 * gi + e] > nthr) {
+                                        if (s[4 * gi + e] > nthr && !((dead >> (4 * gi + e)) & 1u)) {
                                             st_shared_u64(my_ring_s + slot * 8,
                                                           make_key(-s[4 * gi + e], row0 + col0 + c * 32 + 4 * gi + e));
                                             ++head;
@@ -1325,16 +1329,22 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
         for (int pp = 0; pp < P; ++pp) all_valid = all_valid && (int)bitrev((uint32_t)pp, gp.bits) < n_tiles;
         if (!all_valid && (e = cudaMemsetAsync(w->buf, 0xFF, a.nq * (size_t)cap * sizeof(uint64_t), st)) != cudaSuccess) return e;
         if ((e = run_level(0, P, true)) != cudaSuccess) return e;
-        if ((e = run_select(P * 8, rank_after(P))) != cudaSuccess) return e;
+        int rank = rank_after(P);              // rank behind the current threshold
+        if ((e = run_select(P * 8, rank)) != cudaSuccess) return e;
         int seen = P, pos = 0;
         while (pos < n_pos) {
             // positions scale with tiles by n_pos / n_tiles (< 2): use positions directly
             const long want = (long)seen * level_growth();
             int next = (int)std::min<long>(n_pos, pos + want);
-            if ((long)(n_pos - pos) <= want + want / 2) next = n_pos;
+            // stretch the last level over what is left (up to 1.5 x the growth) unless the expected number of
+            // survivors (rank x rows of the level / rows behind the threshold, + the k' carried) comes near the
+            // buffer capacity
+            const long left = n_pos - pos;
+            if (left <= want + want / 2 && (long)rank * left / seen + kp <= (long)cap * 11 / 20) next = n_pos;
             if ((e = run_level(pos, next, false)) != cudaSuccess) return e;
             if (next == n_pos) break;
-            if ((e = run_select(0, rank_after(next))) != cudaSuccess) return e;
+            rank = rank_after(next);
+            if ((e = run_select(0, rank)) != cudaSuccess) return e;
             seen = pos = next;
         }
     }

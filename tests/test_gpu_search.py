@@ -349,6 +349,63 @@ def test_tensor_path_batch_4096_small_blocks_select(vdb):
     assert ix.get_stat("fallback_queries") == 0
 
 
+@pytest.mark.parametrize("metric,k", [("cosine", 10), ("l2", 16), ("ip", 32), ("l2", 100)])
+def test_tensor_path_levels_no_fallback(vdb, metric, k):
+    """150k rows = 586 tiles: probe + two threshold levels (tight rank, then k') + window re-rank.  Random data must
+    neither overflow a level buffer nor fail the certificate for any k class (k' = 32 / 64 / 256)."""
+    n, dim = 150_000, 64
+    ix = vdb.Index(metric, dim)
+    ix.init_index(n)
+    ix.add_synthetic(R.SEED_DB, 0, n)
+    q = R.synth_rows(R.SEED_QUERY, 0, 300, dim)
+    ix.set_option("path", 2)
+    lt, dt, ct = ix.knn_query_padded(q, k)
+    assert ix.get_stat("tensor_batches") >= 1 and ix.get_stat("fallback_queries") == 0
+    from oracle import c_ref
+    raw = c_ref.synth_rows(R.SEED_DB, 0, n, dim)
+    stored = c_ref.normalize(raw) if metric == "cosine" else raw
+    want_l, _, _ = c_ref.knn(q, stored, None, k, metric)
+    for i in range(len(q)):
+        assert ct[i] == k
+        if not np.array_equal(lt[i], want_l[i]):
+            u = np.unique(np.concatenate([want_l[i], lt[i]]))
+            msg = R.check_topk(lt[i], dt[i], q[i], stored[u], u, k, metric, rtol=RTOL)
+            assert msg is None, f"query {i}: {msg}"
+
+
+def test_tensor_path_heavy_tombstones(vdb):
+    """70 % of a 40k-row shard deleted (whole 32-row chunks among them): the probe must pick live rows for its
+    chunk minima, the levels must drop dead survivors, results stay exact."""
+    n = 40_000
+    ix, raw = build(vdb, "cosine", n, dim=128)
+    rng = np.random.default_rng(5)
+    dead = set(np.flatnonzero(rng.random(n) < 0.6).tolist())
+    for c in range(0, n // 32, 3):                     # every third chunk entirely
+        dead.update(range(c * 32, c * 32 + 32))
+    dead = sorted(dead)
+    ix.mark_deleted(dead)
+    ix.set_option("path", 2)
+    q = R.synth_rows(R.SEED_QUERY, 0, 64, 128)
+    assert_parity(ix, raw, "cosine", "f32", q, 10, deleted=dead)
+    assert ix.get_stat("tensor_batches") >= 1 and ix.get_stat("fallback_queries") <= 2
+
+
+def test_tensor_path_clustered_insertion_order(vdb):
+    """rows inserted cluster by cluster (each query's neighbours sit in a few adjacent tiles): thresholds taken
+    from a sample of tiles may be loose or tight, the results must not depend on it."""
+    rng = np.random.default_rng(9)
+    centers = rng.normal(size=(40, 128)).astype(np.float32)
+    rows = np.concatenate([c[None, :] + 0.25 * rng.normal(size=(1500, 128)).astype(np.float32) for c in centers])
+    n = len(rows)
+    ix = vdb.Index("l2", 128)
+    ix.init_index(n)
+    ix.add_items(rows, np.arange(n))
+    ix.set_option("path", 2)
+    q = (centers[rng.integers(0, 40, size=100)] + 0.25 * rng.normal(size=(100, 128))).astype(np.float32)
+    assert_parity(ix, rows, "l2", "f32", q, 10)
+    assert ix.get_stat("tensor_batches") >= 1
+
+
 def test_concurrent_searches_and_a_writer_on_one_index(vdb):
     """the library itself is safe for concurrent searches (one stream + workspace per call in flight) plus one
     writer (SURVEY 8b threading): 6 threads hammer scan and tensor searches while rows are appended; every
