@@ -459,11 +459,11 @@ def run_ours(a):
         cpu = None
         recall = None
         if not a.no_cpu and world == 1:
-            # bounded sample of the same workload, sized from a short probe to ~12 s of CPU work on all host threads
+            # bounded sample of the same workload, sized from a short (cold) probe to 10-20 s of CPU work on all host threads
             nq_cpu = a.cpu_queries
             if not nq_cpu:
                 probe_qps = cpu_knn_qps(a, 64)[0]
-                nq_cpu = int(min(B * 8, max(64, 64 * round(12.0 * probe_qps / 64))))
+                nq_cpu = int(min(B * 8, max(64, 64 * round(20.0 * probe_qps / 64))))
             qps, cores, desc, want_ids = cpu_knn_qps(a, nq_cpu, return_ids=True)
             cpu = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
                    "sample": desc + " (oracle/knn_ref.c exact scan, OpenMP)"}

@@ -879,14 +879,14 @@ __device__ __forceinline__ float approx_eps(const RerankParams& p, float qn2, fl
 //   3. a_k = k-th smallest of the list (radix select over the bits in which the list's values differ)
 //   4. window = list keys at or below a_k + 2 eps
 //   5. exact distances, two rows in flight per warp   6. results written at their rank (by counting), certificate
-constexpr int RW_THREADS = 128;
+constexpr int RW_MAX_THREADS = 256;            // 128 threads per query for k' <= 64, 256 above
 
-// value bits of the `rank`-th smallest (1-based) of the n > = rank real keys in sk[] (no sentinels).  Radix select
+// value bits of the `rank`-th smallest (1-based) of the n >= rank keys in sk[].  Radix select
 // from the highest byte in which the values differ: the bytes above it are common to all keys and would send every
 // atomicAdd of a pass to ONE histogram bin.  Stops as soon as the bin that holds the rank has a single key.
 __device__ __forceinline__ uint32_t block_kth_bits(const uint64_t* sk, int n, int rank, int* hist, uint32_t* sh) {
     // sh[0] = min, sh[1] = max, sh[2] = prefix, sh[3] = rank, sh[4] = count in the chosen bin
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, RW_THREADS = blockDim.x;
     if (tid == 0) { sh[0] = 0xFFFFFFFFu; sh[1] = 0u; }
     __syncthreads();
     uint32_t lo = 0xFFFFFFFFu, hi = 0u;
@@ -954,7 +954,7 @@ __device__ __forceinline__ uint32_t block_kth_bits(const uint64_t* sk, int n, in
 }
 
 template <typename T>
-__global__ void __launch_bounds__(RW_THREADS) rerank_window_kernel(const RerankParams p, const int kp) {
+__global__ void __launch_bounds__(RW_MAX_THREADS) rerank_window_kernel(const RerankParams p, const int kp) {
     pdl_prologue();
     extern __shared__ uint64_t wsm[];
     uint64_t* sk = wsm;                // [cap] buffer keys; from stage 4 the window keys
@@ -965,7 +965,7 @@ __global__ void __launch_bounds__(RW_THREADS) rerank_window_kernel(const RerankP
     __shared__ int s_m1, s_m;
     __shared__ float s_kth;
     __shared__ int s_have_kth;
-    const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, RW_THREADS = blockDim.x;
     const int k = p.k;
     const uint64_t* b = p.approx + (size_t)q * p.stride;
     int n = p.cnt[q];
@@ -994,12 +994,21 @@ __global__ void __launch_bounds__(RW_THREADS) rerank_window_kernel(const RerankP
     __syncthreads();
     // ---- 1. bound from the carried keys (sentinels sort last: fewer than k real ones -> keep everything)
     const int nc = min(n, kp);
-    for (int t = tid; t < nc; t += RW_THREADS) {
-        const uint64_t key = sk[t];
-        int rank = 0;
-        for (int j = 0; j < nc; ++j) rank += sk[j] < key;
-        if (rank == k - 1) s_a1 = (uint32_t)(key >> 32);      // keys are distinct (rows are), sentinels are not:
-    }                                                          // a sentinel of rank k-1 writes 0xFFFFFFFF as well
+    if (nc > 64) {
+        // k' of 128 / 256: radix select (sentinels carry the largest value bits: a sentinel at rank k reads as
+        // "keep everything", like the initial value)
+        if (nc >= k) {
+            const uint32_t a1 = block_kth_bits(sk, nc, k, hist, sh);
+            if (tid == 0) s_a1 = a1;
+        }
+    } else {
+        for (int t = tid; t < nc; t += RW_THREADS) {
+            const uint64_t key = sk[t];
+            int rank = 0;
+            for (int j = 0; j < nc; ++j) rank += sk[j] < key;
+            if (rank == k - 1) s_a1 = (uint32_t)(key >> 32);  // keys are distinct (rows are), sentinels are not:
+        }                                                      // a sentinel of rank k-1 writes 0xFFFFFFFF as well
+    }
     __syncthreads();
     // ---- 2. the keys that can still matter
     const uint32_t w1 = s_a1 == 0xFFFFFFFFu ? 0xFFFFFFFFu : window_bits(s_a1);
@@ -1180,7 +1189,7 @@ static cudaError_t launch_rerank_window(int kp, const RerankParams& rp, size_t n
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    cudaError_t le = launch_pdl(rerank_window_kernel<T>, dim3((unsigned)nq), dim3(RW_THREADS), smem, st, rp, kp);
+    cudaError_t le = launch_pdl(rerank_window_kernel<T>, dim3((unsigned)nq), dim3(kp <= 64 ? 128 : RW_MAX_THREADS), smem, st, rp, kp);
     count_launch();
     return le != cudaSuccess ? le : cudaGetLastError();
 }
