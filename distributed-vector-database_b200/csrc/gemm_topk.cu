@@ -1,8 +1,8 @@
 // gemm_topk.cu -- K2: batched search as a dense contraction on the 5th-gen tensor cores, fused
-// with threshold filtering of the scores, + K2s (select) and K4 (exact fp32 re-rank + coverage
-// certificate).
+// with threshold filtering of the scores, + K2s (select between levels) and K4w (exact fp32
+// re-rank of the keys that can still matter + coverage certificate).
 //
-// Replaces hnswlib.Index.knn_query for nq > 8 (reference call site src/datanode/handler.py:364;
+// Replaces hnswlib.Index.knn_query for batches (reference call site src/datanode/handler.py:364;
 // hnswlib accepts [nq, dim], the reference only ever passes one row).
 //
 // K2 (gemm_filter_kernel): persistent CTA PAIRS (cluster of 2, tcgen05 cta_group::2), 384 threads:
@@ -21,18 +21,19 @@
 //            that beat the query's threshold (a key ring in shared memory; nothing else leaves the SM).
 //   The [nq, n_rows] distance matrix never exists in memory.
 //
-// Thresholds come from LEVELS: the shard's 256-row tiles are visited in bit-reversed order, so
-// every prefix of the order is an evenly spread sample.  Level 0 (a few tiles) keeps everything;
-// K2s then selects each query's k' best approximate keys and their k'-th value becomes the
-// threshold of level 1, which is 8x larger, and so on (expected survivors per level: 8 k').  A row
-// that fails a threshold is provably not among the k' best approximate rows of the union.
+// Thresholds come from a PROBE and LEVELS: the shard's 256-row tiles are visited in bit-reversed
+// order, so every prefix of the order is an evenly spread sample.  The probe (the first 16 tiles)
+// writes only the best live row of every 32-score chunk; the r-th smallest chunk minimum is the first
+// threshold.  Levels then start over at tile 0, each 8x larger than what informed its threshold;
+// between levels K2s keeps each query's k' best approximate keys and publishes the next threshold
+// (the k'-th best, or a tighter rank while little of the shard has been seen).  Thresholds only
+// tighten, and a row that is not in a query's buffer has approximate distance >= its threshold.
 //
-// K4 recomputes the final k' candidates exactly (same summation order as the scan kernel, so
-// batched and single-query searches return bit-identical distances) and proves the result: every
-// non-candidate has approximate distance >= tau (the k'-th approximate distance), hence exact
-// distance >= tau - eps with eps a rigorous bound on the tf32 / fp16-query rounding error; if the
-// k-th exact distance is < tau - eps the exact top-k is inside the candidate set.  Queries that fail
-// the certificate (or whose candidate buffer overflowed) are re-searched with the exact scan.
+// K4w reads the last level's buffer as it is: the keys within 2 eps of the k-th smallest approximate
+// value are recomputed exactly (same summation order as the scan kernel, so batched and single-query
+// searches return bit-identical distances), eps a rigorous bound on the tf32 / fp16 rounding error;
+// if the k-th exact distance is < last threshold - eps no row outside the buffer can enter the top-k.
+// Queries that fail this certificate (or whose buffer overflowed) are re-searched with the exact scan.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
