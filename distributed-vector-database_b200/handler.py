@@ -38,11 +38,93 @@ def _default_index_factory(space: str, dim: int, max_elements: int, store_dtype:
     return ix
 
 
+class _MicroBatcher:
+    """Coalesces concurrent single-query searches into one batched index call.
+
+    The reference serves `search` from a pool of 5 Thrift worker threads (datanode/server.py:25-28) that all
+    queue on one lock (handler.py:23, :348): five concurrent requests cost five index queries back to back.  Here
+    the first thread to arrive becomes the leader: it waits `max_wait_s` for the others to enqueue, runs ONE
+    `run_batch(queries[n, dim], k_max)` (the tensor-core path for n > 4) and hands every follower its rows; the
+    first k entries of an exact top-k_max are the exact top-k, so requests with different k share a batch.
+    Leadership passes to a waiting follower after each batch; no dedicated thread."""
+
+    PEER_WINDOW_S = 5e-3        # "recently": another thread submitted within this long
+
+    class _Item:
+        __slots__ = ("vec", "k", "out", "err", "done")
+
+        def __init__(self, vec, k):
+            self.vec, self.k, self.out, self.err, self.done = vec, k, None, None, False
+
+    def __init__(self, run_batch: Callable, max_batch: int = 256, max_wait_s: float = 2e-4):
+        self._run, self.max_batch, self.max_wait_s = run_batch, max_batch, max_wait_s
+        self._cv = threading.Condition()
+        self._queue: List["_MicroBatcher._Item"] = []
+        self._leader = False
+        self._last_batch = 1
+        self._last_tid, self._last_switch = threading.get_ident(), -1e9
+        self.batches = 0            # statistics: index calls / requests served
+        self.requests = 0
+
+    def submit(self, vec: np.ndarray, k: int):
+        """-> (labels[<=k], distances[<=k], count) of this query; raises what `run_batch` raised."""
+        item = self._Item(vec, k)
+        tid = threading.get_ident()
+        with self._cv:
+            self._queue.append(item)
+            if tid != self._last_tid:                 # requests are coming from more than one thread
+                self._last_tid, self._last_switch = tid, time.perf_counter()
+        while True:
+            with self._cv:
+                while self._leader and not item.done:
+                    self._cv.wait()
+                if item.done:
+                    return self._result(item)
+                self._leader = True                   # nobody is serving: this thread does, for one batch
+            self._lead_one_batch()                    # FIFO: its own item is in it unless max_batch were ahead
+
+    def _lead_one_batch(self) -> None:
+        batch: list = []
+        try:
+            # let the other worker threads enqueue -- only when there are any: requests arriving from ONE thread
+            # (a lone client) never wait, and a queue as long as the last batch needs no waiting either
+            if (self.max_wait_s > 0 and time.perf_counter() - self._last_switch < self.PEER_WINDOW_S
+                    and len(self._queue) < max(self._last_batch, 2)):
+                time.sleep(self.max_wait_s)
+            with self._cv:
+                batch = self._queue[:self.max_batch]
+                del self._queue[:len(batch)]
+            try:
+                k_max = max(it.k for it in batch)
+                labels, dist, counts = self._run(np.stack([it.vec for it in batch]), k_max)
+                for r, it in enumerate(batch):
+                    it.out = (labels[r, :it.k], dist[r, :it.k], min(int(counts[r]), it.k))
+            except BaseException as e:                # every request of the batch sees the failure
+                for it in batch:
+                    it.err = e
+        finally:
+            with self._cv:
+                for it in batch:
+                    it.done = True
+                self.batches += 1
+                self.requests += len(batch)
+                self._last_batch = len(batch)
+                self._leader = False
+                self._cv.notify_all()
+
+    @staticmethod
+    def _result(item):
+        if item.err is not None:
+            raise item.err
+        return item.out
+
+
 class GpuVectorNodeHandler:
     def __init__(self, node_id: str, storage_root: str = "./Static/local_storage", *, space: str = "l2",
                  dim: int = VECTOR_DIM, max_elements: int = 1_000_000, store_dtype: str = "f32", device: int = 0,
                  checkpoint_every: int = 2000, reference_quirks: bool = False, fsync: bool = True,
-                 index_factory: Optional[Callable] = None):
+                 index_factory: Optional[Callable] = None, micro_batch_wait_s: Optional[float] = None,
+                 micro_batch_max: int = 256):
         self.node_id = node_id
         self.index_lock = threading.RLock()                      # handler.py:23
         self.space, self.vector_dim, self.store_dtype, self.device = space, dim, store_dtype, device
@@ -66,6 +148,10 @@ class GpuVectorNodeHandler:
         self._by_key: Dict[str, dict] = {}
         self._key_of_id: Dict[int, str] = {}
         self.hnsw_index = self._factory(space, dim, max_elements, store_dtype, device)
+        # micro_batch_wait_s = None: every search is its own index query under the handler lock, as in the
+        # reference; a number (0 allowed): concurrent searches are coalesced (see _MicroBatcher)
+        self._batcher = (None if micro_batch_wait_s is None else
+                         _MicroBatcher(self._locked_query, micro_batch_max, micro_batch_wait_s))
         self.load_from_checkpoint()
 
     # ---- key table ---------------------------------------------------------------------------
@@ -214,9 +300,15 @@ class GpuVectorNodeHandler:
         return Response(success=True, message=f"key={key}删除成功")
 
     # ---- search / get (handler.py:344-428) -------------------------------------------------------
+    def _locked_query(self, queries: np.ndarray, k: int):
+        with self.index_lock:                                                        # writers stay out, as in :348
+            return self.hnsw_index.knn_query_padded(queries, min(k, max(self.hnsw_index.get_current_count(), 1)))
+
     def search(self, req: SearchRequest) -> Response:
         query_vec = np.array(req.query_vector, dtype=np.float32).reshape(1, -1)     # :345
         top_k = req.top_k if req.top_k and req.top_k > 0 else 5                     # :346
+        if self._batcher is not None:
+            return self._search_coalesced(query_vec, top_k)
         with self.index_lock:
             current_count = self.hnsw_index.get_current_count()
             if current_count == 0:                                                   # :353-354
@@ -229,23 +321,45 @@ class GpuVectorNodeHandler:
                 labels, distances, counts = self.hnsw_index.knn_query_padded(query_vec, k)
             except RuntimeError:                                                     # :366
                 return Response(success=False, message="HNSW index corrupted, search aborted")
-            keys, vectors, scores = [], [], []
-            for i in range(int(counts[0])):                                          # :375
-                hnsw_id = int(labels[0][i])
-                if hnsw_id in self.deleted_ids:                                      # :378 (already masked on the GPU)
-                    continue
-                key = self._get_key_by_hnsw_id(hnsw_id)                              # :382
-                if not key:
-                    continue
-                rec = self._by_key.get(key)                                          # :387
-                if rec is None:
-                    continue
-                keys.append(key)
-                vectors.append(VectorData(key=key, vector=rec["vector"], metadata=rec["metadata"]))   # :398
-                scores.append(float(distances[0][i]))                                # :393
-                if len(keys) >= top_k:                                               # :402
-                    break
-            return Response(success=True, search_result=SearchResult(keys=keys, scores=scores, vectors=vectors))
+            return self._search_response(labels[0], distances[0], int(counts[0]), top_k)
+
+    def _search_response(self, labels, distances, count: int, top_k: int) -> Response:
+        """labels -> keys, vectors, metadata (handler.py:375-408); caller holds index_lock"""
+        keys, vectors, scores = [], [], []
+        for i in range(count):                                                       # :375
+            hnsw_id = int(labels[i])
+            if hnsw_id < 0 or hnsw_id in self.deleted_ids:                           # :378 (already masked on the GPU)
+                continue
+            key = self._get_key_by_hnsw_id(hnsw_id)                                  # :382
+            if not key:
+                continue
+            rec = self._by_key.get(key)                                              # :387
+            if rec is None:
+                continue
+            keys.append(key)
+            vectors.append(VectorData(key=key, vector=rec["vector"], metadata=rec["metadata"]))   # :398
+            scores.append(float(distances[i]))                                       # :393
+            if len(keys) >= top_k:                                                   # :402
+                break
+        return Response(success=True, search_result=SearchResult(keys=keys, scores=scores, vectors=vectors))
+
+    def _search_coalesced(self, query_vec: np.ndarray, top_k: int) -> Response:
+        """`search` with concurrent requests sharing one index query.  The handler lock is held by the batch
+        leader during the query and again for the key lookups of each request; a put/delete that lands between
+        the two can only remove a label from this request's answer (the lookups skip it)."""
+        with self.index_lock:
+            current_count = self.hnsw_index.get_current_count()
+        if current_count == 0:
+            return Response(success=True, search_result=SearchResult(keys=[], scores=[], vectors=[]))
+        k = min(top_k, current_count)
+        if self.reference_quirks and 2 * k > current_count:
+            return Response(success=False, message="HNSW index corrupted, search aborted")
+        try:
+            labels, distances, count = self._batcher.submit(query_vec[0], k)
+        except RuntimeError:
+            return Response(success=False, message="HNSW index corrupted, search aborted")
+        with self.index_lock:
+            return self._search_response(labels, distances, count, top_k)
 
     def search_batch(self, queries, top_k: int):
         """Additive (the IDL has one query per SearchRequest, vector_db.thrift:23-28): many queries in one

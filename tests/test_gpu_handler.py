@@ -102,3 +102,46 @@ def test_concurrent_searches_and_writer(vdb):
     l, d, c = ix.knn_query_padded(q, 10)
     for i in range(4):
         assert R.check_topk(l[i], d[i], q[i], rows, np.arange(13000), 10, "ip", rtol=1e-5) is None
+
+
+def test_micro_batched_handler_on_the_gpu(vdb, tmp_path):
+    """8 worker threads of single-query searches coalesced into tensor-path batches: same keys and scores (bit for
+    bit: the re-rank uses the scan kernel's summation order) as one query at a time, with a writer running."""
+    import threading
+    n = 3000
+    rows = vecs(n)
+    hs = [vdb.GpuVectorNodeHandler(f"node_{i}", storage_root=str(tmp_path), space="cosine", dim=DIM, max_elements=8192,
+                                   checkpoint_every=0, fsync=False, micro_batch_wait_s=w) for i, w in enumerate((None, 1e-3))]
+    items = [vdb.VectorData(key=f"k{i}", vector=rows[i].tolist(), metadata={"i": str(i)}) for i in range(n)]
+    for h in hs:
+        assert h.put_batch(items).success
+    plain, fast = hs
+    qs = R.synth_rows(R.SEED_QUERY, 0, 24, DIM)
+    reqs = [vdb.SearchRequest(query_vector=q.tolist(), top_k=10) for q in qs]
+    want = [plain.search(r).search_result for r in reqs]
+    got, errs = {}, []
+
+    def worker(t):
+        try:
+            for j, r in enumerate(reqs):
+                got[(t, j)] = fast.search(r)
+        except Exception as e:          # noqa
+            errs.append(e)
+
+    def writer():                       # appended rows are far from every query: answers must not change
+        try:
+            far = -qs.sum(axis=0)
+            for j in range(20):
+                assert fast.put(vdb.VectorData(key=f"far{j}", vector=far.tolist(), metadata={})).success
+        except Exception as e:          # noqa
+            errs.append(e)
+
+    ts = [threading.Thread(target=worker, args=(t,)) for t in range(8)] + [threading.Thread(target=writer)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    for (t, j), resp in got.items():
+        assert resp.success and resp.search_result.keys == want[j].keys
+        assert resp.search_result.scores == want[j].scores
+    assert fast._batcher.requests == 8 * 24 and fast._batcher.batches < 8 * 24
+    assert fast.hnsw_index.get_stat("tensor_batches") >= 1

@@ -191,3 +191,64 @@ def test_coordinator_merge_and_routing(vdb, tmp_path):
     assert r.keys == R.datanode_search_exact_live(model, vec(1.4), 5)[1]        # sharded == single node
     assert coord.get("key_3").success is False
     assert vdb.LocalCoordinator({}).search(vdb.SearchRequest(query_vector=vec(1), top_k=1)).success is False
+
+
+# ---------------------------------------------------------------------------------------------
+# micro-batching of concurrent single-query searches
+# ---------------------------------------------------------------------------------------------
+def test_micro_batcher_coalesces_concurrent_searches(vdb, tmp_path):
+    """8 worker threads x 25 requests with different k: every answer equals the one-at-a-time handler's, and
+    the index saw far fewer queries than requests."""
+    import threading
+    plain = make_handler(vdb, tmp_path / "a")
+    fast = make_handler(vdb, tmp_path / "b", micro_batch_wait_s=2e-3)
+    for h in (plain, fast):
+        for i in range(40):
+            assert h.put(vdb.VectorData(key=f"k{i}", vector=vec(i), metadata={"i": str(i)})).success
+        h.delete("k7")
+    reqs = [vdb.SearchRequest(query_vector=vec(3 * j % 41), top_k=(j % 6)) for j in range(25)]
+    want = [plain.search(r).search_result for r in reqs]
+    got, errs = {}, []
+
+    def worker(t):
+        try:
+            for j, r in enumerate(reqs):
+                got[(t, j)] = fast.search(r)
+        except Exception as e:          # noqa
+            errs.append(e)
+
+    ts = [threading.Thread(target=worker, args=(t,)) for t in range(8)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    for (t, j), resp in got.items():
+        assert resp.success
+        assert resp.search_result.keys == want[j].keys and resp.search_result.scores == want[j].scores
+        assert [v.metadata for v in resp.search_result.vectors] == [v.metadata for v in want[j].vectors]
+    b = fast._batcher
+    assert b.requests == 200 and b.batches < 120          # coalesced: 8 threads -> batches of several requests
+
+
+def test_micro_batcher_edge_cases(vdb, tmp_path):
+    """empty index, reference-quirk failure, an index error reaching every request of the batch, and batches
+    larger than max_batch (leadership passes on)."""
+    import threading
+    h = make_handler(vdb, tmp_path, micro_batch_wait_s=0.0, micro_batch_max=2, reference_quirks=True)
+    r = h.search(vdb.SearchRequest(query_vector=vec(1), top_k=3))
+    assert r.success and r.search_result.keys == []
+    for i in range(5):
+        h.put(vdb.VectorData(key=f"k{i}", vector=vec(i)))
+    assert not h.search(vdb.SearchRequest(query_vector=vec(1), top_k=3)).success          # 2k > count
+    assert h.search(vdb.SearchRequest(query_vector=vec(1), top_k=2)).search_result.keys == ["k1", "k0"]
+    out = []
+    ts = [threading.Thread(target=lambda: out.append(h.search(vdb.SearchRequest(query_vector=vec(4), top_k=1))))
+          for _ in range(7)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert len(out) == 7 and all(o.success and o.search_result.keys == ["k4"] for o in out)
+
+    def boom(q, k):
+        raise RuntimeError("index gone")
+    h.hnsw_index.knn_query_padded = boom
+    bad = h.search(vdb.SearchRequest(query_vector=vec(1), top_k=2))
+    assert not bad.success and "HNSW index corrupted" in bad.message
