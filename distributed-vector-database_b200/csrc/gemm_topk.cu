@@ -606,6 +606,8 @@ struct SelectParams {
                               // yield the first threshold (the levels that follow visit the probed tiles again)
     int thr_rank;             // the next level's threshold = the thr_rank-th best kept value (<= kp)
     int np2;                  // keys the shared array sk[] holds (>= cap); kept[kp] lies behind it
+    int min_rank;             // probe: with fewer live chunk minima than thr_rank, the largest of them serves if
+                              // there are at least this many
 };
 
 // Radix select on the 32 distance bits (4 passes of 8 bits): O(n) instead of a full sort.  Keys whose
@@ -648,8 +650,9 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectParams p) {
     const int n_valid = s_valid;
     __syncthreads();
     const bool probe = p.probe_cnt > 0;
-    const int want = probe ? p.thr_rank : p.kp;   // 1-based rank of the key we are looking for
-    if (probe && n_valid < want) {
+    // 1-based rank of the key we are looking for
+    const int want = !probe ? p.kp : (n_valid >= p.thr_rank ? p.thr_rank : n_valid);
+    if (probe && n_valid < p.min_rank) {
         if (threadIdx.x == 0) { p.cnt[q] = 0; p.thr[q] = __int_as_float(0x7f800000); }   // too few live rows probed
         return;
     }
@@ -1148,7 +1151,15 @@ static int probe_tiles(int rank) {
     return std::max(v > 0 ? v : GT_PROBE_TILES, (rank + 1) / 2);
 }
 static int level_growth() { static const int v = std::max(2, env_int("VDB_GROWTH", GT_LEVEL_GROWTH)); return v; }
-static int cap_for_kp(int kp) { return 16 * kp; }
+// keys a query's level buffer holds: 16 k' (the levels are planned for <= 55 % of that); a shard of at most 32 k'
+// rows gets a buffer that holds every row, because its probe may see fewer live chunks than the threshold rank
+// and then publishes no threshold (the single level that follows keeps everything)
+static int cap_for(int kp, size_t n_rows) {
+    int cap = 16 * kp;
+    if (n_rows <= (size_t)32 * kp)
+        while ((size_t)cap < n_rows) cap <<= 1;
+    return cap;
+}
 
 bool gemm_topk_supported(int dim, int ld, bool f16, int k, size_t n_rows) {
     (void)dim;
@@ -1241,7 +1252,7 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
     if (e0 != cudaSuccess) return e0;
     auto* w = static_cast<GemmWsImpl*>(ws.impl);
     const int kp = kp_for_k(a.k);
-    const int cap = cap_for_kp(kp);
+    const int cap = cap_for(kp, a.n_rows);
     const int MB = (int)((a.nq + 2 * GT_BM - 1) / (2 * GT_BM));   // 256-query blocks, one per CTA pair
     const int n_tiles = (int)((a.n_rows + GT_BN - 1) / GT_BN);
     const int num_pairs_max = a.num_sms / 2;
@@ -1291,8 +1302,8 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
     sp.tomb = a.tomb; sp.n_rows = a.n_rows;
     static bool sel_configured = false;
     if (!sel_configured) {
-        if ((e = cudaFuncSetAttribute(select_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(select_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(select_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(select_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)) != cudaSuccess) return e;
         sel_configured = true;
     }
     int sel_np = 2;
@@ -1322,7 +1333,7 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
         return le;
     };
     auto run_select = [&](int probe_cnt, int thr_rank) -> cudaError_t {
-        sp.probe_cnt = probe_cnt; sp.thr_rank = thr_rank;
+        sp.probe_cnt = probe_cnt; sp.thr_rank = thr_rank; sp.min_rank = std::min(kq, thr_rank);
         // one block per query; thousands of queries with a few hundred keys each: small blocks, so that more
         // of them are resident and the barrier chain of a block is short
         cudaError_t le;

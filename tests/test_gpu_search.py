@@ -240,6 +240,17 @@ def test_tensor_path_small_and_ragged(vdb, n):
     assert_parity(ix, raw, "ip", "f32", q, 10)
 
 
+@pytest.mark.parametrize("n,k", [(600, 10), (1000, 10), (1500, 10), (3000, 10), (2500, 64), (4500, 100), (6000, 100)])
+def test_tensor_path_small_shards_stay_on_the_tensor_path(vdb, n, k):
+    """shards between one buffer and a few probes' worth of rows: the probe sees fewer chunks than the threshold
+    rank (no threshold, or the largest chunk minimum) -- the buffers must still hold what the level keeps."""
+    ix, raw = build(vdb, "l2", n, dim=128)
+    ix.set_option("path", 2)
+    q = R.synth_rows(R.SEED_QUERY, 0, 40, 128)
+    assert_parity(ix, raw, "l2", "f32", q, k)
+    assert ix.get_stat("tensor_batches") >= 1 and ix.get_stat("fallback_queries") == 0
+
+
 def test_tensor_path_tombstones(vdb):
     ix, raw = build(vdb, "cosine", 5000)
     ix.set_option("path", 2)
