@@ -38,8 +38,12 @@ class LocalCoordinator:
     """`CoordinatorHandler` over handlers in this process (one per GPU): md5 routing of put/delete/get
     to the shard master (coordinator/handler.py:117-170), broadcast search + merge (:173-228)."""
 
-    def __init__(self, nodes: Dict[str, object], shard_count: Optional[int] = None):
+    def __init__(self, nodes: Dict[str, object], shard_count: Optional[int] = None, parallel: bool = True):
         self.nodes = dict(nodes)
+        self._pool = None
+        if parallel and len(nodes) > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            self._pool = ThreadPoolExecutor(max_workers=len(nodes), thread_name_prefix="coord-fanout")
         self.node_ids = list(self.nodes)
         # with SHARD_COUNT=4 and 8 nodes only 4 nodes would receive data (SURVEY 8a): default to one shard per node
         self.shard_count = shard_count or len(self.node_ids)
@@ -61,12 +65,50 @@ class LocalCoordinator:
         if not self.nodes:
             return Response(success=False, message="无在线数据节点")               # :177-178
         sub = SearchRequest(query_vector=req.query_vector, top_k=req.top_k)       # :186-189 (filter/threshold dropped)
-        results = []
-        for node_id in self.node_ids:                                              # :191
-            resp = self.nodes[node_id].search(sub)
-            results.append(resp.search_result if resp.success and resp.search_result else None)   # :198-199
+
+        def one(node_id):
+            try:
+                resp = self.nodes[node_id].search(sub)
+            except Exception:                                                      # :198-199 a failed node is skipped
+                return None
+            return resp.search_result if resp.success and resp.search_result else None
+
+        if self._pool is not None:
+            # the reference asks the nodes one after the other (:191-197); here all at once -- the GPU calls drop the
+            # GIL -- and the answers are merged in NODE order, so ties resolve exactly as in the serial loop
+            results = list(self._pool.map(one, self.node_ids))
+        else:
+            results = [one(node_id) for node_id in self.node_ids]                  # :191
         merged = merge_search_results(results, req.top_k)
         return Response(success=True, search_result=merged)
+
+    def search_batch(self, queries, top_k: int) -> Tuple[List[List[str]], List[List[float]]]:
+        """Additive: many queries per call (every node's `search_batch`, i.e. the tensor-core path), merged per
+        query with the coordinator's rule.  Returns (keys[nq][<=k], scores[nq][<=k])."""
+        nq = len(queries)
+        if not self.nodes:
+            return [[] for _ in range(nq)], [[] for _ in range(nq)]
+        k = top_k if top_k and top_k > 0 else 5
+
+        def one(node_id):
+            try:
+                return self.nodes[node_id].search_batch(queries, k)
+            except Exception:
+                return None
+
+        per_node = list(self._pool.map(one, self.node_ids)) if self._pool is not None else [one(n) for n in self.node_ids]
+        out_k, out_s = [], []
+        for r in range(nq):
+            lists = [SearchResult(keys=pn[0][r], scores=pn[1][r], vectors=None) for pn in per_node if pn is not None]
+            m = merge_search_results(lists, k)
+            out_k.append(m.keys)
+            out_s.append(m.scores)
+        return out_k, out_s
+
+    def close(self) -> None:
+        if self._pool is not None:
+            self._pool.shutdown(wait=False)
+            self._pool = None
 
 
 class ShardedSearcher:

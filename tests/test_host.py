@@ -190,6 +190,21 @@ def test_coordinator_merge_and_routing(vdb, tmp_path):
     r = coord.search(vdb.SearchRequest(query_vector=vec(1.4), top_k=5)).search_result
     assert r.keys == R.datanode_search_exact_live(model, vec(1.4), 5)[1]        # sharded == single node
     assert coord.get("key_3").success is False
+    serial = vdb.LocalCoordinator(nodes, parallel=False)                       # the reference's serial loop
+    for x in (0.0, 1.4, 7.3, 19.0):
+        for k in (1, 5, 50):
+            a = coord.search(vdb.SearchRequest(query_vector=vec(x), top_k=k)).search_result
+            b = serial.search(vdb.SearchRequest(query_vector=vec(x), top_k=k)).search_result
+            assert a.keys == b.keys == R.datanode_search_exact_live(model, vec(x), k)[1] and a.scores == b.scores
+    ks, ss = coord.search_batch([vec(1.4), vec(7.3)], 5)
+    assert ks == [R.datanode_search_exact_live(model, vec(x), 5)[1] for x in (1.4, 7.3)]
+    assert ss[0] == coord.search(vdb.SearchRequest(query_vector=vec(1.4), top_k=5)).search_result.scores
+
+    class Down:                                                                # a node that fails is skipped (:198-199)
+        def search(self, req):
+            raise ConnectionError("node down")
+    flaky = vdb.LocalCoordinator({**nodes, "zz": Down()}, shard_count=4)
+    assert flaky.search(vdb.SearchRequest(query_vector=vec(1.4), top_k=5)).search_result.keys == r.keys
     assert vdb.LocalCoordinator({}).search(vdb.SearchRequest(query_vector=vec(1), top_k=1)).success is False
 
 
