@@ -967,7 +967,7 @@ __global__ void __launch_bounds__(RW_MAX_THREADS) rerank_window_kernel(const Rer
     __shared__ uint32_t sh[8];
     __shared__ uint32_t s_a1;
     __shared__ int s_m1, s_m;
-    __shared__ float s_kth;
+    __shared__ float s_kth, s_eps0;
     __shared__ int s_have_kth;
     const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, RW_THREADS = blockDim.x;
     const int k = p.k;
@@ -979,13 +979,17 @@ __global__ void __launch_bounds__(RW_MAX_THREADS) rerank_window_kernel(const Rer
     const float dmax2 = __uint_as_float(*p.max_sqnorm_bits);
     const float off = p.metric == 0 ? qn2 : 1.0f;
     const float INF = __int_as_float(0x7f800000);
-    // value bits of a_x + 2 eps (with a margin for the rounding of the sum); non-finite: keep everything
+    // value bits of a_x + 2 eps (with a margin for the rounding of the sum); non-finite: keep everything.
+    // eps(at) = s_eps0 + 4e-7 |at|: the part with the square roots is computed once per query, not per thread
     auto window_bits = [&](uint32_t a_bits) -> uint32_t {
         const float a = ordered_to_float(a_bits);
-        const float wv = a + 2.25f * approx_eps(p, qn2, dmax2, a + off);
+        const float wv = a + 2.25f * (s_eps0 + 4e-7f * fabsf(a + off));
         return (wv == wv && fabsf(wv) < INF) ? float_to_ordered(wv) : 0xFFFFFFFFu;
     };
-    if (tid == 0) { s_a1 = 0xFFFFFFFFu; s_m1 = 0; s_m = 0; s_kth = INF; s_have_kth = 0; }
+    if (tid == 0) {
+        s_a1 = 0xFFFFFFFFu; s_m1 = 0; s_m = 0; s_kth = INF; s_have_kth = 0;
+        s_eps0 = approx_eps(p, qn2, dmax2, 0.0f);
+    }
     // ---- 0. the buffer; padding rows of the last tile and tombstoned rows drop out
     for (int i = tid; i < n; i += RW_THREADS) {
         uint64_t key = b[i];
