@@ -1256,8 +1256,17 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
     if (e0 != cudaSuccess) return e0;
     auto* w = static_cast<GemmWsImpl*>(ws.impl);
     const int kp = kp_for_k(a.k);
-    const int cap = cap_for(kp, a.n_rows);
+    const int kq = std::max(kp / 2, std::min(kp, (16 * a.k + 9) / 10));     // tight threshold rank (see the level plan)
     const int MB = (int)((a.nq + 2 * GT_BM - 1) / (2 * GT_BM));   // 256-query blocks, one per CTA pair
+    // Small batches (one or two query blocks): the survivors of a level are few whatever the threshold, what
+    // costs is every launch's ramp and every select between launches -- a larger probe, then levels that grow
+    // 64x (as far as an 8192-key buffer allows), i.e. probe + ONE level for a million rows.  Measured on
+    // 1M x 512, batch 5..256 (tools/small_batch.py): ~290 -> ~250 us.
+    const bool small_batch = MB <= 2 && env_int("VDB_SMALL_PLAN", 1) != 0;
+    const int growth = small_batch ? std::max(level_growth(), std::min(64, 8192 / (3 * kq))) : level_growth();
+    int cap = cap_for(kp, a.n_rows);
+    if (small_batch)
+        while (cap < 3 * kq * growth && cap < 8192) cap <<= 1;
     const int n_tiles = (int)((a.n_rows + GT_BN - 1) / GT_BN);
     const int num_pairs_max = a.num_sms / 2;
     const size_t esz = a.f16 ? 2 : 4;
@@ -1322,7 +1331,6 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
     // Threshold rank: while at most a quarter of the shard has been seen, max(k'/2, 1.6 k) instead of k' -- the
     // sample's k'-th best is then far looser than the certificate needs, and every row that passes costs a trip
     // through the key rings.  The k' best stay candidates either way.
-    const int kq = std::max(kp / 2, std::min(kp, (16 * a.k + 9) / 10));
     auto rank_after = [&](int seen) { return 4L * seen <= n_pos ? kq : kp; };
     auto run_level = [&](int p0, int p1, bool probe) -> cudaError_t {
         gp.pos_begin = p0; gp.pos_end = p1; gp.probe = probe ? 1 : 0;
@@ -1347,7 +1355,7 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
         return le != cudaSuccess ? le : cudaGetLastError();
     };
     {
-        const int P = std::min(n_pos, probe_tiles(kq));
+        const int P = std::min(n_pos, std::max(probe_tiles(kq), small_batch ? 64 : 0));
         // the probe writes fixed positions; positions whose tile is past the end must read as sentinel: fill the
         // buffer only when there is such a position (never for shards of a few thousand rows or more)
         bool all_valid = true;
@@ -1359,7 +1367,7 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
         int seen = P, pos = 0;
         while (pos < n_pos) {
             // positions scale with tiles by n_pos / n_tiles (< 2): use positions directly
-            const long want = (long)seen * level_growth();
+            const long want = (long)seen * growth;
             int next = (int)std::min<long>(n_pos, pos + want);
             // stretch the last level over what is left (up to 1.5 x the growth) unless the expected number of
             // survivors (rank x rows of the level / rows behind the threshold, + the k' carried) comes near the

@@ -360,15 +360,17 @@ def test_tensor_path_batch_4096_small_blocks_select(vdb):
     assert ix.get_stat("fallback_queries") == 0
 
 
+@pytest.mark.parametrize("nq", [300, 700])
 @pytest.mark.parametrize("metric,k", [("cosine", 10), ("l2", 16), ("ip", 32), ("l2", 100)])
-def test_tensor_path_levels_no_fallback(vdb, metric, k):
-    """150k rows = 586 tiles: probe + two threshold levels (tight rank, then k') + window re-rank.  Random data must
-    neither overflow a level buffer nor fail the certificate for any k class (k' = 32 / 64 / 256)."""
+def test_tensor_path_levels_no_fallback(vdb, metric, k, nq):
+    """150k rows = 586 tiles.  700 queries (3 query blocks): probe + two threshold levels (tight rank, then k') +
+    window re-rank; 300 queries: the small-batch plan (larger probe, levels growing 64x).  Random data must neither
+    overflow a level buffer nor fail the certificate for any k class (k' = 32 / 64 / 256)."""
     n, dim = 150_000, 64
     ix = vdb.Index(metric, dim)
     ix.init_index(n)
     ix.add_synthetic(R.SEED_DB, 0, n)
-    q = R.synth_rows(R.SEED_QUERY, 0, 300, dim)
+    q = R.synth_rows(R.SEED_QUERY, 0, nq, dim)
     ix.set_option("path", 2)
     lt, dt, ct = ix.knn_query_padded(q, k)
     assert ix.get_stat("tensor_batches") >= 1 and ix.get_stat("fallback_queries") == 0
