@@ -85,7 +85,7 @@ struct GemmParams {
     int n_tiles;             // 256-row tiles of the shard
     int bits;                // tile order = bit reversal over `bits` bits
     int pos_begin, pos_end;  // this level's positions in that order
-    int probe;               // level 0: one key per 32-score chunk (its best live row), at fixed positions
+    int probe;               // probe level: one key per 32-score chunk (its best live row), at fixed positions
     int dbg;                 // experiments only: 2 = epilogue releases TMEM at once, 8 = TMEM reads but no filtering
     const float* sqnorm;     // [n_rows] (L2 only)
     const float* thr;        // [nq] threshold of this level (approximate distance); unused by the probe
@@ -426,7 +426,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 if (q_ok) thr = p.thr[q];
             }
             const float nthr = -thr;
-            uint64_t* dense_dst = p.buf + (size_t)(q_ok ? q : 0) * p.cap;
+            uint64_t* probe_dst = p.buf + (size_t)(q_ok ? q : 0) * p.cap;
             float n_next = 0.0f;
             bool first_tile = true;
 
@@ -464,7 +464,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     // per tile and query).  The r-th smallest of those chunk minima is the value of a real row with
                     // at least r rows at or below it: a valid threshold for the levels that follow, which visit
                     // these tiles again.
-                    uint64_t* dd = dense_dst + (size_t)(pos - p.pos_begin) * 8 + half * NCH;
+                    uint64_t* dd = probe_dst + (size_t)(pos - p.pos_begin) * 8 + half * NCH;
 #pragma unroll 1
                     for (int c = 0; c < NCH; ++c) {
                         uint32_t v[32];
@@ -761,13 +761,13 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// K4: exact re-rank of the k' approximate candidates + coverage certificate
+// K4w: exact re-rank of the candidates that can still matter + coverage certificate
 // ------------------------------------------------------------------------------------------
 struct RerankParams {
-    const uint64_t* approx;   // [nq][stride] ascending approximate keys (distance-like value, row); first KP used
+    const uint64_t* approx;   // [nq][stride] level buffers: approximate keys (distance-like value, row), unordered
     size_t stride;
     const int* overflow;      // [nq] 1 = the candidate buffer overflowed: certificate void
-    const float* tau;         // [nq] KP-th best approximate value (+inf: fewer than KP live rows, all are candidates)
+    const float* tau;         // [nq] last level's threshold: every row outside the buffer is >= it (+inf: there is none)
     const void* rows; uint32_t row_bytes; uint32_t ld;
     const uint32_t* labels;
     const float* q;           // prepared queries [nq][ld] fp32
@@ -780,7 +780,6 @@ struct RerankParams {
     int64_t* out_ids; float* out_dist; int* out_counts;
     int* flags;               // [nq] 1 = certificate failed
     int* n_flagged;
-    // window kernel only: the level buffers as the last level left them (no final select)
     const int* cnt;           // [nq] keys in the buffer (may exceed cap: overflow)
     int cap;
     const uint32_t* tomb; uint32_t n_rows;
@@ -866,7 +865,7 @@ __device__ __forceinline__ float approx_eps(const RerankParams& p, float qn2, fl
 }
 
 // ------------------------------------------------------------------------------------------
-// K4w: K4 straight from the level buffers -- no select after the last level, and only the candidates that can
+// K4w: the re-rank straight from the level buffers -- no select after the last level, and only the candidates that can
 // still reach the exact top-k are re-ranked.
 //   Buffer of query q after the last level: the k' keys the previous select carried over + every row of the last
 //   level whose approximate value beat that level's threshold thr.  Every row that is NOT in the buffer failed a

@@ -17,7 +17,7 @@ struct GemmWorkspace {     // per in-flight call: candidate lists, thresholds, f
 struct GemmSearchArgs {
     const void* rows; int ld; int dim; bool f16; uint32_t n_rows;
     // optional fp16 shadow plane of fp32 rows [n_rows][ld16]: when set, K2 contracts it (kind::f16) against
-    // fp16-rounded queries instead of the fp32 rows (kind::tf32); K4 always re-ranks from `rows`
+    // fp16-rounded queries instead of the fp32 rows (kind::tf32); K4w always re-ranks from `rows`
     const void* shadow = nullptr; int ld16 = 0;
     const float* sqnorm; const uint32_t* labels; const uint32_t* tomb;
     bool prepped = false;  // the caller filled gemm_topk_prep_targets() while preparing the queries

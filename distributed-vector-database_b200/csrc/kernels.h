@@ -83,7 +83,7 @@ cudaError_t launch_gather_rows(const void* rows, int ld, int dim, bool f16, cons
                                cudaStream_t st);
 cudaError_t launch_iota_u32(uint32_t* out, size_t n, uint32_t start, cudaStream_t st);
 
-// ---- K2 / K4 batched tensor-core path (gemm_topk.cu, rerank.cu) ---------------------------
+// ---- K2 / K2s / K4w batched tensor-core path (gemm_topk.cu) ---------------------------
 struct GemmTopkPlan;  // opaque, owns tensor maps
 
 uint64_t launch_count();

@@ -263,7 +263,7 @@ def test_tensor_path_tombstones(vdb):
 
 
 def test_tensor_path_equals_scan_path_bitwise(vdb):
-    """K4 re-ranks with the scan kernel's summation order: all paths return identical bits."""
+    """K4w re-ranks with the scan kernel's summation order: all paths return identical bits."""
     ix, raw = build(vdb, "cosine", 20000)
     q = R.synth_rows(R.SEED_QUERY, 0, 300, 512)
     ix.set_option("path", 1)
