@@ -56,10 +56,16 @@ constexpr int GT_KB_BYTES = 128;                     // one 128B swizzle atom pe
 constexpr int GT_A_BYTES = GT_BM * GT_KB_BYTES;      // 16 KB
 constexpr int GT_B_BYTES = GT_BN_HALF * GT_KB_BYTES; // 16 KB (this CTA's half of the 256-row tile)
 constexpr int GT_STAGE_BYTES = GT_A_BYTES + GT_B_BYTES;
-constexpr int GT_STAGES = 4;
+#ifndef VDB_GT_STAGES
+#define VDB_GT_STAGES 4       // -D overrides: tuning builds only (tools/level_sweep.sh documents the measured choices)
+#endif
+#ifndef VDB_GT_RING
+#define VDB_GT_RING 40
+#endif
+constexpr int GT_STAGES = VDB_GT_STAGES;
 constexpr int GT_THREADS = 384;                      // 12 warps: TMA, MMA, 2 movers, 8 epilogue
-constexpr int GT_RING = 40;                          // keys per ring (one ring per epilogue thread)
-constexpr int GT_RING_STRIDE = 41;                   // padded: same-slot appends of a warp spread over banks
+constexpr int GT_RING = VDB_GT_RING;                  // keys per ring (one ring per epilogue thread)
+constexpr int GT_RING_STRIDE = GT_RING + 1;                   // padded: same-slot appends of a warp spread over banks
 constexpr int GT_EPI_THREADS = 256;                  // 2 threads per query (TMEM lane): columns 0-127 / 128-255
 constexpr int GT_EPI_WARPS = GT_EPI_THREADS / 32;
 constexpr int GT_TMEM_COLS = 512;
