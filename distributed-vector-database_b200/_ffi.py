@@ -53,6 +53,7 @@ SIGNATURES = {
     "vdb_get_stat": (C.c_long, [_vp, C.c_char_p]),
     "vdb_last_error": (C.c_char_p, []),
     "vdb_version": (C.c_char_p, []),
+    "vdb_debug_level_plan": (C.c_int, [C.c_size_t, C.c_size_t, C.c_int, C.POINTER(C.c_int), C.c_int]),
 }
 
 _lib = None

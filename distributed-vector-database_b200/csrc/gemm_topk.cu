@@ -1255,23 +1255,59 @@ cudaError_t gemm_topk_prep_targets(GemmWorkspace& ws, const GemmSearchArgs& a, G
     return cudaSuccess;
 }
 
+// The launch sequence of one search as data (pure host arithmetic: tests/test_abi.py checks its invariants on CPU
+// over a grid of shapes through vdb_debug_level_plan).
+//   Probe: the first P positions of the bit-reversed tile order, chunk minima only -> first threshold.  Then levels
+//   from position 0 on, each covering `growth` x the positions that informed its threshold; the last one takes what
+//   is left if that is at most 1.5 x the growth and the expected survivors stay under 55 % of the buffer.  A select
+//   follows every level but the last (the window re-rank reads the last level's buffer as it is).
+//   Threshold rank: while at most a quarter of the shard has been seen, max(k'/2, 1.6 k) instead of k' -- the
+//   sample's k'-th best is then far looser than the certificate needs, and every row that passes costs a trip
+//   through the key rings.  The k' best stay candidates either way.
+//   Small batches (one or two query blocks): the survivors of a level are few whatever the threshold, what costs
+//   is every launch's ramp and every select between launches -- a larger probe, then levels that grow 64x (as far
+//   as an 8192-key buffer allows), i.e. probe + ONE level for a million rows.  Measured on 1M x 512, batch 5..256
+//   (tools/small_batch.py): ~290 -> ~265 us.
+LevelPlan gemm_topk_level_plan(size_t nq, size_t n_rows, int k) {
+    LevelPlan lp;
+    lp.kp = kp_for_k(k);
+    lp.kq = std::max(lp.kp / 2, std::min(lp.kp, (16 * k + 9) / 10));
+    lp.query_blocks = (int)((nq + 2 * GT_BM - 1) / (2 * GT_BM));       // 256-query blocks, one per CTA pair
+    lp.small_batch = lp.query_blocks <= 2 && env_int("VDB_SMALL_PLAN", 1) != 0;
+    lp.growth = lp.small_batch ? std::max(level_growth(), std::min(64, 8192 / (3 * lp.kq))) : level_growth();
+    lp.cap = cap_for(lp.kp, n_rows);
+    if (lp.small_batch)
+        while (lp.cap < 3 * lp.kq * lp.growth && lp.cap < 8192) lp.cap <<= 1;
+    lp.n_tiles = (int)((n_rows + GT_BN - 1) / GT_BN);
+    lp.bits = 0;
+    while ((1 << lp.bits) < lp.n_tiles) ++lp.bits;
+    lp.n_pos = 1 << lp.bits;                 // positions in bit-reversed order; those mapping past n_tiles are skipped
+    const int n_pos = lp.n_pos;
+    auto rank_after = [&](int seen) { return 4L * seen <= n_pos ? lp.kq : lp.kp; };
+    lp.probe_tiles = std::min(n_pos, std::max(probe_tiles(lp.kq), lp.small_batch ? 64 : 0));
+    lp.probe_rank = rank_after(lp.probe_tiles);
+    int rank = lp.probe_rank, seen = lp.probe_tiles, pos = 0;
+    while (pos < n_pos) {
+        // positions scale with tiles by n_pos / n_tiles (< 2): use positions directly
+        const long want = (long)seen * lp.growth;
+        int next = (int)std::min<long>(n_pos, pos + want);
+        const long left = n_pos - pos;
+        if (left <= want + want / 2 && (long)rank * left / seen + lp.kp <= (long)lp.cap * 11 / 20) next = n_pos;
+        LevelPlan::Level lv{pos, next, 0};
+        if (next < n_pos) lv.rank_after = rank = rank_after(next);
+        lp.levels.push_back(lv);
+        seen = pos = next;
+    }
+    return lp;
+}
+
 cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearchArgs& a, cudaStream_t st, std::string& err) {
     if (!plan.impl) plan.impl = new GemmPlanImpl();
     cudaError_t e0 = ensure_ws(ws);
     if (e0 != cudaSuccess) return e0;
     auto* w = static_cast<GemmWsImpl*>(ws.impl);
-    const int kp = kp_for_k(a.k);
-    const int kq = std::max(kp / 2, std::min(kp, (16 * a.k + 9) / 10));     // tight threshold rank (see the level plan)
-    const int MB = (int)((a.nq + 2 * GT_BM - 1) / (2 * GT_BM));   // 256-query blocks, one per CTA pair
-    // Small batches (one or two query blocks): the survivors of a level are few whatever the threshold, what
-    // costs is every launch's ramp and every select between launches -- a larger probe, then levels that grow
-    // 64x (as far as an 8192-key buffer allows), i.e. probe + ONE level for a million rows.  Measured on
-    // 1M x 512, batch 5..256 (tools/small_batch.py): ~290 -> ~250 us.
-    const bool small_batch = MB <= 2 && env_int("VDB_SMALL_PLAN", 1) != 0;
-    const int growth = small_batch ? std::max(level_growth(), std::min(64, 8192 / (3 * kq))) : level_growth();
-    int cap = cap_for(kp, a.n_rows);
-    if (small_batch)
-        while (cap < 3 * kq * growth && cap < 8192) cap <<= 1;
+    const LevelPlan lp = gemm_topk_level_plan(a.nq, a.n_rows, a.k);
+    const int kp = lp.kp, kq = lp.kq, MB = lp.query_blocks, cap = lp.cap;
     const int n_tiles = (int)((a.n_rows + GT_BN - 1) / GT_BN);
     const int num_pairs_max = a.num_sms / 2;
     const size_t esz = a.f16 ? 2 : 4;
@@ -1309,9 +1345,7 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
     gp.kb_elems = (int)(GT_KB_BYTES / gesz);
     { const char* d = getenv("VDB_GEMM_DBG"); gp.dbg = d ? atoi(d) : 0; }
     gp.MB = MB; gp.n_tiles = n_tiles;
-    gp.bits = 0;
-    while ((1 << gp.bits) < n_tiles) ++gp.bits;
-    const int n_pos = 1 << gp.bits;          // positions in bit-reversed order; those mapping past n_tiles are skipped
+    gp.bits = lp.bits;
     gp.sqnorm = a.sqnorm; gp.thr = w->thr; gp.buf = w->buf; gp.cnt = w->cnt; gp.cap = cap; gp.tomb = a.tomb;
     const bool l2 = a.metric == 0;
 
@@ -1329,14 +1363,6 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
     sp.np2 = sel_np;
     const size_t sel_smem = ((size_t)sel_np + kp) * 8;
 
-    // Level plan over positions (bit-reversed tile order).  Probe: the first P positions, chunk minima only ->
-    // first threshold.  Then levels from position 0 on, each covering level_growth() x the positions that informed
-    // its threshold; the last one takes what is left if that is at most 1.5 x the growth.  A select follows every
-    // level but the last (the window re-rank reads the last level's buffer as it is).
-    // Threshold rank: while at most a quarter of the shard has been seen, max(k'/2, 1.6 k) instead of k' -- the
-    // sample's k'-th best is then far looser than the certificate needs, and every row that passes costs a trip
-    // through the key rings.  The k' best stay candidates either way.
-    auto rank_after = [&](int seen) { return 4L * seen <= n_pos ? kq : kp; };
     auto run_level = [&](int p0, int p1, bool probe) -> cudaError_t {
         gp.pos_begin = p0; gp.pos_end = p1; gp.probe = probe ? 1 : 0;
         gp.S = choose_slices(MB, p1 - p0, num_pairs_max);
@@ -1360,30 +1386,17 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
         return le != cudaSuccess ? le : cudaGetLastError();
     };
     {
-        const int P = std::min(n_pos, std::max(probe_tiles(kq), small_batch ? 64 : 0));
+        const int P = lp.probe_tiles;
         // the probe writes fixed positions; positions whose tile is past the end must read as sentinel: fill the
         // buffer only when there is such a position (never for shards of a few thousand rows or more)
         bool all_valid = true;
         for (int pp = 0; pp < P; ++pp) all_valid = all_valid && (int)bitrev((uint32_t)pp, gp.bits) < n_tiles;
         if (!all_valid && (e = cudaMemsetAsync(w->buf, 0xFF, a.nq * (size_t)cap * sizeof(uint64_t), st)) != cudaSuccess) return e;
         if ((e = run_level(0, P, true)) != cudaSuccess) return e;
-        int rank = rank_after(P);              // rank behind the current threshold
-        if ((e = run_select(P * 8, rank)) != cudaSuccess) return e;
-        int seen = P, pos = 0;
-        while (pos < n_pos) {
-            // positions scale with tiles by n_pos / n_tiles (< 2): use positions directly
-            const long want = (long)seen * growth;
-            int next = (int)std::min<long>(n_pos, pos + want);
-            // stretch the last level over what is left (up to 1.5 x the growth) unless the expected number of
-            // survivors (rank x rows of the level / rows behind the threshold, + the k' carried) comes near the
-            // buffer capacity
-            const long left = n_pos - pos;
-            if (left <= want + want / 2 && (long)rank * left / seen + kp <= (long)cap * 11 / 20) next = n_pos;
-            if ((e = run_level(pos, next, false)) != cudaSuccess) return e;
-            if (next == n_pos) break;
-            rank = rank_after(next);
-            if ((e = run_select(0, rank)) != cudaSuccess) return e;
-            seen = pos = next;
+        if ((e = run_select(P * 8, lp.probe_rank)) != cudaSuccess) return e;
+        for (const LevelPlan::Level& lv : lp.levels) {
+            if ((e = run_level(lv.p0, lv.p1, false)) != cudaSuccess) return e;
+            if (lv.rank_after && (e = run_select(0, lv.rank_after)) != cudaSuccess) return e;
         }
     }
 

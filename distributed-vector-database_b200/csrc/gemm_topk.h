@@ -39,6 +39,16 @@ struct GemmSearchArgs {
 struct GemmPrepTargets { void* q16 = nullptr; int gld = 0; int* overflow = nullptr; int* n_flagged = nullptr; };
 cudaError_t gemm_topk_prep_targets(GemmWorkspace& ws, const struct GemmSearchArgs& a, GemmPrepTargets* out);
 
+// the launch sequence of one search (see gemm_topk.cu): probe, then levels with the rank of the threshold published
+// after each (0 = last level, no select)
+struct LevelPlan {
+    int kp, kq, cap, growth, query_blocks, n_tiles, bits, n_pos, probe_tiles, probe_rank;
+    bool small_batch;
+    struct Level { int p0, p1, rank_after; };
+    std::vector<Level> levels;
+};
+LevelPlan gemm_topk_level_plan(size_t nq, size_t n_rows, int k);
+
 bool gemm_topk_supported(int dim, int ld, bool f16, int k, size_t n_rows);
 cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearchArgs& a, cudaStream_t st, std::string& err);
 // after gemm_topk_search: synchronises `st` and lists the queries whose certificate failed

@@ -432,6 +432,17 @@ const char* vdb_last_error(void) { return t_err.c_str(); }
 const char* vdb_version(void) { return "vdb_b200 0.1 (sm_100a)"; }
 uint64_t vdb_launch_count(void) { return launch_count(); }
 
+int vdb_debug_level_plan(size_t nq, size_t n_rows, int k, int* out, int out_len) {
+    if (nq < 1 || n_rows < 1 || k < 1 || k > 128 || n_rows > 0xFFFFFFFFull) return fail(VDB_EINVAL, "bad argument");
+    const LevelPlan lp = gemm_topk_level_plan(nq, n_rows, k);
+    std::vector<int> v = {lp.kp, lp.kq, lp.cap, lp.growth, lp.query_blocks, lp.n_tiles, lp.n_pos, lp.probe_tiles,
+                          lp.probe_rank, (int)lp.levels.size()};
+    for (const LevelPlan::Level& lv : lp.levels) { v.push_back(lv.p0); v.push_back(lv.p1); v.push_back(lv.rank_after); }
+    for (int i = 0; i < (int)v.size() && i < out_len; ++i)
+        if (out) out[i] = v[i];
+    return (int)v.size();
+}
+
 int vdb_create(int dim, int metric, int store_dtype, size_t capacity, int device, vdb_t** out) {
     if (!out) return fail(VDB_EINVAL, "out is null");
     *out = nullptr;

@@ -129,6 +129,12 @@ int vdb_set_option(vdb_t *db, const char *name, long value);
 long vdb_get_stat(vdb_t *db, const char *name); /* "fallback_queries", "tensor_batches", ... */
 const char *vdb_last_error(void);
 const char *vdb_version(void);
+/* The launch sequence the batched tensor-core search would use for nq queries over n_rows rows at top-k (pure
+ * host arithmetic, no device needed).  out[0..9] = k', tight rank, buffer keys per query, growth, 256-query blocks,
+ * 256-row tiles, positions (tiles rounded up to a power of two), probe positions, probe threshold rank, levels L;
+ * then L triples (first position, end position, threshold rank published after the level; 0 = last level).
+ * Returns the number of ints the plan needs (written up to out_len), or a negative error code. */
+int vdb_debug_level_plan(size_t nq, size_t n_rows, int k, int *out, int out_len);
 
 #ifdef __cplusplus
 }
