@@ -226,58 +226,25 @@ def run_ours(a):
         vdb._ffi.check(lib.vdb_synth_dev(SEED_QUERY, 0, nq, a.dim, q.data_ptr(), stream), "synth")
         return q
 
-    def exchange_buffers(nq):
-        """N>1: per-rank lists [nq,k] -> all-to-all by query slice -> [world, nq/world, k] on the owner of the slice"""
-        sl = (nq + world - 1) // world
-        return (torch.empty((world, sl, a.k), dtype=torch.int64, device=dev),
-                torch.empty((world, sl, a.k), dtype=torch.float32, device=dev),
-                torch.empty((sl, a.k), dtype=torch.int64, device=dev),
-                torch.empty((sl, a.k), dtype=torch.float32, device=dev))
-
-    px = None
-    if world > 1 and a.exchange == "p2p":
-        def gather_handles(mine: bytes):
-            t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(dev)
-            o = torch.empty((world, 64), dtype=torch.uint8, device=dev)
-            dist.all_gather_into_tensor(o, t)
-            return [o[r].cpu().numpy().tobytes() for r in range(world)]
-        px = vdb.PeerExchange(local, rank, world, max_slice=global_batch(a, world) // world, max_k=a.k,
-                              exchange_handles=gather_handles)
-
-    def exchange_and_merge(ids, dd, nq, bufs):
-        g_ids, g_dd, o_ids, o_dd = bufs
-        if px is not None:      # one kernel: peer stores over NVLink, flags, merge of the owned slice
-            px.merge(dd.data_ptr(), ids.data_ptr(), nq, a.k, o_dd.data_ptr(), o_ids.data_ptr(), stream)
-            return
-        dist.all_to_all_single(g_ids.view(nq, a.k), ids)      # rank r receives every rank's lists for slice r
-        dist.all_to_all_single(g_dd.view(nq, a.k), dd)
-        vdb._ffi.check(lib.vdb_merge_topk(g_dd.data_ptr(), g_ids.data_ptr(), world, nq // world, a.k, a.k,
-                                          o_dd.data_ptr(), o_ids.data_ptr(), 1, local, stream), "merge")
+    # N > 1: the sharded client API (ShardedIndex: slice upload + NVLink all-gather of the queries, local search of
+    # the whole batch, exchange by query slice + merge on the owner)
+    sx = None
+    if world > 1:
+        sx = vdb.ShardedIndex(ix, max_batch=global_batch(a, world), max_k=a.k, exchange=a.exchange)
 
     def device_leg(nq, steps, warmup):
         """queries + results resident in HBM; returns (seconds for `steps`, dominant-kernel ns, launches)"""
-        sharded = world > 1 and (nq % world == 0 or px is not None)    # K5x takes ragged batches (a single query)
         q = make_queries(nq)
         ids = torch.empty((nq, a.k), dtype=torch.int64, device=dev)
         dd = torch.empty((nq, a.k), dtype=torch.float32, device=dev)
         cnt = torch.empty((nq,), dtype=torch.int32, device=dev)
-        if sharded:
-            bufs = exchange_buffers(nq)
-        elif world > 1:     # a single query: all-gather the lists, every rank merges
-            g_ids = torch.empty((world, nq, a.k), dtype=torch.int64, device=dev)
-            g_dd = torch.empty((world, nq, a.k), dtype=torch.float32, device=dev)
-            o_ids = torch.empty((nq, a.k), dtype=torch.int64, device=dev)
-            o_dd = torch.empty((nq, a.k), dtype=torch.float32, device=dev)
+        res = [None]
 
         def step():
-            ix.search_device(q.data_ptr(), nq, a.k, ids.data_ptr(), dd.data_ptr(), cnt.data_ptr(), stream)
-            if sharded:
-                exchange_and_merge(ids, dd, nq, bufs)
-            elif world > 1:
-                dist.all_gather_into_tensor(g_ids, ids)
-                dist.all_gather_into_tensor(g_dd, dd)
-                vdb._ffi.check(lib.vdb_merge_topk(g_dd.data_ptr(), g_ids.data_ptr(), world, nq, a.k, a.k,
-                                                  o_dd.data_ptr(), o_ids.data_ptr(), 1, local, stream), "merge")
+            if sx is None:
+                ix.search_device(q.data_ptr(), nq, a.k, ids.data_ptr(), dd.data_ptr(), cnt.data_ptr(), stream)
+            else:
+                res[0] = sx.search_device(q, a.k)           # (dist, ids) of this rank's slice
 
         for _ in range(warmup):
             step()
@@ -303,59 +270,30 @@ def run_ours(a):
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        final = (bufs[2] if sharded else (o_ids if world > 1 else ids))[:4096].cpu().numpy()   # rank 0: the first queries of the batch (its slice when sharded)
+        final = (ids if sx is None else res[0][1])[:4096].cpu().numpy()   # rank 0: the first queries of the batch (its slice when sharded)
         return float(ms.item()) * 1e-3, kern_ns, nprof, launches, final
 
     def e2e_leg(nq, steps, warmup):
         """through the public host-buffer API: H2D of the queries and D2H of the results inside the timed region"""
-        sharded = world > 1 and (nq % world == 0 or px is not None)
         qh = vdb.pinned_empty((nq, a.dim), np.float32)   # page-locked host buffers, filled outside the timed region
         qh[:] = make_queries(nq).cpu().numpy()
-        outs = (vdb.pinned_empty((nq, a.k), np.int64), vdb.pinned_empty((nq, a.k), np.float32),
-                vdb.pinned_empty((nq,), np.int32))
-        if world > 1:
-            # the batch arrives split over the ranks' hosts: each rank uploads ITS slice of the queries and the
-            # slices are all-gathered over NVLink (every rank needs the whole batch); results of the rank's
-            # slice go back to its page-locked host buffers
-            even = nq % world == 0
-            sl = nq // world if even else nq
-            pin_q = torch.from_numpy(qh[rank * sl:(rank + 1) * sl] if even else qh).pin_memory()
-            qd = torch.empty((nq, a.dim), dtype=torch.float32, device=dev)
-            ids = torch.empty((nq, a.k), dtype=torch.int64, device=dev)
-            dd = torch.empty((nq, a.k), dtype=torch.float32, device=dev)
-            n_out = (nq + world - 1) // world if sharded else nq
-            h_ids = torch.empty((n_out, a.k), dtype=torch.int64).pin_memory()
-            h_dd = torch.empty((n_out, a.k), dtype=torch.float32).pin_memory()
-            if sharded:
-                bufs = exchange_buffers(nq)
-            else:
-                g_ids = torch.empty((world, nq, a.k), dtype=torch.int64, device=dev)
-                g_dd = torch.empty((world, nq, a.k), dtype=torch.float32, device=dev)
-                o_ids = torch.empty((nq, a.k), dtype=torch.int64, device=dev)
-                o_dd = torch.empty((nq, a.k), dtype=torch.float32, device=dev)
+        if sx is None:
+            outs = (vdb.pinned_empty((nq, a.k), np.int64), vdb.pinned_empty((nq, a.k), np.float32),
+                    vdb.pinned_empty((nq,), np.int32))
 
-        def step():
-            if world == 1:
+            def step():
                 return ix.knn_query_padded(qh, a.k, out=outs)
-            if even:
-                qd[rank * sl:(rank + 1) * sl].copy_(pin_q, non_blocking=True)
-                dist.all_gather_into_tensor(qd, qd[rank * sl:(rank + 1) * sl])
-            else:
-                qd.copy_(pin_q, non_blocking=True)            # a single query: every rank uploads it
-            ix.search_device(qd.data_ptr(), nq, a.k, ids.data_ptr(), dd.data_ptr(), 0, stream)
-            if sharded:
-                exchange_and_merge(ids, dd, nq, bufs)
-                h_ids.copy_(bufs[2], non_blocking=True)       # each rank returns the results of its slice
-                h_dd.copy_(bufs[3], non_blocking=True)
-            else:
-                dist.all_gather_into_tensor(g_ids, ids)
-                dist.all_gather_into_tensor(g_dd, dd)
-                vdb._ffi.check(lib.vdb_merge_topk(g_dd.data_ptr(), g_ids.data_ptr(), world, nq, a.k, a.k,
-                                                  o_dd.data_ptr(), o_ids.data_ptr(), 1, local, stream), "merge")
-                h_ids.copy_(o_ids, non_blocking=True)
-                h_dd.copy_(o_dd, non_blocking=True)
-            torch.cuda.current_stream().synchronize()         # the caller holds its results when step() returns
-            return h_ids, h_dd
+        else:
+            # the batch arrives split over the ranks' hosts: each rank passes ITS slice and gets that slice's results;
+            # a batch that does not divide by N (the single query) is passed whole by every rank
+            even = nq % world == 0
+            sl = nq // world
+            pin_q = torch.from_numpy(qh[rank * sl:(rank + 1) * sl] if even else qh).pin_memory()
+            out = [None]
+
+            def step():
+                out[0] = sx.search_host(pin_q, a.k, whole_batch=not even, out=out[0])
+                return out[0]
 
         for _ in range(warmup):
             step()
@@ -479,7 +417,7 @@ def run_ours(a):
             "config": {"workload": workload_name(a, world), "global_batch": B, "rows_total": a.rows,
                        "rows_per_gpu": hi - lo, "sharding": f"contiguous rows x{world}",
                        "exchange": "none" if world == 1 else (
-                           "fused NVLink peer-store exchange + merge kernel, by query slice" if px is not None
+                           "fused NVLink peer-store exchange + merge kernel, by query slice" if a.exchange == "p2p"
                            else "all-to-all by query slice (NCCL) + GPU merge"),
                        "l2": "inputs larger than L2 (no flush needed)", "path": "tensor" if tensor_batches > 0 else "scan"},
             "e2e": {"value": B * a.steps / e2e_sec, "unit": "queries/s",

@@ -202,3 +202,126 @@ class PeerExchange:
             self.close()
         except Exception:
             pass
+
+
+class ShardedIndex:
+    """One rank of a database sharded by rows over the GPUs of one box (one process per GPU in a torch.distributed
+    job; GPU g holds what datanode g would): the call a client of rank r makes -- ITS SLICE of the query batch in,
+    the merged results of that slice out -- i.e. coordinator/handler.py:186-216 with every step on the GPUs:
+
+      1. each rank uploads its slice of the queries; the slices are all-gathered over NVLink (every shard must see
+         the whole batch -- the broadcast of :191-197)
+      2. each rank searches its shard for the whole batch (`Index.search_device`: K1 / K2)
+      3. the per-rank lists are exchanged by query slice and merged on the slice's owner (:200-216): the fused
+         NVLink exchange + merge kernel (`exchange="p2p"`, K5x) or NCCL all-to-all + the merge kernel ("nccl")
+
+    A batch that does not divide by the world size (a single query) is replicated: every rank passes the whole
+    batch and gets the whole result.  Buffers are allocated once for `max_batch` x `max_k`."""
+
+    def __init__(self, index, *, max_batch: int, max_k: int, exchange: str = "p2p", group=None):
+        import torch
+        import torch.distributed as dist
+        from . import _ffi
+        self._torch, self._dist, self._ffi = torch, dist, _ffi
+        self.ix, self.group = index, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.dev = torch.device("cuda", index.device)
+        self.max_batch, self.max_k = int(max_batch), int(max_k)
+        sl = (self.max_batch + self.world - 1) // self.world
+        self.px = None
+        if exchange == "p2p" and self.world > 1:
+            self.px = PeerExchange(index.device, self.rank, self.world, max_slice=sl, max_k=self.max_k,
+                                   exchange_handles=self._gather_handles)
+        elif exchange not in ("p2p", "nccl"):
+            raise ValueError("exchange must be 'p2p' or 'nccl'")
+        e = lambda *shape, dtype: torch.empty(shape, dtype=dtype, device=self.dev)          # noqa: E731
+        self._q = e(self.max_batch, index.dim, dtype=torch.float32)
+        self._ids = e(self.max_batch * self.max_k, dtype=torch.int64)
+        self._dd = e(self.max_batch * self.max_k, dtype=torch.float32)
+        self._g_ids = e(self.world * self.max_batch * self.max_k, dtype=torch.int64)         # nccl path / replicated batch
+        self._g_dd = e(self.world * self.max_batch * self.max_k, dtype=torch.float32)
+        self._o_ids = e(self.max_batch * self.max_k, dtype=torch.int64)
+        self._o_dd = e(self.max_batch * self.max_k, dtype=torch.float32)
+        self._views = {}
+
+    def _gather_handles(self, mine: bytes):
+        torch, dist = self._torch, self._dist
+        t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(self.dev)
+        o = torch.empty((self.world, 64), dtype=torch.uint8, device=self.dev)
+        dist.all_gather_into_tensor(o, t, group=self.group)
+        return [o[r].cpu().numpy().tobytes() for r in range(self.world)]
+
+    def slice_of(self, nq: int) -> Tuple[int, int]:
+        """rows [lo, hi) of a batch of nq queries whose results this rank gets back: slices of ceil(nq / world)
+        (a single query belongs to rank 0; ranks past the end own nothing)"""
+        s = (nq + self.world - 1) // self.world
+        return min(nq, self.rank * s), min(nq, (self.rank + 1) * s)
+
+    def search_device(self, d_queries, k: int):
+        """`d_queries` [nq, dim] fp32 on this rank's GPU, the WHOLE batch -> (dist [n, k], ids [n, k]) device tensors
+        of this rank's slice (`slice_of(nq)`; views of internal buffers, valid until the next call; enqueued on the
+        current stream)."""
+        torch, dist = self._torch, self._dist
+        nq = int(d_queries.shape[0])
+        if nq > self.max_batch or k > self.max_k:
+            raise ValueError("batch or k beyond what this ShardedIndex was sized for")
+        stream = torch.cuda.current_stream().cuda_stream
+        v = self._views.get((nq, k))
+        if v is None:                 # tensor views per batch shape, made once (they cost more than the launches)
+            lo, hi = self.slice_of(nq)
+            s = (nq + self.world - 1) // self.world
+            v = self._views[(nq, k)] = (self._ids[:nq * k].view(nq, k), self._dd[:nq * k].view(nq, k), lo, hi, s,
+                                        self._o_ids[:s * k].view(s, k), self._o_dd[:s * k].view(s, k),
+                                        self._o_ids[:s * k].view(s, k)[:hi - lo], self._o_dd[:s * k].view(s, k)[:hi - lo])
+        ids, dd, lo, hi, s, o_ids, o_dd, r_ids, r_dd = v
+        self.ix.search_device(d_queries.data_ptr(), nq, k, ids.data_ptr(), dd.data_ptr(), 0, stream)
+        if self.world == 1:
+            return dd, ids
+        if self.px is not None:       # one kernel: peer stores over NVLink, flags, merge of the owned slice (ragged too)
+            self.px.merge(dd.data_ptr(), ids.data_ptr(), nq, k, o_dd.data_ptr(), o_ids.data_ptr(), stream)
+            return r_dd, r_ids
+        lib = self._ffi.lib()
+        if nq % self.world == 0:      # rank r receives every rank's lists for slice r
+            g_ids, g_dd = self._g_ids[:nq * k].view(nq, k), self._g_dd[:nq * k].view(nq, k)
+            dist.all_to_all_single(g_ids, ids, group=self.group)
+            dist.all_to_all_single(g_dd, dd, group=self.group)
+            self._ffi.check(lib.vdb_merge_topk(g_dd.data_ptr(), g_ids.data_ptr(), self.world, s, k, k, o_dd.data_ptr(),
+                                               o_ids.data_ptr(), 1, self.ix.device, stream), "merge")
+            return o_dd, o_ids
+        # ragged batch: all-gather the lists, every rank merges, keeps its slice
+        g_ids = self._g_ids[:self.world * nq * k].view(self.world * nq, k)
+        g_dd = self._g_dd[:self.world * nq * k].view(self.world * nq, k)
+        dist.all_gather_into_tensor(g_ids, ids, group=self.group)
+        dist.all_gather_into_tensor(g_dd, dd, group=self.group)
+        a_ids, a_dd = self._ids[:nq * k].view(nq, k), self._dd[:nq * k].view(nq, k)      # the local lists are spent
+        self._ffi.check(lib.vdb_merge_topk(g_dd.data_ptr(), g_ids.data_ptr(), self.world, nq, k, k, a_dd.data_ptr(),
+                                           a_ids.data_ptr(), 1, self.ix.device, stream), "merge")
+        return a_dd[lo:hi], a_ids[lo:hi]
+
+    def search_host(self, q, k: int, *, whole_batch: bool = False, out=None):
+        """The client call.  `q`: float32 [n, dim] in page-locked host memory (torch pinned tensor; a numpy array is
+        wrapped) -- this rank's rows of the batch (every rank passes the same number of rows; the batch is their
+        concatenation in rank order), or with `whole_batch=True` the entire batch on every rank (batches that do
+        not divide by the world size: a single query).  Returns (ids int64 [m, k], dist float32 [m, k]): page-locked
+        host tensors with the results of the rows this rank owns (`slice_of`), complete when the call returns.
+        `out=(ids, dist)` reuses result buffers of the right shape."""
+        torch, dist = self._torch, self._dist
+        if not torch.is_tensor(q):
+            q = torch.from_numpy(q)
+        n = int(q.shape[0])
+        if whole_batch or self.world == 1:
+            d_q = self._q[:n]
+            d_q.copy_(q, non_blocking=True)
+        else:
+            d_q = self._q[:n * self.world]
+            mine = d_q[self.rank * n:(self.rank + 1) * n]
+            mine.copy_(q, non_blocking=True)
+            dist.all_gather_into_tensor(d_q, mine, group=self.group)     # in place: slice r of d_q is rank r's upload
+        dd, ids = self.search_device(d_q, k)
+        if out is None or tuple(out[0].shape) != tuple(ids.shape):
+            out = (torch.empty(tuple(ids.shape), dtype=torch.int64).pin_memory(),
+                   torch.empty(tuple(dd.shape), dtype=torch.float32).pin_memory())
+        out[0].copy_(ids, non_blocking=True)
+        out[1].copy_(dd, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out

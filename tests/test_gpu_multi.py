@@ -171,3 +171,66 @@ def test_peer_exchange_equals_nccl_and_oracle(metric, nq, k):
             for i in range(sl):
                 msg = R.check_topk(ids[i], dd[i], q[r * sl + i], stored, np.arange(n), k, metric, rtol=1e-5)
                 assert msg is None, f"step {step} rank {r} query {i}: {msg}"
+
+
+def _worker_sharded_index(rank, world, port, n, dim, k, exchange, out):
+    """the client API (ShardedIndex.search_host): slices in, slices out; even and ragged batches"""
+    import torch
+    import torch.distributed as dist
+    import dvdb_b200 as vdb
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        lo, hi = vdb.sharding.contiguous_range(n, rank, world)
+        ix = vdb.Index("cosine", dim, device=rank)
+        ix.init_index(hi - lo)
+        ix.add_items(R.synth_rows(R.SEED_DB, lo, hi - lo, dim), np.arange(lo, hi))
+        sx = vdb.ShardedIndex(ix, max_batch=64, max_k=k, exchange=exchange)
+        res = {}
+        for nq in (64, 1, 3, 64):
+            q = R.synth_rows(R.SEED_QUERY, 11 * nq, nq, dim)
+            if nq % world == 0:
+                sl = nq // world
+                mine = vdb.pinned_empty((sl, dim), np.float32)
+                mine[:] = q[rank * sl:(rank + 1) * sl]
+                ids, dd = sx.search_host(mine, k)
+            else:
+                ids, dd = sx.search_host(torch.from_numpy(q).pin_memory(), k, whole_batch=True)
+            assert (lo_hi := sx.slice_of(nq)) and ids.shape[0] == lo_hi[1] - lo_hi[0]
+            res[nq] = (lo_hi, ids.numpy().copy(), dd.numpy().copy())
+        out.put((rank, res))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+def test_sharded_index_client_api(exchange):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    n, dim, k, world = 5000, 512, 10, 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_sharded_index, args=(r, world, port, n, dim, k, exchange, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(out.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    stored = R.prepare_rows(R.synth_rows(R.SEED_DB, 0, n, dim), "cosine")
+    for nq in (64, 1, 3):
+        q = R.synth_rows(R.SEED_QUERY, 11 * nq, nq, dim)
+        covered = []
+        for r in range(world):
+            (lo, hi), ids, dd = got[r][nq]
+            covered += list(range(lo, hi))
+            for i in range(hi - lo):
+                msg = R.check_topk(ids[i], dd[i], q[lo + i], stored, np.arange(n), k, "cosine", rtol=1e-5)
+                assert msg is None, f"{exchange} nq {nq} rank {r} query {lo + i}: {msg}"
+        assert covered == list(range(nq))            # every query answered by exactly one rank
