@@ -267,3 +267,33 @@ def test_micro_batcher_edge_cases(vdb, tmp_path):
     h.hnsw_index.knn_query_padded = boom
     bad = h.search(vdb.SearchRequest(query_vector=vec(1), top_k=2))
     assert not bad.success and "HNSW index corrupted" in bad.message
+
+
+# ---------------------------------------------------------------------------------------------
+# bench.py contract (the reference arm runs without a GPU)
+# ---------------------------------------------------------------------------------------------
+def test_bench_reference_arm_prints_the_contract_line():
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "2",
+                          "--warmup", "1", "--rows", "20000", "--cpu-queries", "16"], capture_output=True, text=True,
+                         timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1                                   # ONE json line
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "cpu_baseline", "impl"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["unit"] == "queries/s" and d["higher_is_better"] is True
+    assert d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 1 and d["vs_baseline"] is None
+    assert d["config"]["workload"].startswith("20000x512 f32 cosine top-10") and "model" not in d["config"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    # a rank other than 0 prints nothing and exits 0
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                         capture_output=True, text=True, timeout=120, cwd=root, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
