@@ -47,6 +47,7 @@ SIGNATURES = {
     "vdb_xchg_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, C.POINTER(_vp), _vp]),
     "vdb_xchg_connect": (C.c_int, [_vp, _vp]),
     "vdb_xchg_merge_dev": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_int, _vp, _vp, _vp]),
+    "vdb_xchg_status": (C.c_int, [_vp]),
     "vdb_xchg_destroy": (None, [_vp]),
     "vdb_launch_count": (C.c_uint64, []),
     "vdb_set_option": (C.c_int, [_vp, C.c_char_p, C.c_long]),

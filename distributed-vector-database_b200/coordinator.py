@@ -192,6 +192,11 @@ class PeerExchange:
         self._ffi.check(self._ffi.lib().vdb_xchg_merge_dev(self._h, d_dist_ptr, d_ids_ptr, nq, int(k), o_dist_ptr,
                                                            o_ids_ptr, stream or None), "xchg_merge")
 
+    def status(self) -> None:
+        """Raises RuntimeError if a step failed (a peer never arrived, or arrived with another batch size / k).
+        Call after synchronising the stream the step was enqueued on."""
+        self._ffi.check(self._ffi.lib().vdb_xchg_status(self._h), "xchg_status")
+
     def close(self):
         if self._h is not None:
             self._ffi.lib().vdb_xchg_destroy(self._h)
@@ -243,6 +248,12 @@ class ShardedIndex:
         self._o_ids = e(self.max_batch * self.max_k, dtype=torch.int64)
         self._o_dd = e(self.max_batch * self.max_k, dtype=torch.float32)
         self._views = {}
+
+    def close(self) -> None:
+        """Releases the peer-memory exchange (collective: every rank closes before the process group goes away)."""
+        if self.px is not None:
+            self.px.close()
+            self.px = None
 
     def _gather_handles(self, mine: bytes):
         torch, dist = self._torch, self._dist

@@ -1188,13 +1188,23 @@ static cudaError_t grow_dev(T*& ptr, size_t& cap, size_t need) {
     return e;
 }
 
+// cudaFuncSetAttribute is per device: a process that holds shards on several GPUs (one handler per GPU under a
+// LocalCoordinator) must configure every kernel once on each of them
+constexpr int MAX_DEVICES = 64;
+static int current_device_slot() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev & (MAX_DEVICES - 1);
+}
+
 template <bool F16, bool L2>
 static cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& gp, int grid, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[MAX_DEVICES] = {};
+    const int slot = current_device_slot();
+    if (!configured[slot]) {
         cudaError_t e = cudaFuncSetAttribute(gemm_filter_kernel<F16, L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES_FILTER);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured[slot] = true;
     }
     cudaError_t e = launch_pdl(gemm_filter_kernel<F16, L2>, dim3(grid), dim3(GT_THREADS), GT_SMEM_BYTES_FILTER, st, tmA, tmB, gp);
     count_launch();
@@ -1204,11 +1214,12 @@ static cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, c
 template <typename T>
 static cudaError_t launch_rerank_window(int kp, const RerankParams& rp, size_t nq, cudaStream_t st) {
     const size_t smem = 2 * (size_t)rp.cap * sizeof(uint64_t);
-    static size_t configured = 0;
-    if (smem > configured) {
+    static size_t configured[MAX_DEVICES] = {};
+    const int slot = current_device_slot();
+    if (smem > configured[slot]) {
         cudaError_t e = cudaFuncSetAttribute(rerank_window_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
+        configured[slot] = smem;
     }
     cudaError_t le = launch_pdl(rerank_window_kernel<T>, dim3((unsigned)nq), dim3(kp <= 64 ? 128 : RW_MAX_THREADS), smem, st, rp, kp);
     count_launch();
@@ -1352,11 +1363,12 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
     SelectParams sp{};
     sp.buf = w->buf; sp.cnt = w->cnt; sp.cap = cap; sp.kp = kp; sp.thr = w->thr; sp.overflow = w->overflow;
     sp.tomb = a.tomb; sp.n_rows = a.n_rows;
-    static bool sel_configured = false;
-    if (!sel_configured) {
+    static bool sel_configured[MAX_DEVICES] = {};
+    const int dev_slot = current_device_slot();
+    if (!sel_configured[dev_slot]) {
         if ((e = cudaFuncSetAttribute(select_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(select_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)) != cudaSuccess) return e;
-        sel_configured = true;
+        sel_configured[dev_slot] = true;
     }
     int sel_np = 2;
     while (sel_np < cap) sel_np <<= 1;
@@ -1409,8 +1421,10 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
     // |approx dot - exact dot| <= eps_rel * ||q|| * ||d||  (+ eps_abs_unit * sqrt(dim) * (||q|| + ||d||) for fp16
     // subnormal rounding).  fp16 shard: only the query is rounded (u = 2^-11 = 4.9e-4); shadow plane: query and
     // row are rounded (2u + u^2 = 9.8e-4); tf32 operands are truncated to 10 mantissa bits (2 * 2^-10 = 1.95e-3).
-    // The rest is slack for the fp32 accumulation inside the tensor core.
-    rp.eps_rel = a.f16 ? 6.5e-4f : (a.shadow ? 1.3e-3f : 2.5e-3f);
+    // Accumulation term: the tensor core adds `dim` exact products in fp32; with truncating adds the partial sums
+    // drift by at most dim * 2^-23 * sum|q_i d_i| <= dim * 2^-23 * ||q|| ||d|| (6.1e-5 at dim 512, 9.8e-4 at 8192).
+    const float eps_round = a.f16 ? 4.9e-4f : (a.shadow ? 9.8e-4f : 1.96e-3f);
+    rp.eps_rel = eps_round + (float)a.dim * 1.1920929e-7f + 1.0e-4f;
     rp.eps_abs = g16 ? 3.0e-8f * sqrtf((float)a.dim) : 0.0f;     // 2^-25 per element, Cauchy-Schwarz over dim
     rp.f16_range = g16 ? 1 : 0;
     rp.out_ids = a.out_ids; rp.out_dist = a.out_dist; rp.out_counts = a.out_counts;

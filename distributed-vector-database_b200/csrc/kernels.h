@@ -50,16 +50,20 @@ cudaError_t launch_merge_topk(const MergeParams& p, cudaStream_t st);
 
 // ---- K5x exchange + merge over NVLink peer memory (merge_topk.cu) ---------------------------
 constexpr int XCHG_MAX_WORLD = 16;
+enum { XCHG_ERR_TIMEOUT = 1, XCHG_ERR_SHAPE = 2, XCHG_ERR_STEP = 3 };
 struct XchgParams {
     int rank, world, parity;
     uint32_t step;                 // 1, 2, 3, ... (flags start at 0)
+    uint32_t shape;                // hash of (nq, k): must be the same on every rank of a step
+    unsigned long long timeout_ns; // bound on the wait for the peers
+    uint32_t* err;                 // host-visible (mapped pinned) [4]: code, step, peer, -
     size_t nq, slice, owned;       // global batch; slice = ceil(nq / world); queries this rank owns (<= slice)
     int k;
     const int64_t* ids;            // this rank's lists [nq][k] (id < 0 = padding)
     const float* dist;
     uint64_t* peer_buf[XCHG_MAX_WORLD];    // receive buffer of every rank: [2][world][stride_src] keys
-    uint32_t* peer_flag[XCHG_MAX_WORLD];   // flag words of every rank: [2][world]
-    const uint32_t* local_flag;
+    uint64_t* peer_flag[XCHG_MAX_WORLD];   // flag words of every rank: [2][world] of (shape << 32 | step)
+    const uint64_t* local_flag;
     size_t stride_parity, stride_src;
     unsigned int* done_counter;    // local, zeroed by the launcher
 };

@@ -190,16 +190,30 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_select_kernel(const Merge
 // r.  One launch per rank:
 //   phase 1  pack (distance, id) into sortable keys and STORE each query's list straight into the owner's
 //            receive buffer (peer pointers opened with CUDA IPC; coalesced 8-byte stores over NVLink)
-//   phase 2  the last CTA to finish phase 1 publishes this step's number in every peer's flag word
-//            (system-scope fence + store)
+//   phase 2  the last CTA to finish phase 1 publishes (shape, step) in every peer's flag word: one 8-byte store
+//            per peer after a system-scope fence
 //   phase 3  wait until all G flags carry this step, then merge the G lists of each owned query
 // Receive buffers are double-buffered by step parity: a rank can only be two steps ahead of a peer after that
 // peer has pushed the step in between, which it does after finishing its merge of the older step.
+//
+// Liveness.  Every CTA waits in phase 3 while this rank's own flag is only published once ALL its CTAs have
+// finished phase 1: a CTA queued behind waiting ones would deadlock two ranks against each other.  The launch
+// is therefore COOPERATIVE (the driver places the whole grid at once or not at all, whatever else runs on the
+// device) and the grid is sized from the occupancy calculator.  The wait itself is bounded: a peer that never
+// arrives (it raised before its launch, or died) or arrives with another (nq, k) makes every CTA give up,
+// pad its outputs and record the failure in a host-visible word that vdb_xchg_status / the next merge report.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(MERGE_THREADS) exchange_merge_kernel(const XchgParams x, const MergeParams mp) {
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void __launch_bounds__(MERGE_THREADS, 2) exchange_merge_kernel(const XchgParams x, const MergeParams mp) {
     __shared__ uint64_t buf[MERGE_BUF];
-    __shared__ int s_last;
+    __shared__ int s_last, s_fail;
     const size_t total = x.nq * (size_t)x.k;
+    if (threadIdx.x == 0) s_fail = 0;
     for (size_t i = blockIdx.x * (size_t)MERGE_THREADS + threadIdx.x; i < total; i += (size_t)gridDim.x * MERGE_THREADS) {
         const size_t q = i / x.k;
         const int j = (int)(i - q * x.k);
@@ -213,17 +227,42 @@ __global__ void __launch_bounds__(MERGE_THREADS) exchange_merge_kernel(const Xch
     __syncthreads();
     if (threadIdx.x == 0) s_last = atomicAdd(x.done_counter, 1u) == gridDim.x - 1 ? 1 : 0;
     __syncthreads();
+    const uint64_t my_word = ((uint64_t)x.shape << 32) | x.step;
     if (s_last) {
         __threadfence_system();
         if (threadIdx.x < x.world)
-            *reinterpret_cast<volatile uint32_t*>(x.peer_flag[threadIdx.x] + x.parity * x.world + x.rank) = x.step;
+            *reinterpret_cast<volatile uint64_t*>(x.peer_flag[threadIdx.x] + x.parity * x.world + x.rank) = my_word;
     }
     if (threadIdx.x < x.world) {
-        const volatile uint32_t* f = x.local_flag + x.parity * x.world + threadIdx.x;
-        while (*f < x.step) __nanosleep(200);
+        const volatile uint64_t* f = x.local_flag + x.parity * x.world + threadIdx.x;
+        const uint64_t t0 = global_timer_ns();
+        uint64_t w;
+        int fail = 0;
+        while ((uint32_t)(w = *f) < x.step) {       // steps only grow; a peer already past this step is a protocol error
+            __nanosleep(200);
+            if (global_timer_ns() - t0 > x.timeout_ns) { fail = XCHG_ERR_TIMEOUT; break; }
+        }
+        if (!fail && w != my_word) fail = (uint32_t)w != x.step ? XCHG_ERR_STEP : XCHG_ERR_SHAPE;
+        if (fail) {
+            s_fail = fail;
+            // host-visible record: code, step, peer (first writer wins; all CTAs report the same kind of failure)
+            if (atomicCAS(reinterpret_cast<unsigned int*>(x.err), 0u, (unsigned int)fail) == 0u) {
+                x.err[1] = x.step;
+                x.err[2] = (uint32_t)threadIdx.x;
+                __threadfence_system();
+            }
+        }
     }
     __threadfence_system();
     __syncthreads();
+    if (s_fail) {                                     // no usable input: pad this rank's outputs
+        for (size_t i = blockIdx.x * (size_t)MERGE_THREADS + threadIdx.x; i < x.owned * (size_t)mp.k_out;
+             i += (size_t)gridDim.x * MERGE_THREADS) {
+            if (mp.out_ids) mp.out_ids[i] = -1;
+            if (mp.out_dist) mp.out_dist[i] = __int_as_float(0x7f800000);
+        }
+        return;
+    }
     for (size_t ql = blockIdx.x; ql < x.owned; ql += gridDim.x) {   // queries this rank owns (ragged last slice)
         merge_stream(mp, ql, buf);
         __syncthreads();
@@ -234,11 +273,27 @@ cudaError_t launch_exchange_merge(const XchgParams& x, const MergeParams& mp, in
     if (mp.k_out < 1 || mp.k_out > MERGE_BUF / 2) return cudaErrorInvalidValue;
     cudaError_t e = cudaMemsetAsync(x.done_counter, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess) return e;
-    // every CTA waits for the peers in phase 3: keep the grid co-resident (no CTA may queue behind a waiting one)
-    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((size_t)num_sms * 2, std::max(x.slice, (x.nq * x.k + MERGE_THREADS - 1) / MERGE_THREADS)));
-    exchange_merge_kernel<<<grid, MERGE_THREADS, 0, st>>>(x, mp);
+    // co-resident grid: what the occupancy calculator says fits, launched cooperatively (see the kernel's header)
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, exchange_merge_kernel, MERGE_THREADS, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    const size_t resident = (size_t)num_sms * (size_t)std::min(per_sm, 2);
+    const size_t useful = std::max(x.slice, (x.nq * x.k + MERGE_THREADS - 1) / MERGE_THREADS);
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min(resident, useful));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(MERGE_THREADS);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, exchange_merge_kernel, x, mp);
     count_launch();
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t launch_merge_topk(const MergeParams& p, cudaStream_t st) {

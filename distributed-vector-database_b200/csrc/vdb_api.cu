@@ -254,6 +254,14 @@ struct ProfScope {   // records start/stop events around the dominant kernel whe
 static void prof_begin_cb(void* ctx, cudaStream_t) { static_cast<ProfScope*>(ctx)->begin(); }
 static void prof_end_cb(void* ctx, cudaStream_t) { static_cast<ProfScope*>(ctx)->end(); }
 
+// Queries one scan pass takes: up to 8, fewer when the rows are so long that 8 query vectors + k-lists no longer fit
+// beside the copy ring in shared memory (dim > 1152 fp32 / 1792 fp16).  0: k does not fit even for one query.
+int scan_group(const vdb* db, int k, size_t nq) {
+    int g = nq >= 8 ? 8 : nq >= 4 ? 4 : nq >= 2 ? 2 : 1;
+    while (g > 1 && scan_max_k(g, db->ld, (uint32_t)db->row_bytes()) < k) g >>= 1;
+    return scan_max_k(g, db->ld, (uint32_t)db->row_bytes()) >= k ? g : 0;
+}
+
 // Exact scan (K1 + K5) of nq PREPARED queries [nq][ld]; groups of up to 8 queries per pass.
 int scan_prepared(vdb* db, Workspace* ws, const float* d_qp, size_t nq, int k, int64_t* d_ids, float* d_dist,
                   int* d_cnt, cudaStream_t st, size_t n, bool raw = false) {
@@ -267,13 +275,15 @@ int scan_prepared(vdb* db, Workspace* ws, const float* d_qp, size_t nq, int k, i
     sp.tomb = db->any_dead ? db->tomb : nullptr;
     sp.k = k;
     sp.metric = db->metric == VDB_L2 ? 0 : 1;
-    // every pass of this call uses the launch shape of the widest pass (nq_t = min(nq, 8) rounded up)
-    const ScanPlan pl = scan_plan((int)std::min<size_t>(8, nq), (uint32_t)db->ld, sp.row_bytes, k, (uint32_t)n, db->num_sms);
+    // every pass of this call uses the launch shape of the widest pass
+    const int group = scan_group(db, k, nq);
+    if (group == 0) return fail(VDB_EINVAL, "k too large for the scan kernel at this dimension");
+    const ScanPlan pl = scan_plan(group, (uint32_t)db->ld, sp.row_bytes, k, (uint32_t)n, db->num_sms);
     if (pl.grid == 0) return fail(VDB_EINVAL, "k too large for the scan kernel at this dimension");
     const int grid = pl.grid;
     CU_TRY(grow(ws->d_keys, ws->keys_cap, nq * (size_t)grid * k));
-    for (size_t g = 0; g < nq; g += 8) {
-        sp.nq = (int)std::min<size_t>(8, nq - g);
+    for (size_t g = 0; g < nq; g += (size_t)group) {
+        sp.nq = (int)std::min<size_t>((size_t)group, nq - g);
         if (raw) {   // queries as the caller gave them: normalised / padded inside the kernel
             sp.q_raw = d_qp + g * (size_t)db->dim;
             sp.dim = db->dim;
@@ -417,10 +427,7 @@ bool is_pinned_host(const void* p) {
 
 int check_k(const vdb* db, int k, size_t nq) {
     if (k < 1 || k > K_MAX) return fail(VDB_EINVAL, "k must be in [1, 1024]");
-    const int nq_t = nq >= 8 ? 8 : nq >= 4 ? 4 : nq >= 2 ? 2 : 1;
-    const int kmax = scan_max_k(nq_t, db->ld, (uint32_t)db->row_bytes());
-    if (kmax < 1) return fail(VDB_EINVAL, "dim too large for the scan kernel's shared-memory ring");
-    if (k > kmax) return fail(VDB_EINVAL, "k too large for this dim");
+    if (scan_group(db, k, nq) == 0) return fail(VDB_EINVAL, "k too large for this dim");
     return VDB_OK;
 }
 
@@ -466,7 +473,9 @@ int vdb_create(int dim, int metric, int store_dtype, size_t capacity, int device
     db->opt_scan_batch.store(store_dtype == VDB_F16 ? 2 : 4);
     const int unit = store_dtype == VDB_F16 ? 256 : 128;   // one 512-byte warp load
     db->ld = (dim + unit - 1) / unit * unit;
-    if (scan_max_k(1, db->ld, (uint32_t)db->row_bytes()) < 1) return fail(VDB_EINVAL, "dim too large for the scan kernel");
+    if (scan_max_k(1, db->ld, (uint32_t)db->row_bytes()) < 1)
+        return fail(VDB_EINVAL, "dim too large: a shard row must fit the scan kernel's shared-memory ring (dim <= 1408 for "
+                                "fp32 rows, <= 2816 for fp16 rows)");
     // fp32 shards keep an fp16 shadow plane for the batched tensor path (+50 % HBM); VDB_SHADOW=0 opts out
     const char* sh = getenv("VDB_SHADOW");
     if (store_dtype == VDB_F32 && !(sh && sh[0] == '0')) db->ld16 = (dim + 63) / 64 * 64;
@@ -681,6 +690,12 @@ int vdb_search(vdb_t* db, const float* queries, size_t nq, int k, int64_t* out_l
     if (!ws) return fail(VDB_ECUDA, "cannot create a search workspace (stream)");
     WsGuard guard{db, ws};
     cudaStream_t st = ws->stream;
+    // a vdb_search_dev call may have returned this workspace to the pool while its kernels were still running on
+    // the CALLER's stream: order this call's use of the scratch after them on the GPU
+    if (ws->used) {
+        CU_TRY(cudaStreamWaitEvent(st, ws->done, 0));
+        ws->used = false;          // this call synchronises `st` before it returns: nothing stays in flight
+    }
     const size_t qelems = nq * (size_t)db->dim, nout = nq * (size_t)k;
     CU_TRY(grow(ws->d_q_in, ws->q_in_cap, qelems));
     CU_TRY(grow_host(ws->h_q, ws->h_q_cap, qelems));
@@ -975,9 +990,22 @@ struct vdb_xchg {
     uint8_t* peer_base[XCHG_MAX_WORLD] = {};       // peer mappings ([rank] == base)
     bool connected = false;
     unsigned int* done_counter = nullptr;
+    uint32_t* h_err = nullptr;                     // pinned, mapped: [code, step, peer, -] written by the kernel
+    uint32_t* d_err = nullptr;                     // device alias of h_err
+    unsigned long long timeout_ns = 30ull * 1000000000ull;
     uint32_t step = 0;
     std::mutex mu;
 };
+
+static int xchg_error(vdb_xchg* x) {
+    const uint32_t code = *reinterpret_cast<volatile uint32_t*>(x->h_err);
+    if (!code) return VDB_OK;
+    const uint32_t step = x->h_err[1], peer = x->h_err[2];
+    const char* what = code == XCHG_ERR_TIMEOUT ? "timed out waiting for rank " :
+                       code == XCHG_ERR_SHAPE ? "batch size / k differs from rank " : "step counter out of sync with rank ";
+    return fail(VDB_ECUDA, std::string("vdb_xchg: step ") + std::to_string(step) + " " + what + std::to_string(peer) +
+                               "; the exchange is unusable (every rank must call vdb_xchg_merge_dev once per step with the same nq and k)");
+}
 
 int vdb_xchg_create(int device, int rank, int world, size_t max_slice, int max_k, vdb_xchg_t** out, unsigned char* handle64) {
     if (!out || !handle64) return fail(VDB_EINVAL, "null argument");
@@ -991,13 +1019,21 @@ int vdb_xchg_create(int device, int rank, int world, size_t max_slice, int max_k
     cudaDeviceProp prop;
     CU_TRY(cudaGetDeviceProperties(&prop, device));
     x->num_sms = prop.multiProcessorCount;
-    x->flag_bytes = 256;                                             // 2 * world u32, padded
+    x->flag_bytes = 256;                                             // [2 parities][16 ranks] x 8 bytes (shape << 32 | step)
+    static_assert(2 * XCHG_MAX_WORLD * sizeof(uint64_t) <= 256, "flag area");
+    if (const char* t = getenv("VDB_XCHG_TIMEOUT_MS")) {
+        const long ms = atol(t);
+        if (ms > 0) x->timeout_ns = (unsigned long long)ms * 1000000ull;
+    }
     x->stride_src = max_slice * (size_t)max_k;                       // keys per source rank
     x->stride_parity = x->stride_src * world;
     x->total_bytes = x->flag_bytes + 2 * x->stride_parity * sizeof(uint64_t);
     CU_TRY(cudaMalloc((void**)&x->base, x->total_bytes));
     CU_TRY(cudaMemset(x->base, 0, x->flag_bytes));
     CU_TRY(cudaMalloc((void**)&x->done_counter, sizeof(unsigned int)));
+    CU_TRY(cudaHostAlloc((void**)&x->h_err, 4 * sizeof(uint32_t), cudaHostAllocMapped));
+    memset(x->h_err, 0, 4 * sizeof(uint32_t));
+    CU_TRY(cudaHostGetDevicePointer((void**)&x->d_err, x->h_err, 0));
     CU_TRY(cudaDeviceSynchronize());
     cudaIpcMemHandle_t h;
     CU_TRY(cudaIpcGetMemHandle(&h, x->base));
@@ -1032,10 +1068,14 @@ int vdb_xchg_merge_dev(vdb_xchg_t* x, const float* d_dist, const int64_t* d_ids,
     const size_t slice = (nq + x->world - 1) / x->world;     // rank r owns queries [r*slice, min(nq, (r+1)*slice))
     if (slice > x->max_slice || k < 1 || k > x->max_k) return fail(VDB_EINVAL, "batch slice or k beyond what the exchange was created for");
     std::lock_guard<std::mutex> lk(x->mu);
+    if (int rc = xchg_error(x)) return rc;          // an earlier step failed: the ranks are no longer in lockstep
     CU_TRY(cudaSetDevice(x->device));
     XchgParams xp{};
     xp.rank = x->rank; xp.world = x->world;
     xp.step = ++x->step;
+    xp.shape = (uint32_t)((nq * 2654435761ull) ^ ((uint64_t)k << 20) ^ (nq >> 12));
+    xp.timeout_ns = x->timeout_ns;
+    xp.err = x->d_err;
     xp.parity = (int)(xp.step & 1);
     xp.nq = nq; xp.slice = slice; xp.k = k;
     { const size_t lo = std::min(nq, (size_t)x->rank * slice), hi = std::min(nq, lo + slice); xp.owned = hi - lo; }
@@ -1044,10 +1084,10 @@ int vdb_xchg_merge_dev(vdb_xchg_t* x, const float* d_dist, const int64_t* d_ids,
     xp.stride_src = slice * (size_t)k;
     xp.stride_parity = x->stride_parity;
     for (int r = 0; r < x->world; ++r) {
-        xp.peer_flag[r] = reinterpret_cast<uint32_t*>(x->peer_base[r]);
+        xp.peer_flag[r] = reinterpret_cast<uint64_t*>(x->peer_base[r]);
         xp.peer_buf[r] = reinterpret_cast<uint64_t*>(x->peer_base[r] + x->flag_bytes);
     }
-    xp.local_flag = reinterpret_cast<const uint32_t*>(x->base);
+    xp.local_flag = reinterpret_cast<const uint64_t*>(x->base);
     xp.done_counter = x->done_counter;
     MergeParams mp{};
     mp.in_keys = reinterpret_cast<const uint64_t*>(x->base + x->flag_bytes) + (size_t)xp.parity * x->stride_parity;
@@ -1066,7 +1106,13 @@ void vdb_xchg_destroy(vdb_xchg_t* x) {
         if (r != x->rank && x->peer_base[r]) cudaIpcCloseMemHandle(x->peer_base[r]);
     if (x->base) cudaFree(x->base);
     if (x->done_counter) cudaFree(x->done_counter);
+    if (x->h_err) cudaFreeHost(x->h_err);
     delete x;
+}
+
+int vdb_xchg_status(vdb_xchg_t* x) {
+    if (!x) return fail(VDB_EINVAL, "null argument");
+    return xchg_error(x);
 }
 
 int vdb_set_option(vdb_t* db, const char* name, long value) {

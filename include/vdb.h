@@ -42,7 +42,9 @@ enum vdb_error {
 };
 
 /* hnswlib.Index(space, dim) + init_index(max_elements, ...)   src/datanode/handler.py:46,86
- * ef_construction / M have no meaning for an exact index and are not taken. */
+ * ef_construction / M have no meaning for an exact index and are not taken.
+ * dim <= 1408 for fp32 rows, <= 2816 for fp16 rows (16 rows of a shard must fit one stage of the scan kernel's
+ * shared-memory ring; CLIP-style embeddings are 512 - 1024 wide); larger dims fail with VDB_EINVAL. */
 int vdb_create(int dim, int metric, int store_dtype, size_t capacity, int device, vdb_t **out);
 void vdb_destroy(vdb_t *db);
 
@@ -114,13 +116,18 @@ int vdb_merge_topk(const float *dist, const int64_t *ids, int G, size_t nq, int 
  *   merge  : d_dist/d_ids [nq,k] = this rank's lists (id < 0 = padding) -> o_dist/o_ids [slice,k] with
  *            slice = ceil(nq/G) (rank r owns queries [r*slice, min(nq,(r+1)*slice)); rows beyond what it owns
  *            are left untouched), enqueued on `stream`.  Collective: every rank must call it once per step with the same nq and k; one step in
- *            flight per rank; nothing else may keep the GPU's SMs busy while it waits for its peers. */
+ *            flight per rank.  The kernel is launched cooperatively (its whole grid is placed at once), so other work
+ *            on the same GPU -- searches on other streams -- can delay but not deadlock it. */
 typedef struct vdb_xchg vdb_xchg_t;
 int vdb_xchg_create(int device, int rank, int world, size_t max_slice, int max_k, vdb_xchg_t **out,
                     unsigned char *handle64);
 int vdb_xchg_connect(vdb_xchg_t *x, const unsigned char *handles /* world * 64 bytes */);
 int vdb_xchg_merge_dev(vdb_xchg_t *x, const float *d_dist, const int64_t *d_ids, size_t nq, int k,
                        float *o_dist, int64_t *o_ids, void *stream);
+/* 0, or VDB_ECUDA once a step has failed: a peer did not arrive within the timeout (30 s; VDB_XCHG_TIMEOUT_MS),
+ * or arrived with another (nq, k) / step.  The failing step's outputs are padding (-1 / +inf); the exchange stays
+ * failed (vdb_xchg_merge_dev returns the same error).  Read it after synchronising the stream of the step. */
+int vdb_xchg_status(vdb_xchg_t *x);
 void vdb_xchg_destroy(vdb_xchg_t *x);
 
 /* Introspection for bench.py / tests */

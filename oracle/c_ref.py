@@ -33,6 +33,8 @@ def lib():
         L.oracle_normalize.argtypes = [fp, C.c_size_t, C.c_int, fp]
         L.oracle_synth_rows.argtypes = [C.c_uint64, C.c_uint64, C.c_size_t, C.c_int, fp]
         L.oracle_num_threads.restype = C.c_int
+        L.oracle_set_threads.argtypes = [C.c_int]
+        L.oracle_round_f16.argtypes = [fp, C.c_size_t]
         _lib = L
     return _lib
 
@@ -85,6 +87,26 @@ def knn(queries: np.ndarray, stored: np.ndarray, labels, k: int, metric: str, de
     if rc != 0:
         raise RuntimeError(f"oracle_knn failed rc={rc}")
     return out_l, out_d, cnt
+
+
+def set_threads(n: int) -> None:
+    """Thread count of every OpenMP region of the C oracle (overrides an inherited OMP_NUM_THREADS)."""
+    lib().oracle_set_threads(int(n))
+
+
+def host_cores() -> int:
+    """Cores this process may run on (the CPU baseline states this number)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def round_f16_(x: np.ndarray) -> np.ndarray:
+    """In place fp32 -> fp16 -> fp32 (what an fp16-stored shard holds)."""
+    assert x.dtype == np.float32 and x.flags.c_contiguous
+    lib().oracle_round_f16(_p(x, C.c_float), x.size)
+    return x
 
 
 def num_threads() -> int:

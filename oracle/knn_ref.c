@@ -207,6 +207,23 @@ int oracle_knn(const float *queries, size_t nq, const float *rows, const int64_t
     return 0;
 }
 
+/* OpenMP thread count for every function of this file (torchrun exports OMP_NUM_THREADS=1 to its workers:
+ * a CPU baseline timed there must ask for the host's cores explicitly). */
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+/* In place: fp32 -> fp16 (round to nearest even) -> fp32, the value an fp16-stored shard holds
+ * (same as numpy's astype(float16).astype(float32)). */
+void oracle_round_f16(float *x, size_t n) {
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)n; ++i) x[i] = (float)(_Float16)x[i];
+}
+
 int oracle_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -28,12 +28,20 @@ CASES = [  # name, metric, dim, store, n, nq, k, scale, n_deleted
     ("ip_768_f16", "ip", 768, "f16", 2000, 4, 10, 1.0, 0),
     ("l2_100_odd", "l2", 100, "f32", 777, 3, 7, 1.0, 5),
     ("cos_tiny", "cosine", 512, "f32", 7, 2, 10, 1.0, 0),
+    # the widest rows the shard accepts, ALL-POSITIVE components (scale < 0 means |row| * |scale|): every product of
+    # the contraction has the same sign, the worst case for the accumulation term of the tensor path's error bound
+    ("ip_1408_pos", "ip", 1408, "f32", 1500, 9, 10, -1.0, 0),
+    ("l2_1408_pos", "l2", 1408, "f32", 1500, 9, 10, -1.3, 0),
+    ("cos_1024_pos_k100", "cosine", 1024, "f32", 1500, 5, 100, -1.0, 10),
+    ("ip_2816_f16_pos", "ip", 2816, "f16", 1200, 9, 10, -1.0, 0),
 ]
 
 
 def case_inputs(metric, dim, store, n, nq, scale, n_del):
-    raw = R.synth_rows(R.SEED_DB, 0, n, dim) * np.float32(scale)
+    raw = R.synth_rows(R.SEED_DB, 0, n, dim) * np.float32(abs(scale))
     q = R.synth_rows(R.SEED_QUERY, 0, nq, dim) * np.float32(0.9)
+    if scale < 0:
+        raw, q = np.abs(raw), np.abs(q)
     deleted = list(range(3, 3 + 2 * n_del, 2))
     return raw, q, deleted
 

@@ -234,3 +234,172 @@ def test_sharded_index_client_api(exchange):
                 msg = R.check_topk(ids[i], dd[i], q[lo + i], stored, np.arange(n), k, "cosine", rtol=1e-5)
                 assert msg is None, f"{exchange} nq {nq} rank {r} query {lo + i}: {msg}"
         assert covered == list(range(nq))            # every query answered by exactly one rank
+
+
+# ---------------------------------------------------------------------------------------------
+# robustness: several devices in one process, K5x next to other work, K5x when a peer misbehaves
+# ---------------------------------------------------------------------------------------------
+def test_two_indexes_on_two_devices_in_one_process(vdb):
+    """LocalCoordinator's documented use: one handler (index) per GPU inside ONE process.  Every kernel's
+    per-device launch configuration (dynamic shared memory opt-in) must be made on both devices: scan path,
+    tensor path, merge."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    n, dim, k = 6000, 512, 10
+    raw = R.synth_rows(R.SEED_DB, 0, n, dim)
+    stored = R.prepare_rows(raw, "cosine")
+    ixs = []
+    for d in (0, 1):
+        ix = vdb.Index("cosine", dim, device=d)
+        ix.init_index(n)
+        ix.add_items(raw, np.arange(n))
+        ixs.append(ix)
+    for nq in (1, 40):                                  # scan kernel, then the tensor path, on device 0 THEN 1
+        q = R.synth_rows(R.SEED_QUERY, 5 * nq, nq, dim)
+        for d, ix in enumerate(ixs):
+            labels, dd, cnt = ix.knn_query_padded(q, k)
+            for i in range(nq):
+                msg = R.check_topk(labels[i], dd[i], q[i], stored, np.arange(n), k, "cosine", rtol=1e-5)
+                assert msg is None, f"device {d} nq {nq} query {i}: {msg}"
+    assert all(ix.get_stat("tensor_batches") == 1 and ix.get_stat("fallback_queries") == 0 for ix in ixs)
+    for ix in ixs:
+        ix.close()
+
+
+def _worker_concurrent(rank, world, port, n, dim, nq, k, out):
+    """K5x while another stream of the same GPU runs searches back to back: the cooperative launch may be delayed
+    by them but must complete, with the right answer."""
+    import threading
+    import torch
+    import torch.distributed as dist
+    import dvdb_b200 as vdb
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        lo, hi = vdb.sharding.contiguous_range(n, rank, world)
+        ix = vdb.Index("cosine", dim, device=rank)
+        ix.init_index(hi - lo)
+        ix.add_items(R.synth_rows(R.SEED_DB, lo, hi - lo, dim), np.arange(lo, hi))
+        sx = vdb.ShardedIndex(ix, max_batch=nq, max_k=k, exchange="p2p")
+        stop = threading.Event()
+        noise_q = R.synth_rows(R.SEED_QUERY, 999, 300, dim)
+
+        def noise():                                    # host-buffer searches on the library's own streams
+            while not stop.is_set():
+                ix.knn_query_padded(noise_q, k)
+
+        t = threading.Thread(target=noise)
+        t.start()
+        res = []
+        try:
+            for step in range(6):
+                q = torch.from_numpy(R.synth_rows(R.SEED_QUERY, 100 * step, nq, dim)).to(dev)
+                dd, ids = sx.search_device(q, k)
+                torch.cuda.synchronize()
+                sx.px.status()
+                res.append((ids.cpu().numpy().copy(), dd.cpu().numpy().copy()))
+        finally:
+            stop.set()
+            t.join()
+        out.put((rank, res))
+        dist.barrier()
+        sx.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_exchange_with_a_concurrent_search_stream():
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    n, dim, nq, k, world = 20000, 512, 256, 10, 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_concurrent, args=(r, world, port, n, dim, nq, k, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(out.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    stored = R.prepare_rows(R.synth_rows(R.SEED_DB, 0, n, dim), "cosine")
+    sl = nq // world
+    for step in range(6):
+        q = R.synth_rows(R.SEED_QUERY, 100 * step, nq, dim)
+        for r in range(world):
+            ids, dd = got[r][step]
+            for i in range(0, sl, 7):
+                msg = R.check_topk(ids[i], dd[i], q[r * sl + i], stored, np.arange(n), k, "cosine", rtol=1e-5)
+                assert msg is None, f"step {step} rank {r} query {i}: {msg}"
+
+
+def _worker_misbehaving_peer(rank, world, port, mode, out):
+    """mode 'absent': rank 1 never launches its step; mode 'shape': rank 1 calls with another batch size.  Rank 0
+    must come back (bounded wait), report the failure and refuse further steps; nothing may hang."""
+    import torch
+    import torch.distributed as dist
+    os.environ["VDB_XCHG_TIMEOUT_MS"] = "1500"
+    import dvdb_b200 as vdb
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        def gather_handles(mine: bytes):
+            t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(dev)
+            o = torch.empty((world, 64), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(o, t)
+            return [bytes(o[r].cpu().numpy().tobytes()) for r in range(world)]
+
+        k, nq = 10, 8
+        px = vdb.PeerExchange(rank, rank, world, max_slice=8, max_k=k, exchange_handles=gather_handles)
+        stream = torch.cuda.current_stream().cuda_stream
+        my_nq = nq if (rank == 0 or mode != "shape") else nq + 2
+        ids = torch.arange(my_nq * k, dtype=torch.int64, device=dev).view(my_nq, k)
+        dd = torch.rand((my_nq, k), device=dev).sort(dim=1).values
+        o_ids = torch.zeros((8, k), dtype=torch.int64, device=dev)
+        o_dd = torch.zeros((8, k), dtype=torch.float32, device=dev)
+        verdict = "ok"
+        if not (mode == "absent" and rank == 1):
+            px.merge(dd.data_ptr(), ids.data_ptr(), my_nq, k, o_dd.data_ptr(), o_ids.data_ptr(), stream)
+            torch.cuda.synchronize()
+            try:
+                px.status()
+            except RuntimeError as e:
+                verdict = str(e)
+                assert (o_ids[: (my_nq + world - 1) // world].cpu().numpy() == -1).all()     # padded, not garbage
+                with pytest.raises(RuntimeError):                                             # and it stays failed
+                    px.merge(dd.data_ptr(), ids.data_ptr(), my_nq, k, o_dd.data_ptr(), o_ids.data_ptr(), stream)
+        out.put((rank, verdict))
+        dist.barrier()
+        px.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["absent", "shape"])
+def test_peer_exchange_reports_a_misbehaving_peer(mode):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_misbehaving_peer, args=(r, world, port, mode, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(out.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    if mode == "absent":
+        assert "timed out waiting for rank 1" in got[0] and got[1] == "ok"
+    else:
+        assert "differs from rank" in got[0] and "differs from rank" in got[1]

@@ -466,3 +466,57 @@ def test_concurrent_searches_and_a_writer_on_one_index(vdb):
     assert not errors, errors[:3]
     assert ix.get_current_count() == n1
     assert_parity(ix, raw, "cosine", "f32", qs, k)
+
+
+@pytest.mark.parametrize("metric,store,dim", [("ip", "f32", 1408), ("l2", "f32", 1408), ("cosine", "f32", 1152),
+                                              ("ip", "f16", 2816), ("l2", "f16", 1792)])
+def test_widest_rows_all_positive(vdb, metric, store, dim):
+    """The widest rows a shard accepts, every component positive: all `dim` products of the contraction share a
+    sign, the worst case for the accumulation term (dim * 2^-23) of the tensor path's error bound.  Both paths
+    must meet the parity bar, the scan in groups smaller than 8 queries where 8 no longer fit, and random data
+    must stay on the tensor path (certificates hold)."""
+    n, k = 12000, 10
+    ix = vdb.Index(metric, dim, store_dtype=store)
+    ix.init_index(n)
+    raw = np.abs(R.synth_rows(R.SEED_DB, 0, n, dim))
+    ix.add_items(raw, np.arange(n))
+    q = np.abs(R.synth_rows(R.SEED_QUERY, 0, 24, dim)) * np.float32(0.9)
+    ix.set_option("path", 2)
+    assert_parity(ix, raw, metric, store, q, k)
+    assert ix.get_stat("tensor_batches") == 1 and ix.get_stat("fallback_queries") == 0
+    ix.set_option("path", 1)
+    assert_parity(ix, raw, metric, store, q[:11], k)          # 11 queries: 8 + 3, or 4 + 4 + 3, ... by row length
+
+
+def test_dims_beyond_the_ring_are_refused(vdb):
+    for store, dim in (("f32", 1409), ("f16", 2817), ("f32", 8192)):
+        ix = vdb.Index("l2", dim, store_dtype=store)
+        with pytest.raises(RuntimeError, match="dim too large"):
+            ix.init_index(100)
+
+
+def test_device_call_then_host_call_share_a_workspace(vdb):
+    """vdb_search_dev returns its workspace to the pool while its kernels may still run on the caller's stream; a
+    host-buffer search that picks the same workspace must order itself after them (event wait), not overwrite the
+    scratch in flight."""
+    import torch
+    n, dim, k, nq = 200_000, 512, 10, 512
+    ix = vdb.Index("cosine", dim)
+    ix.init_index(n)
+    ix.add_synthetic(R.SEED_DB, 0, n)
+    dev = torch.device("cuda", 0)
+    q_np = R.synth_rows(R.SEED_QUERY, 0, nq, dim)
+    q2_np = R.synth_rows(R.SEED_QUERY, 5000, nq, dim)
+    want1 = ix.knn_query_padded(q_np, k)
+    want2 = ix.knn_query_padded(q2_np, k)
+    side = torch.cuda.Stream()
+    q = torch.from_numpy(q_np).to(dev)
+    ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    dd = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    for _ in range(5):
+        ix.search_device(q.data_ptr(), nq, k, ids.data_ptr(), dd.data_ptr(), 0, side.cuda_stream)   # async on `side`
+        got2 = ix.knn_query_padded(q2_np, k)                                                       # same workspace
+        side.synchronize()
+        assert np.array_equal(ids.cpu().numpy(), want1[0]) and np.array_equal(dd.cpu().numpy(), want1[1])
+        assert np.array_equal(got2[0], want2[0]) and np.array_equal(got2[1], want2[1])

@@ -276,9 +276,10 @@ def test_bench_reference_arm_prints_the_contract_line():
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the arm must still use every host core
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "2",
                           "--warmup", "1", "--rows", "20000", "--cpu-queries", "16"], capture_output=True, text=True,
-                         timeout=600, cwd=root)
+                         timeout=600, cwd=root, env=dict(os.environ, OMP_NUM_THREADS="1"))
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1                                   # ONE json line
@@ -289,7 +290,9 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["unit"] == "queries/s" and d["higher_is_better"] is True
     assert d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 1 and d["vs_baseline"] is None
     assert d["config"]["workload"].startswith("20000x512 f32 cosine top-10") and "model" not in d["config"]
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["sample"]
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert "brute-force" in d["config"]["note"]              # labelled for what it is: not the HNSW walk
     assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     # a rank other than 0 prints nothing and exits 0
@@ -297,3 +300,39 @@ def test_bench_reference_arm_prints_the_contract_line():
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"],
                          capture_output=True, text=True, timeout=120, cwd=root, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_bench_checkers_on_cpu():
+    """bench.py's parity helpers: the chunked whole-database oracle equals one exact scan, and compare_topk applies
+    the parity bar (ids identical, swaps only inside distance ties within 1e-5 relative)."""
+    import importlib.util
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    sys.modules["bench_mod"] = bench                         # dataclasses look the module up by name
+    spec.loader.exec_module(bench)
+    from oracle import c_ref
+    for metric, store in (("cosine", "f32"), ("l2", "f32"), ("ip", "f16")):
+        wl = bench.Workload("t", 3000, 96, 7, metric, store, 16)
+        q_idx = np.array([0, 3, 11])
+        ids, dd, info = bench.oracle_topk(wl, q_idx, budget_s=60.0, chunk=700)       # 5 ragged chunks
+        assert info["rows_scanned"] == 3000
+        stored = bench.stored_rows(c_ref, wl, 0, 3000)
+        q = np.concatenate([c_ref.synth_rows(bench.SEED_QUERY, int(i), 1, 96) for i in q_idx])
+        want_i, want_d, _ = c_ref.knn(q, stored, None, 7, metric)
+        assert np.array_equal(ids, want_i) and np.array_equal(dd.view(np.uint32), want_d.view(np.uint32))
+        assert np.array_equal(bench.oracle_distances_of(wl, q_idx, ids).view(np.uint32), want_d.view(np.uint32))
+        ok = bench.compare_topk(ids, dd, want_i, want_d)
+        assert ok["parity_ok"] and ok["recall_at_k"] == 1.0 and ok["ordered_ids_equal"] == 1.0
+    # a wrong id at a clear gap fails; a swap inside a tie passes; a distance off by 1e-4 fails
+    wi = np.array([[5, 9, 2]]); wd = np.array([[0.1, 0.2, 0.2000001]], dtype=np.float32)
+    assert not bench.compare_topk(np.array([[5, 9, 7]]), wd, wi, np.array([[0.1, 0.2, 0.3]], dtype=np.float32))["parity_ok"]
+    assert bench.compare_topk(np.array([[5, 2, 9]]), wd, wi, wd)["parity_ok"]
+    assert not bench.compare_topk(wi, wd + np.float32(1e-4), wi, wd)["parity_ok"]
+    # the workloads bench.py runs at 8 GPUs are BASELINE.json's configs 3 and 4 at full size
+    class A: configs = "auto"
+    w3, w4 = bench.extra_workloads(A, 8)
+    assert (w3.rows, w3.dim, w3.k, w3.metric, w3.store, w3.batch) == (10_000_000, 512, 100, "l2", "f32", 4096)
+    assert (w4.rows, w4.dim, w4.k, w4.metric, w4.store) == (100_000_000, 768, 10, "ip", "f16")
+    assert bench.extra_workloads(A, 4) == []
