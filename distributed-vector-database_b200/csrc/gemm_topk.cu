@@ -600,6 +600,19 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (warp == 2) tmem_dealloc(tmem_base, GT_TMEM_COLS);
 }
 
+// error model of the approximate values (approximate-value units: ||d||^2 - 2 q.d for L2, -q.d otherwise):
+// |approximate + offset - exact| <= eps for every row, offset = ||q||^2 (L2) / 1 (ip, cosine)
+struct EpsModel {
+    float eps_rel;            // bound on |approx dot - exact dot| / (||q|| ||d||)
+    float eps_abs;            // + eps_abs * (||q|| + ||d||max): fp16 subnormal rounding of single elements
+    int metric;               // 0 = L2, 1 = ip / cosine
+};
+// `at` = the value (offset included) whose magnitude scales the fp32 slack
+__device__ __forceinline__ float approx_eps(const EpsModel& m, float qn2, float dmax2, float at) {
+    const float eb = m.eps_rel * sqrtf(qn2) * sqrtf(dmax2) + m.eps_abs * (sqrtf(qn2) + sqrtf(dmax2));
+    return m.metric == 0 ? 2.0f * eb + 4e-7f * (qn2 + dmax2 + fabsf(at)) : eb + 4e-7f * (1.0f + fabsf(at));
+}
+
 // ------------------------------------------------------------------------------------------
 // K2s: per query, keep the KP best approximate keys of what the level collected; their KP-th value
 // is the next level's threshold.  Padding rows of the last tile and tombstoned rows are dropped here.
@@ -614,7 +627,86 @@ struct SelectParams {
     int np2;                  // keys the shared array sk[] holds (>= cap); kept[kp] lies behind it
     int min_rank;             // probe: with fewer live chunk minima than thr_rank, the largest of them serves if
                               // there are at least this many
+    // Tight thresholds: the published threshold is min(thr_rank-th best, a_k + margin * eps), a_k = the k-th best
+    // approximate value seen so far.  Any value is a VALID threshold (rows are only ever dropped at or above it);
+    // this one is the smallest that still lets the certificate of the re-rank pass: the k-th exact distance is
+    // <= a_k + offset + eps, the certificate asks for < threshold + offset - eps.  margin = 0: rank rule only.
+    int k; float margin;
+    const float* qn2; const unsigned int* max_sqnorm_bits;
+    EpsModel em;
 };
+
+// value bits of the `rank`-th smallest (1-based) of the n >= rank keys in sk[].  Radix select
+// from the highest byte in which the values differ: the bytes above it are common to all keys and would send every
+// atomicAdd of a pass to ONE histogram bin.  Stops as soon as the bin that holds the rank has a single key.
+__device__ __forceinline__ uint32_t block_kth_bits(const uint64_t* sk, int n, int rank, int* hist, uint32_t* sh) {
+    // sh[0] = min, sh[1] = max, sh[2] = prefix, sh[3] = rank, sh[4] = count in the chosen bin
+    const int tid = threadIdx.x, RW_THREADS = blockDim.x;
+    if (tid == 0) { sh[0] = 0xFFFFFFFFu; sh[1] = 0u; }
+    __syncthreads();
+    uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+    for (int i = tid; i < n; i += RW_THREADS) {
+        const uint32_t v = (uint32_t)(sk[i] >> 32);
+        lo = min(lo, v); hi = max(hi, v);
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((tid & 31) == 0) { atomicMin(&sh[0], lo); atomicMax(&sh[1], hi); }
+    __syncthreads();
+    lo = sh[0]; hi = sh[1];
+    if (lo == hi) return lo;
+    int shift = ((31 - __clz(lo ^ hi)) >> 3) << 3;          // byte of the highest differing bit
+    uint32_t mask = shift == 24 ? 0u : ~((1u << (shift + 8)) - 1u);
+    if (tid == 0) { sh[2] = lo & mask; sh[3] = (uint32_t)rank; sh[4] = 0u; }
+    for (; shift >= 0; shift -= 8) {
+        for (int i = tid; i < 256; i += RW_THREADS) hist[i] = 0;
+        __syncthreads();
+        const uint32_t prefix = sh[2];
+        for (int i = tid; i < n; i += RW_THREADS) {
+            const uint32_t v = (uint32_t)(sk[i] >> 32);
+            if ((v & mask) == prefix) atomicAdd(&hist[(v >> shift) & 255], 1);
+        }
+        __syncthreads();
+        if (tid < 32) {
+            int local[8], sum = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { local[i] = hist[tid * 8 + i]; sum += local[i]; }
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (tid >= o) incl += t;
+            }
+            const int excl = incl - sum;
+            const int r = (int)sh[3];
+            if (r > excl && r <= incl) {
+                int run = excl;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (r > run && r <= run + local[i]) {
+                        sh[2] = prefix | ((uint32_t)(tid * 8 + i) << shift);
+                        sh[3] = (uint32_t)(r - run);
+                        sh[4] = (uint32_t)local[i];
+                    }
+                    run += local[i];
+                }
+            }
+        }
+        mask |= 0xFFu << shift;
+        __syncthreads();
+        if (sh[4] == 1u && shift > 0) {            // one key left under this prefix: it is the answer
+            const uint32_t prefix1 = sh[2];
+            __syncthreads();
+            for (int i = tid; i < n; i += RW_THREADS) {
+                const uint32_t v = (uint32_t)(sk[i] >> 32);
+                if ((v & mask) == prefix1) sh[2] = v;
+            }
+            __syncthreads();
+            break;
+        }
+    }
+    return sh[2];
+}
 
 // Radix select on the 32 distance bits (4 passes of 8 bits): O(n) instead of a full sort.  Keys whose
 // distance bits equal the KP-th value are taken in arrival order until KP are kept.  Output unordered.
@@ -625,8 +717,17 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectParams p) {
     __shared__ int hist[256];
     __shared__ uint32_t s_prefix, s_rank, s_min, s_max;
     __shared__ int s_valid, s_c1, s_c2;
+    __shared__ uint32_t sh[8];
+    __shared__ uint32_t s_tr, s_ak;
     const size_t q = blockIdx.x;
     uint64_t* b = p.buf + q * (size_t)p.cap;
+    // threshold of the tight rule from the bits of a_k
+    auto tight_thr = [&](uint32_t ak_bits) -> float {
+        const float a = ordered_to_float(ak_bits);
+        const float off = p.em.metric == 0 ? p.qn2[q] : 1.0f;
+        const float t = a + p.margin * approx_eps(p.em, p.qn2[q], __uint_as_float(*p.max_sqnorm_bits), a + off);
+        return t == t ? t : __int_as_float(0x7f800000);          // NaN: no tightening
+    };
     int n = p.probe_cnt > 0 ? p.probe_cnt : p.cnt[q];
     if (n > p.cap) {
         if (threadIdx.x == 0) p.overflow[q] = 1;
@@ -727,13 +828,20 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectParams p) {
     }
     const uint32_t T = s_prefix;                  // distance bits of the want-th best key
     if (probe) {
-        if (threadIdx.x == 0) { p.cnt[q] = 0; p.thr[q] = ordered_to_float(T); }
+        float thr = ordered_to_float(T);
+        if (p.margin > 0.0f && n_valid >= p.k && p.k < want) {
+            // the k-th smallest chunk minimum bounds the k-th best probed row from above (sentinels sort last)
+            __syncthreads();
+            thr = fminf(thr, tight_thr(block_kth_bits(sk, n, p.k, hist, sh)));
+        }
+        if (threadIdx.x == 0) { p.cnt[q] = 0; p.thr[q] = thr; }
         return;
     }
     const int need_eq = (int)s_rank;              // how many keys with exactly these bits to keep
     const int n_less = p.kp - need_eq;
     uint64_t* kept = sk + p.np2;                  // [kp] behind the key array
-    const bool tighter = p.thr_rank < p.kp;
+    const bool tight = p.margin > 0.0f && p.k < p.kp;
+    const bool tighter = p.thr_rank < p.kp || tight;
     for (int i = threadIdx.x; i < n; i += THREADS) {
         const uint64_t key = sk[i];
         if (key == KEY_SENTINEL) continue;
@@ -762,7 +870,14 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectParams p) {
         const uint64_t key = kept[t];
         int rank = 0;
         for (int j = 0; j < p.kp; ++j) rank += kept[j] < key;
-        if (rank == p.thr_rank - 1) p.thr[q] = ordered_to_float((uint32_t)(key >> 32));
+        if (rank == p.thr_rank - 1) s_tr = (uint32_t)(key >> 32);
+        if (rank == p.k - 1) s_ak = (uint32_t)(key >> 32);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float thr = ordered_to_float(s_tr);
+        if (tight) thr = fminf(thr, tight_thr(s_ak));
+        p.thr[q] = thr;
     }
 }
 
@@ -780,8 +895,7 @@ struct RerankParams {
     const float* qn2;         // [nq]
     const unsigned int* max_sqnorm_bits;
     int k, metric;            // metric 0 = L2 (approx value = ||d||^2 - 2 q.d), 1 = ip/cos (approx value = -q.d)
-    float eps_rel;            // bound on |approx dot - exact dot| / (||q|| ||d||)
-    float eps_abs;            // + eps_abs * (||q|| + ||d||max): fp16 subnormal rounding of single elements
+    EpsModel em;              // error model of the approximate values
     int f16_range;            // operands were rounded to fp16: norms beyond its range void the certificate
     int64_t* out_ids; float* out_dist; int* out_counts;
     int* flags;               // [nq] 1 = certificate failed
@@ -862,14 +976,6 @@ __device__ __forceinline__ void exact_keys(const RerankParams& p, const float* q
     }
 }
 
-// error bound of the approximate values of query q (approximate-value units: ||d||^2 - 2 q.d for L2, -q.d otherwise):
-// |approximate + offset - exact| <= eps for every row, offset = ||q||^2 (L2) / 1 (ip, cosine); `at` = the value
-// (offset included) whose magnitude scales the fp32 slack
-__device__ __forceinline__ float approx_eps(const RerankParams& p, float qn2, float dmax2, float at) {
-    const float eb = p.eps_rel * sqrtf(qn2) * sqrtf(dmax2) + p.eps_abs * (sqrtf(qn2) + sqrtf(dmax2));
-    return p.metric == 0 ? 2.0f * eb + 4e-7f * (qn2 + dmax2 + fabsf(at)) : eb + 4e-7f * (1.0f + fabsf(at));
-}
-
 // ------------------------------------------------------------------------------------------
 // K4w: the re-rank straight from the level buffers -- no select after the last level, and only the candidates that can
 // still reach the exact top-k are re-ranked.
@@ -889,78 +995,6 @@ __device__ __forceinline__ float approx_eps(const RerankParams& p, float qn2, fl
 //   4. window = list keys at or below a_k + 2 eps
 //   5. exact distances, two rows in flight per warp   6. results written at their rank (by counting), certificate
 constexpr int RW_MAX_THREADS = 256;            // 128 threads per query for k' <= 64, 256 above
-
-// value bits of the `rank`-th smallest (1-based) of the n >= rank keys in sk[].  Radix select
-// from the highest byte in which the values differ: the bytes above it are common to all keys and would send every
-// atomicAdd of a pass to ONE histogram bin.  Stops as soon as the bin that holds the rank has a single key.
-__device__ __forceinline__ uint32_t block_kth_bits(const uint64_t* sk, int n, int rank, int* hist, uint32_t* sh) {
-    // sh[0] = min, sh[1] = max, sh[2] = prefix, sh[3] = rank, sh[4] = count in the chosen bin
-    const int tid = threadIdx.x, RW_THREADS = blockDim.x;
-    if (tid == 0) { sh[0] = 0xFFFFFFFFu; sh[1] = 0u; }
-    __syncthreads();
-    uint32_t lo = 0xFFFFFFFFu, hi = 0u;
-    for (int i = tid; i < n; i += RW_THREADS) {
-        const uint32_t v = (uint32_t)(sk[i] >> 32);
-        lo = min(lo, v); hi = max(hi, v);
-    }
-    lo = __reduce_min_sync(0xffffffffu, lo);
-    hi = __reduce_max_sync(0xffffffffu, hi);
-    if ((tid & 31) == 0) { atomicMin(&sh[0], lo); atomicMax(&sh[1], hi); }
-    __syncthreads();
-    lo = sh[0]; hi = sh[1];
-    if (lo == hi) return lo;
-    int shift = ((31 - __clz(lo ^ hi)) >> 3) << 3;          // byte of the highest differing bit
-    uint32_t mask = shift == 24 ? 0u : ~((1u << (shift + 8)) - 1u);
-    if (tid == 0) { sh[2] = lo & mask; sh[3] = (uint32_t)rank; sh[4] = 0u; }
-    for (; shift >= 0; shift -= 8) {
-        for (int i = tid; i < 256; i += RW_THREADS) hist[i] = 0;
-        __syncthreads();
-        const uint32_t prefix = sh[2];
-        for (int i = tid; i < n; i += RW_THREADS) {
-            const uint32_t v = (uint32_t)(sk[i] >> 32);
-            if ((v & mask) == prefix) atomicAdd(&hist[(v >> shift) & 255], 1);
-        }
-        __syncthreads();
-        if (tid < 32) {
-            int local[8], sum = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { local[i] = hist[tid * 8 + i]; sum += local[i]; }
-            int incl = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (tid >= o) incl += t;
-            }
-            const int excl = incl - sum;
-            const int r = (int)sh[3];
-            if (r > excl && r <= incl) {
-                int run = excl;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (r > run && r <= run + local[i]) {
-                        sh[2] = prefix | ((uint32_t)(tid * 8 + i) << shift);
-                        sh[3] = (uint32_t)(r - run);
-                        sh[4] = (uint32_t)local[i];
-                    }
-                    run += local[i];
-                }
-            }
-        }
-        mask |= 0xFFu << shift;
-        __syncthreads();
-        if (sh[4] == 1u && shift > 0) {            // one key left under this prefix: it is the answer
-            const uint32_t prefix1 = sh[2];
-            __syncthreads();
-            for (int i = tid; i < n; i += RW_THREADS) {
-                const uint32_t v = (uint32_t)(sk[i] >> 32);
-                if ((v & mask) == prefix1) sh[2] = v;
-            }
-            __syncthreads();
-            break;
-        }
-    }
-    return sh[2];
-}
 
 template <typename T>
 __global__ void __launch_bounds__(RW_MAX_THREADS) rerank_window_kernel(const RerankParams p, const int kp) {
@@ -993,7 +1027,7 @@ __global__ void __launch_bounds__(RW_MAX_THREADS) rerank_window_kernel(const Rer
     };
     if (tid == 0) {
         s_a1 = 0xFFFFFFFFu; s_m1 = 0; s_m = 0; s_kth = INF; s_have_kth = 0;
-        s_eps0 = approx_eps(p, qn2, dmax2, 0.0f);
+        s_eps0 = approx_eps(p.em, qn2, dmax2, 0.0f);
     }
     // ---- 0. the buffer; padding rows of the last tile and tombstoned rows drop out
     for (int i = tid; i < n; i += RW_THREADS) {
@@ -1085,7 +1119,7 @@ __global__ void __launch_bounds__(RW_MAX_THREADS) rerank_window_kernel(const Rer
         const float a_tau = p.tau[q];
         if (a_tau < INF) {                          // rows outside the buffer exist: prove they cannot matter
             const float tau = a_tau + off;
-            ok = ok && s_have_kth && s_kth < tau - approx_eps(p, qn2, dmax2, tau);
+            ok = ok && s_have_kth && s_kth < tau - approx_eps(p.em, qn2, dmax2, tau);
         }
         // an element above the fp16 range became +-inf in the operand plane (|x_i| <= ||x||): no bound holds
         if (p.f16_range && (qn2 >= 4.0e9f || dmax2 >= 4.0e9f)) ok = false;
@@ -1360,7 +1394,21 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
     gp.sqnorm = a.sqnorm; gp.thr = w->thr; gp.buf = w->buf; gp.cnt = w->cnt; gp.cap = cap; gp.tomb = a.tomb;
     const bool l2 = a.metric == 0;
 
+    // |approx dot - exact dot| <= eps_rel * ||q|| * ||d||  (+ eps_abs_unit * sqrt(dim) * (||q|| + ||d||) for fp16
+    // subnormal rounding).  fp16 shard: only the query is rounded (u = 2^-11 = 4.9e-4); shadow plane: query and
+    // row are rounded (2u + u^2 = 9.8e-4); tf32 operands are truncated to 10 mantissa bits (2 * 2^-10 = 1.95e-3).
+    // Accumulation term: the tensor core adds `dim` exact products in fp32; with truncating adds the partial sums
+    // drift by at most dim * 2^-23 * sum|q_i d_i| <= dim * 2^-23 * ||q|| ||d|| (6.1e-5 at dim 512, 1.7e-4 at 1408).
+    EpsModel em{};
+    {
+        const float eps_round = a.f16 ? 4.9e-4f : (a.shadow ? 9.8e-4f : 1.96e-3f);
+        em.eps_rel = eps_round + (float)a.dim * 1.1920929e-7f + 1.0e-4f;
+        em.eps_abs = g16 ? 3.0e-8f * sqrtf((float)a.dim) : 0.0f;     // 2^-25 per element, Cauchy-Schwarz over dim
+        em.metric = a.metric;
+    }
     SelectParams sp{};
+    sp.k = a.k; sp.qn2 = a.qn2; sp.max_sqnorm_bits = a.d_max_sqnorm_bits; sp.em = em;
+    { static const float m = [] { const char* e = getenv("VDB_TIGHT_MARGIN"); return e && *e ? (float)atof(e) : 2.5f; }(); sp.margin = m; }
     sp.buf = w->buf; sp.cnt = w->cnt; sp.cap = cap; sp.kp = kp; sp.thr = w->thr; sp.overflow = w->overflow;
     sp.tomb = a.tomb; sp.n_rows = a.n_rows;
     static bool sel_configured[MAX_DEVICES] = {};
@@ -1418,14 +1466,7 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
     rp.rows = a.rows; rp.row_bytes = (uint32_t)((size_t)a.ld * esz); rp.ld = a.ld;
     rp.labels = a.labels; rp.q = a.q; rp.qn2 = a.qn2; rp.max_sqnorm_bits = a.d_max_sqnorm_bits;
     rp.k = a.k; rp.metric = a.metric;
-    // |approx dot - exact dot| <= eps_rel * ||q|| * ||d||  (+ eps_abs_unit * sqrt(dim) * (||q|| + ||d||) for fp16
-    // subnormal rounding).  fp16 shard: only the query is rounded (u = 2^-11 = 4.9e-4); shadow plane: query and
-    // row are rounded (2u + u^2 = 9.8e-4); tf32 operands are truncated to 10 mantissa bits (2 * 2^-10 = 1.95e-3).
-    // Accumulation term: the tensor core adds `dim` exact products in fp32; with truncating adds the partial sums
-    // drift by at most dim * 2^-23 * sum|q_i d_i| <= dim * 2^-23 * ||q|| ||d|| (6.1e-5 at dim 512, 9.8e-4 at 8192).
-    const float eps_round = a.f16 ? 4.9e-4f : (a.shadow ? 9.8e-4f : 1.96e-3f);
-    rp.eps_rel = eps_round + (float)a.dim * 1.1920929e-7f + 1.0e-4f;
-    rp.eps_abs = g16 ? 3.0e-8f * sqrtf((float)a.dim) : 0.0f;     // 2^-25 per element, Cauchy-Schwarz over dim
+    rp.em = em;
     rp.f16_range = g16 ? 1 : 0;
     rp.out_ids = a.out_ids; rp.out_dist = a.out_dist; rp.out_counts = a.out_counts;
     rp.flags = w->flags; rp.n_flagged = w->n_flagged;

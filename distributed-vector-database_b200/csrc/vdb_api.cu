@@ -19,6 +19,7 @@
 #include "../../include/vdb.h"
 #include "common.cuh"
 #include "gemm_topk.h"
+#include "growbuf.h"
 #include "kernels.h"
 
 namespace vdbk {
@@ -97,12 +98,24 @@ cudaError_t grow_host(T*& p, size_t& cap, size_t need) {
 
 }  // namespace
 
+// Concurrency (SURVEY 8b "Threading"; reference: one RLock around everything, src/datanode/handler.py:23):
+//   * searches take `mu` SHARED and snapshot `count` (acquire): they read rows [0, count) only
+//   * writers (add / mark_deleted / get_rows / save / resize) serialise on `wmu` and ALSO take `mu` shared: an
+//     append fills rows at and above `count` -- which no search looks at -- and publishes the new count (release)
+//     once the insert kernels have completed; tombstone bits flip while searches run (a search sees the delete or
+//     it does not).  A search never waits for a writer and the other way round.
+//   * the slabs grow in place (growbuf.h): resize maps more memory behind the same base pointers.  Only when a
+//     slab's address reservation is exhausted (8x the initial capacity) is `mu` taken EXCLUSIVE to move to a
+//     larger reservation -- the one operation that makes searches wait.
 struct vdb {
     int dim = 0, ld = 0, metric = 0, dtype = 0, device = 0, num_sms = 148;
-    size_t capacity = 0;
+    std::atomic<size_t> capacity{0};
     std::atomic<size_t> count{0};
-    size_t live = 0;
-    void* rows = nullptr;
+    std::atomic<size_t> live{0};
+    size_t va_rows = 0;               // rows the address reservations hold
+    GrowBuf b_rows, b_shadow, b_sqnorm, b_labels, b_tomb;
+    size_t tomb_words_zeroed = 0;
+    void* rows = nullptr;             // == b_rows.ptr() etc.: stable while `mu` is held shared
     void* shadow = nullptr;           // fp16 copy of fp32 rows [capacity][ld16]: operand plane of the tensor path
     int ld16 = 0;
     float* sqnorm = nullptr;
@@ -113,12 +126,13 @@ struct vdb {
     uint32_t* d_idx = nullptr; size_t idx_cap = 0;
     cudaStream_t wstream = nullptr;   // writer stream
     mutable std::shared_mutex mu;
+    std::mutex wmu;                   // writers, one at a time (lock order: wmu, then mu)
     // label -> row
     bool affine = true;
     int64_t label_base = 0;
     std::unordered_map<int64_t, uint32_t> map;
-    std::vector<uint64_t> h_dead;     // host mirror of the tombstone bitmap
-    bool any_dead = false;
+    std::vector<uint64_t> h_dead;     // host mirror of the tombstone bitmap (writers only)
+    std::atomic<bool> any_dead{false};
     // workspaces
     std::mutex ws_mu;
     std::condition_variable ws_cv;
@@ -159,26 +173,64 @@ struct vdb {
 
 namespace {
 
+static size_t tomb_words_for(size_t cap) { return (cap + 31) / 32 + 4; }
+
+// Back every slab for `cap` rows (maps the missing tail; the prefix and the base pointers stay).  Caller holds wmu.
+int map_capacity(vdb* db, size_t cap) {
+    cap = std::max(cap, (size_t)1);
+    std::string err;
+    if (!db->b_rows.ensure(cap * db->row_bytes(), err) ||
+        (db->ld16 && !db->b_shadow.ensure(cap * (size_t)db->ld16 * 2, err)) ||
+        !db->b_sqnorm.ensure(cap * sizeof(float), err) || !db->b_labels.ensure(cap * sizeof(uint32_t), err) ||
+        !db->b_tomb.ensure(tomb_words_for(cap) * sizeof(uint32_t), err))
+        return fail(err.find("out of memory") != std::string::npos ? VDB_ENOMEM : VDB_ECUDA, err);
+    const size_t words = tomb_words_for(cap);
+    if (words > db->tomb_words_zeroed) {      // freshly mapped memory is not zero
+        CU_TRY(cudaMemsetAsync(db->tomb + db->tomb_words_zeroed, 0, (words - db->tomb_words_zeroed) * sizeof(uint32_t), db->wstream));
+        CU_TRY(cudaStreamSynchronize(db->wstream));
+        db->tomb_words_zeroed = words;
+    }
+    if (db->h_dead.size() < (cap + 63) / 64) db->h_dead.resize((cap + 63) / 64, 0);
+    return VDB_OK;
+}
+
+// Address reservations for `va_rows` rows per slab.  First call: reserves; later (reservation exhausted): moves the
+// mapped chunks to larger ranges -- the base pointers change, the caller holds `mu` exclusive and the device is idle.
+int reserve_rows(vdb* db, size_t va_rows) {
+    std::string err;
+    const bool first = db->rows == nullptr;
+    auto one = [&](GrowBuf& b, size_t bytes) { return first ? b.reserve(db->device, bytes, err) : b.rebase(bytes, err); };
+    if (!one(db->b_rows, va_rows * db->row_bytes()) || (db->ld16 && !one(db->b_shadow, va_rows * (size_t)db->ld16 * 2)) ||
+        !one(db->b_sqnorm, va_rows * sizeof(float)) || !one(db->b_labels, va_rows * sizeof(uint32_t)) ||
+        !one(db->b_tomb, tomb_words_for(va_rows) * sizeof(uint32_t)))
+        return fail(VDB_ECUDA, err);
+    db->va_rows = va_rows;
+    db->rows = db->b_rows.ptr();
+    db->shadow = db->ld16 ? db->b_shadow.ptr() : nullptr;
+    db->sqnorm = static_cast<float*>(db->b_sqnorm.ptr());
+    db->labels = static_cast<uint32_t*>(db->b_labels.ptr());
+    db->tomb = static_cast<uint32_t*>(db->b_tomb.ptr());
+    return VDB_OK;
+}
+
 int alloc_shard(vdb* db) {
     CU_TRY(cudaSetDevice(db->device));
-    const size_t cap = std::max(db->capacity, (size_t)1);
-    CU_TRY(cudaMalloc(&db->rows, cap * db->row_bytes()));
-    if (db->ld16) CU_TRY(cudaMalloc(&db->shadow, cap * (size_t)db->ld16 * 2));
-    CU_TRY(cudaMalloc((void**)&db->sqnorm, cap * sizeof(float)));
-    CU_TRY(cudaMalloc((void**)&db->labels, cap * sizeof(uint32_t)));
-    const size_t words = (cap + 31) / 32 + 4;
-    CU_TRY(cudaMalloc((void**)&db->tomb, words * sizeof(uint32_t)));
-    CU_TRY(cudaMemset(db->tomb, 0, words * sizeof(uint32_t)));
-    CU_TRY(cudaMalloc((void**)&db->d_max_sqnorm, sizeof(unsigned int)));
-    CU_TRY(cudaMemset(db->d_max_sqnorm, 0, sizeof(unsigned int)));
-    CU_TRY(cudaMalloc((void**)&db->d_stage, STAGE_ROWS * (size_t)db->dim * sizeof(float)));
-    CU_TRY(cudaStreamCreateWithFlags(&db->wstream, cudaStreamNonBlocking));
-    db->h_dead.assign((cap + 63) / 64, 0);
+    CU_TRY(cudaFree(nullptr));                                   // make sure the primary context exists and is current
     cudaDeviceProp prop;
     CU_TRY(cudaGetDeviceProperties(&prop, db->device));
     db->num_sms = prop.multiProcessorCount;
     if (prop.major != 10)
         return fail(VDB_ECUDA, std::string("this library is built for sm_100a (B200); device is ") + prop.name);
+    CU_TRY(cudaStreamCreateWithFlags(&db->wstream, cudaStreamNonBlocking));
+    const size_t cap = std::max(db->capacity.load(), (size_t)1);
+    // room to grow 8x in place (address space only; at least 1M rows so that small shards never re-reserve)
+    int rc = reserve_rows(db, std::max(cap * 8, (size_t)1 << 20));
+    if (rc) return rc;
+    rc = map_capacity(db, cap);
+    if (rc) return rc;
+    CU_TRY(cudaMalloc((void**)&db->d_max_sqnorm, sizeof(unsigned int)));
+    CU_TRY(cudaMemset(db->d_max_sqnorm, 0, sizeof(unsigned int)));
+    CU_TRY(cudaMalloc((void**)&db->d_stage, STAGE_ROWS * (size_t)db->dim * sizeof(float)));
     return VDB_OK;
 }
 
@@ -272,7 +324,7 @@ int scan_prepared(vdb* db, Workspace* ws, const float* d_qp, size_t nq, int k, i
     sp.ld = db->ld;
     sp.n_rows = (uint32_t)n;
     sp.labels = db->labels;
-    sp.tomb = db->any_dead ? db->tomb : nullptr;
+    sp.tomb = db->any_dead.load() ? db->tomb : nullptr;
     sp.k = k;
     sp.metric = db->metric == VDB_L2 ? 0 : 1;
     // every pass of this call uses the launch shape of the widest pass
@@ -370,7 +422,7 @@ int search_core(vdb* db, Workspace* ws, const float* d_q_raw, size_t nq, int k, 
         GemmSearchArgs a{};
         a.rows = db->rows; a.ld = db->ld; a.dim = db->dim; a.f16 = f16; a.n_rows = (uint32_t)n;
         if (db->shadow && db->opt_shadow.load()) { a.shadow = db->shadow; a.ld16 = db->ld16; }
-        a.sqnorm = db->sqnorm; a.labels = db->labels; a.tomb = db->any_dead ? db->tomb : nullptr;
+        a.sqnorm = db->sqnorm; a.labels = db->labels; a.tomb = db->any_dead.load() ? db->tomb : nullptr;
         a.q = ws->d_q; a.qn2 = ws->d_qn2; a.nq = nq; a.k = k;
         a.metric = db->metric == VDB_L2 ? 0 : 1;
         a.d_max_sqnorm_bits = db->d_max_sqnorm;
@@ -496,11 +548,7 @@ void vdb_destroy(vdb_t* db) {
     for (auto& ev : db->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto& ev : db->prof_pool) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     gemm_plan_free(db->gemm_plan);
-    if (db->rows) cudaFree(db->rows);
-    if (db->shadow) cudaFree(db->shadow);
-    if (db->sqnorm) cudaFree(db->sqnorm);
-    if (db->labels) cudaFree(db->labels);
-    if (db->tomb) cudaFree(db->tomb);
+    // the slabs (GrowBuf members) unmap and release themselves
     if (db->d_max_sqnorm) cudaFree(db->d_max_sqnorm);
     if (db->d_stage) cudaFree(db->d_stage);
     if (db->d_idx) cudaFree(db->d_idx);
@@ -509,15 +557,11 @@ void vdb_destroy(vdb_t* db) {
 }
 
 size_t vdb_count(const vdb_t* db) { return db ? db->count.load() : 0; }
-size_t vdb_live_count(const vdb_t* db) {
-    if (!db) return 0;
-    std::shared_lock<std::shared_mutex> lk(db->mu);
-    return db->live;
-}
-size_t vdb_capacity(const vdb_t* db) { return db ? db->capacity : 0; }
+size_t vdb_live_count(const vdb_t* db) { return db ? db->live.load() : 0; }
+size_t vdb_capacity(const vdb_t* db) { return db ? db->capacity.load() : 0; }
 int vdb_dim(const vdb_t* db) { return db ? db->dim : 0; }
 
-// caller holds the exclusive lock.  Tombstones rows on host mirror + device.
+// caller holds wmu.  Tombstones rows on host mirror + device (searches in flight see the old or the new bit).
 static int tombstone_rows(vdb* db, const std::vector<uint32_t>& rows, bool set) {
     if (rows.empty()) return VDB_OK;
     CU_TRY(grow(db->d_idx, db->idx_cap, rows.size()));
@@ -525,11 +569,11 @@ static int tombstone_rows(vdb* db, const std::vector<uint32_t>& rows, bool set) 
     CU_TRY(launch_set_bits(db->tomb, db->d_idx, rows.size(), set, db->wstream));
     CU_TRY(cudaStreamSynchronize(db->wstream));
     for (uint32_t r : rows) db->set_dead(r, set);
-    if (set) db->any_dead = true;
+    if (set) db->any_dead.store(true);
     return VDB_OK;
 }
 
-// caller holds the exclusive lock.  Registers labels for rows [row0, row0+n) and uploads them.
+// caller holds wmu.  Registers labels for rows [row0, row0+n) (not yet visible to searches) and uploads them.
 static int register_labels(vdb* db, const int64_t* labels, size_t n, size_t row0) {
     for (size_t i = 0; i < n; ++i)
         if (labels[i] < 0 || labels[i] > (int64_t)LABEL_MAX) return fail(VDB_EINVAL, "labels must lie in [0, 2^32-2]");
@@ -573,7 +617,7 @@ static int register_labels(vdb* db, const int64_t* labels, size_t n, size_t row0
         // rows killed inside this batch are not yet counted live
         int rc = tombstone_rows(db, kill, true);
         if (rc) return rc;
-        db->live -= kill.size();   // in-batch duplicates are compensated by the caller's += n
+        db->live.fetch_sub(kill.size());   // in-batch duplicates are compensated by the caller's += n
     }
     return VDB_OK;
 }
@@ -582,10 +626,11 @@ static int add_impl(vdb* db, const float* rows, bool rows_on_device, const int64
     if (!db) return fail(VDB_EINVAL, "db is null");
     if (n == 0) return VDB_OK;
     if (!rows || !labels) return fail(VDB_EINVAL, "rows/labels is null");
-    std::unique_lock<std::shared_mutex> lk(db->mu);
+    std::lock_guard<std::mutex> wlk(db->wmu);                 // one writer at a time ...
+    std::shared_lock<std::shared_mutex> lk(db->mu);           // ... next to any number of searches
     CU_TRY(cudaSetDevice(db->device));
     const size_t row0 = db->count.load();
-    if (row0 + n > db->capacity)
+    if (row0 + n > db->capacity.load())
         return fail(VDB_EFULL, "The number of elements exceeds the specified limit");   // hnswlib's message
     if (rows_on_device && user) CU_TRY(cudaStreamSynchronize(user));
     int rc = register_labels(db, labels, n, row0);
@@ -604,8 +649,8 @@ static int add_impl(vdb* db, const float* rows, bool rows_on_device, const int64
         if (!rows_on_device) CU_TRY(cudaStreamSynchronize(db->wstream));   // staging buffer is reused
     }
     CU_TRY(cudaStreamSynchronize(db->wstream));
-    db->live += n;
-    db->count.store(row0 + n);
+    db->live.fetch_add(n);
+    db->count.store(row0 + n, std::memory_order_release);     // the rows are complete: searches may see them
     return VDB_OK;
 }
 
@@ -623,10 +668,11 @@ int vdb_synth_dev(uint64_t seed, uint64_t row_start, size_t n, int dim, float* d
 int vdb_add_synthetic(vdb_t* db, uint64_t seed, uint64_t row_start, size_t n, int64_t label_start) {
     if (!db) return fail(VDB_EINVAL, "db is null");
     if (n == 0) return VDB_OK;
-    std::unique_lock<std::shared_mutex> lk(db->mu);
+    std::lock_guard<std::mutex> wlk(db->wmu);
+    std::shared_lock<std::shared_mutex> lk(db->mu);
     CU_TRY(cudaSetDevice(db->device));
     const size_t row0 = db->count.load();
-    if (row0 + n > db->capacity) return fail(VDB_EFULL, "The number of elements exceeds the specified limit");
+    if (row0 + n > db->capacity.load()) return fail(VDB_EFULL, "The number of elements exceeds the specified limit");
     if (label_start < 0 || label_start + (int64_t)n - 1 > (int64_t)LABEL_MAX) return fail(VDB_EINVAL, "labels must lie in [0, 2^32-2]");
     // labels are label_start + i: keep the affine map when possible, else fall back to the generic path
     const bool keeps_affine = db->affine && (row0 == 0 || label_start == db->label_base + (int64_t)row0);
@@ -648,8 +694,8 @@ int vdb_add_synthetic(vdb_t* db, uint64_t seed, uint64_t row_start, size_t n, in
             CU_TRY(launch_shadow_rows((const float*)db->rows, db->ld, db->shadow, db->ld16, row0 + off, m, db->wstream));
     }
     CU_TRY(cudaStreamSynchronize(db->wstream));
-    db->live += n;
-    db->count.store(row0 + n);
+    db->live.fetch_add(n);
+    db->count.store(row0 + n, std::memory_order_release);
     return VDB_OK;
 }
 
@@ -657,7 +703,8 @@ static int mark_impl(vdb* db, const int64_t* labels, size_t n, bool set) {
     if (!db) return fail(VDB_EINVAL, "db is null");
     if (n == 0) return VDB_OK;
     if (!labels) return fail(VDB_EINVAL, "labels is null");
-    std::unique_lock<std::shared_mutex> lk(db->mu);
+    std::lock_guard<std::mutex> wlk(db->wmu);
+    std::shared_lock<std::shared_mutex> lk(db->mu);
     CU_TRY(cudaSetDevice(db->device));
     std::vector<uint32_t> rows;
     rows.reserve(n);
@@ -670,8 +717,8 @@ static int mark_impl(vdb* db, const int64_t* labels, size_t n, bool set) {
     rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
     int rc = tombstone_rows(db, rows, set);
     if (rc) return rc;
-    if (set) db->live -= rows.size();
-    else db->live += rows.size();
+    if (set) db->live.fetch_sub(rows.size());
+    else db->live.fetch_add(rows.size());
     return VDB_OK;
 }
 int vdb_mark_deleted(vdb_t* db, const int64_t* labels, size_t n) { return mark_impl(db, labels, n, true); }
@@ -685,7 +732,7 @@ int vdb_search(vdb_t* db, const float* queries, size_t nq, int k, int64_t* out_l
     if (rc) return rc;
     std::shared_lock<std::shared_mutex> lk(db->mu);
     CU_TRY(cudaSetDevice(db->device));
-    const size_t n = db->count.load();
+    const size_t n = db->count.load(std::memory_order_acquire);     // snapshot: rows appended later are not looked at
     Workspace* ws = acquire_ws(db);
     if (!ws) return fail(VDB_ECUDA, "cannot create a search workspace (stream)");
     WsGuard guard{db, ws};
@@ -764,7 +811,7 @@ int vdb_search_dev(vdb_t* db, const float* d_queries, size_t nq, int k, int64_t*
     if (rc) return rc;
     std::shared_lock<std::shared_mutex> lk(db->mu);
     CU_TRY(cudaSetDevice(db->device));
-    const size_t n = db->count.load();
+    const size_t n = db->count.load(std::memory_order_acquire);
     Workspace* ws = acquire_ws(db);
     if (!ws) return fail(VDB_ECUDA, "cannot create a search workspace (stream)");
     WsGuard guard{db, ws};
@@ -779,35 +826,24 @@ int vdb_search_dev(vdb_t* db, const float* d_queries, size_t nq, int k, int64_t*
 
 int vdb_resize(vdb_t* db, size_t new_capacity) {
     if (!db) return fail(VDB_EINVAL, "db is null");
-    std::unique_lock<std::shared_mutex> lk(db->mu);
-    CU_TRY(cudaSetDevice(db->device));
-    CU_TRY(cudaDeviceSynchronize());
-    const size_t n = db->count.load();
-    if (new_capacity < n) return fail(VDB_EINVAL, "new capacity below current count");
+    std::lock_guard<std::mutex> wlk(db->wmu);
+    if (new_capacity < db->count.load()) return fail(VDB_EINVAL, "new capacity below current count");
     if (new_capacity >= 0xFFFFFFF0ull) return fail(VDB_EINVAL, "capacity must be below 2^32 rows per shard");
-    const size_t cap = std::max(new_capacity, (size_t)1);
-    void* rows = nullptr; float* sq = nullptr; uint32_t* lab = nullptr; uint32_t* tomb = nullptr;
-    const size_t words = (cap + 31) / 32 + 4, old_words = (db->capacity + 31) / 32;
-    CU_TRY(cudaMalloc(&rows, cap * db->row_bytes()));
-    CU_TRY(cudaMalloc((void**)&sq, cap * sizeof(float)));
-    CU_TRY(cudaMalloc((void**)&lab, cap * sizeof(uint32_t)));
-    CU_TRY(cudaMalloc((void**)&tomb, words * sizeof(uint32_t)));
-    CU_TRY(cudaMemset(tomb, 0, words * sizeof(uint32_t)));
-    CU_TRY(cudaMemcpy(rows, db->rows, n * db->row_bytes(), cudaMemcpyDeviceToDevice));
-    if (db->shadow) {
-        void* shadow = nullptr;
-        CU_TRY(cudaMalloc(&shadow, cap * (size_t)db->ld16 * 2));
-        CU_TRY(cudaMemcpy(shadow, db->shadow, n * (size_t)db->ld16 * 2, cudaMemcpyDeviceToDevice));
-        cudaFree(db->shadow);
-        db->shadow = shadow;
+    if (new_capacity > db->va_rows) {
+        // the address reservations are exhausted: move the mapped chunks to larger ranges (no copy).  The base
+        // pointers change, so this one step keeps searches out and waits for the device.
+        std::unique_lock<std::shared_mutex> lk(db->mu);
+        CU_TRY(cudaSetDevice(db->device));
+        CU_TRY(cudaDeviceSynchronize());
+        int rc = reserve_rows(db, std::max(new_capacity, db->va_rows * 8));
+        if (rc) return rc;
     }
-    CU_TRY(cudaMemcpy(sq, db->sqnorm, n * sizeof(float), cudaMemcpyDeviceToDevice));
-    CU_TRY(cudaMemcpy(lab, db->labels, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
-    CU_TRY(cudaMemcpy(tomb, db->tomb, std::min(words, old_words) * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
-    cudaFree(db->rows); cudaFree(db->sqnorm); cudaFree(db->labels); cudaFree(db->tomb);
-    db->rows = rows; db->sqnorm = sq; db->labels = lab; db->tomb = tomb;
-    db->capacity = new_capacity;
-    db->h_dead.resize((cap + 63) / 64, 0);
+    // growing maps more physical memory behind the same pointers: searches keep running
+    std::shared_lock<std::shared_mutex> lk(db->mu);
+    CU_TRY(cudaSetDevice(db->device));
+    int rc = map_capacity(db, new_capacity);
+    if (rc) return rc;
+    db->capacity.store(new_capacity);      // shrinking (>= count) lowers the limit; the memory stays mapped
     return VDB_OK;
 }
 
@@ -815,7 +851,8 @@ int vdb_get_rows(vdb_t* db, const int64_t* labels, size_t n, float* out) {
     if (!db) return fail(VDB_EINVAL, "db is null");
     if (n == 0) return VDB_OK;
     if (!labels || !out) return fail(VDB_EINVAL, "null buffer");
-    std::unique_lock<std::shared_mutex> lk(db->mu);   // uses the writer stream + d_idx
+    std::lock_guard<std::mutex> wlk(db->wmu);          // uses the writer stream + d_idx + the label map
+    std::shared_lock<std::shared_mutex> lk(db->mu);
     CU_TRY(cudaSetDevice(db->device));
     std::vector<uint32_t> rows(n);
     for (size_t i = 0; i < n; ++i) {
@@ -846,9 +883,10 @@ struct SnapHeader {
 
 int vdb_save(vdb_t* db, const char* path) {
     if (!db || !path) return fail(VDB_EINVAL, "null argument");
-    std::unique_lock<std::shared_mutex> lk(db->mu);
+    std::lock_guard<std::mutex> wlk(db->wmu);          // no writer changes the shard while it is read out;
+    std::shared_lock<std::shared_mutex> lk(db->mu);    // searches carry on
     CU_TRY(cudaSetDevice(db->device));
-    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaStreamSynchronize(db->wstream));
     const size_t n = db->count.load();
     std::string tmp = std::string(path) + ".tmp";
     FILE* f = fopen(tmp.c_str(), "wb");
@@ -856,7 +894,7 @@ int vdb_save(vdb_t* db, const char* path) {
     SnapHeader h{};
     memcpy(h.magic, "VDBB200\0", 8);
     h.version = 1; h.dim = db->dim; h.ld = db->ld; h.metric = db->metric; h.dtype = db->dtype; h.affine = db->affine;
-    h.count = n; h.live = db->live; h.label_base = db->label_base;
+    h.count = n; h.live = db->live.load(); h.label_base = db->label_base;
     cudaMemcpy(&h.max_sqnorm_bits, db->d_max_sqnorm, 4, cudaMemcpyDeviceToHost);
     bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
     const size_t chunk_rows = std::max<size_t>(1, (64u << 20) / db->row_bytes());
@@ -919,7 +957,7 @@ int vdb_load(const char* path, size_t capacity, int device, vdb_t** out) {
             bool any = false;
             for (size_t r = 0; r < n; ++r)
                 if (db->dead(r)) { words[r >> 5] |= 1u << (r & 31); any = true; }
-            db->any_dead = any;
+            db->any_dead.store(any);
             ok = cudaMemcpy(db->tomb, words.data(), ((n + 31) / 32) * 4, cudaMemcpyHostToDevice) == cudaSuccess;
         }
     }
@@ -935,7 +973,7 @@ int vdb_load(const char* path, size_t capacity, int device, vdb_t** out) {
         }
     }
     db->label_base = h.label_base;
-    db->live = h.live;
+    db->live.store(h.live);
     db->count.store(n);
     *out = db;
     return VDB_OK;

@@ -7,8 +7,9 @@ What changes underneath:
 
  * `hnswlib.Index`  -> `index.Index` (exact search on the B200, tombstones masked in the scan, so
    the handler asks for `top_k` results instead of `2*top_k` and never runs short)
- * LevelDB JSON values + the O(N) id->key scan (handler.py:145-153) -> an in-memory key table with
-   O(1) id<->key maps, persisted as `kv.jsonl` inside checkpoints
+ * LevelDB JSON values + the O(N) id->key scan (handler.py:145-153) -> `kvstore.KeyStore`: O(1) id<->key
+   maps in memory, raw vectors and metadata in two append-only files under `leveldb_data/` (a checkpoint
+   records a position in them instead of copying the store)
  * `index.bin` is the flat GPU shard snapshot (vdb_save) instead of hnswlib's private format
  * the index is NOT rewritten to disk on every put (handler.py:302-304); durability comes from the
    WAL (group commit) + periodic checkpoints, as in the reference's own recovery path.
@@ -27,6 +28,7 @@ from typing import Callable, Dict, List, Optional
 import numpy as np
 
 from .sharding import VECTOR_DIM
+from .kvstore import KeyStore
 from .ttypes import Response, SearchRequest, SearchResult, VectorData
 from .wal import WALManager
 
@@ -124,12 +126,13 @@ class GpuVectorNodeHandler:
                  dim: int = VECTOR_DIM, max_elements: int = 1_000_000, store_dtype: str = "f32", device: int = 0,
                  checkpoint_every: int = 2000, reference_quirks: bool = False, fsync: bool = True,
                  index_factory: Optional[Callable] = None, micro_batch_wait_s: Optional[float] = None,
-                 micro_batch_max: int = 256):
+                 micro_batch_max: int = 256, keep_checkpoints: int = 2):
         self.node_id = node_id
         self.index_lock = threading.RLock()                      # handler.py:23
         self.space, self.vector_dim, self.store_dtype, self.device = space, dim, store_dtype, device
         self.max_elements = max_elements
         self.checkpoint_every = checkpoint_every                 # handler.py:316
+        self.keep_checkpoints = keep_checkpoints
         self.reference_quirks = reference_quirks
         self._factory = index_factory or _default_index_factory
         # directory layout of the reference (handler.py:27-36)
@@ -144,74 +147,102 @@ class GpuVectorNodeHandler:
         self.wal_manager = WALManager(self.wal_dir, node_id=str(node_id), fsync=fsync)
         self.next_hnsw_id = 0
         self.deleted_ids: set = set()
-        # key table: replaces LevelDB (key -> {hnsw_id, vector, metadata}) and gives id -> key in O(1)
-        self._by_key: Dict[str, dict] = {}
-        self._key_of_id: Dict[int, str] = {}
+        # key <-> id maps, raw vectors, metadata: replaces LevelDB (handler.py:288-297) and its O(N) reverse scan
+        self.store = KeyStore(self.leveldb_dir, dim, fsync=fsync)
         self.hnsw_index = self._factory(space, dim, max_elements, store_dtype, device)
-        # micro_batch_wait_s = None: every search is its own index query under the handler lock, as in the
-        # reference; a number (0 allowed): concurrent searches are coalesced (see _MicroBatcher)
+        # micro_batch_wait_s = None: every search is its own index query, as in the reference; a number (0 allowed):
+        # concurrent searches are coalesced (see _MicroBatcher)
         self._batcher = (None if micro_batch_wait_s is None else
                          _MicroBatcher(self._locked_query, micro_batch_max, micro_batch_wait_s))
         self.load_from_checkpoint()
 
     # ---- key table ---------------------------------------------------------------------------
     def _get_hnsw_id_by_key(self, key: str) -> int:               # handler.py:136-143
-        rec = self._by_key.get(key)
-        return -1 if rec is None else rec["hnsw_id"]
+        return self.store.id_of(key)
 
     def _get_key_by_hnsw_id(self, hnsw_id: int) -> str:           # handler.py:145-153, O(1) here
-        return self._key_of_id.get(hnsw_id, "")
+        return self.store.key_of(hnsw_id)
+
+    def stored_vector(self, hnsw_id: int) -> np.ndarray:
+        """The raw vector given at put time (WAL records of bulk inserts point here instead of carrying it)."""
+        return np.array(self.store.vector(int(hnsw_id)), dtype=np.float32)
 
     # ---- checkpoints (handler.py:156-219) ------------------------------------------------------
     def save_checkpoint(self) -> str:
+        """index.bin (flat shard snapshot) + leveldb_data/kv_pos.json (a POSITION in the append-only key store, not a
+        copy of it) + deleted_ids.json + wal_pos.txt (timestamp, as the reference) + wal_seq.txt (the exact record
+        number the checkpoint contains).  Older checkpoints beyond `keep_checkpoints` are removed."""
         with self.index_lock:
             ts = int(time.time() * 1000)
             path = os.path.join(self.checkpoint_dir, f"checkpoint_{ts}")
             while os.path.exists(path):
                 ts += 1
                 path = os.path.join(self.checkpoint_dir, f"checkpoint_{ts}")
-            os.makedirs(path)
-            self.hnsw_index.save_index(os.path.join(path, "index.bin"))
-            kv_dir = os.path.join(path, "leveldb_data")
+            tmp = path + ".tmp"
+            os.makedirs(tmp)
+            self.hnsw_index.save_index(os.path.join(tmp, "index.bin"))
+            self.store.flush()
+            kv_dir = os.path.join(tmp, "leveldb_data")
             os.makedirs(kv_dir, exist_ok=True)
-            with open(os.path.join(kv_dir, "kv.jsonl"), "w", encoding="utf-8") as f:
-                for key, rec in self._by_key.items():
-                    f.write(json.dumps({"key": key, **rec}, ensure_ascii=False) + "\n")
-            with open(os.path.join(path, "deleted_ids.json"), "w", encoding="utf-8") as f:
+            with open(os.path.join(kv_dir, "kv_pos.json"), "w", encoding="utf-8") as f:
+                json.dump(dict(self.store.position(), next_hnsw_id=self.next_hnsw_id), f)
+            with open(os.path.join(tmp, "deleted_ids.json"), "w", encoding="utf-8") as f:
                 json.dump(sorted(self.deleted_ids), f)
-            with open(os.path.join(path, "wal_pos.txt"), "w") as f:
+            with open(os.path.join(tmp, "wal_pos.txt"), "w") as f:
                 f.write(str(ts))
+            with open(os.path.join(tmp, "wal_seq.txt"), "w") as f:
+                f.write(str(self.wal_manager.last_seq))
+            os.rename(tmp, path)                                  # a checkpoint directory is complete or absent
+            if self.keep_checkpoints and self.keep_checkpoints > 0:
+                done = sorted(d for d in os.listdir(self.checkpoint_dir) if d.startswith("checkpoint_") and not d.endswith(".tmp"))
+                for old in done[:-self.keep_checkpoints]:
+                    shutil.rmtree(os.path.join(self.checkpoint_dir, old), ignore_errors=True)
             return path
 
     def load_from_checkpoint(self) -> None:
-        dirs = sorted(d for d in os.listdir(self.checkpoint_dir) if d.startswith("checkpoint_"))
+        dirs = sorted(d for d in os.listdir(self.checkpoint_dir) if d.startswith("checkpoint_") and not d.endswith(".tmp"))
         if not dirs:
-            self.wal_manager.replay(self)                         # no snapshot: full replay (wal_manager.py:116)
+            self.store.rollback({"log_bytes": 0})                 # no snapshot: full replay (wal_manager.py:116)
+            self.wal_manager.replay(self)
             return
         path = os.path.join(self.checkpoint_dir, dirs[-1])
         index_path = os.path.join(path, "index.bin")
         if os.path.exists(index_path):
             self.hnsw_index.load_index(index_path, max_elements=self.max_elements)     # handler.py:195
             self.next_hnsw_id = self.hnsw_index.get_current_count()
-        kv_path = os.path.join(path, "leveldb_data", "kv.jsonl")
-        self._by_key.clear()
-        self._key_of_id.clear()
-        if os.path.exists(kv_path):
-            with open(kv_path, "r", encoding="utf-8") as f:
-                for line in f:
-                    rec = json.loads(line)
-                    key = rec.pop("key")
-                    self._by_key[key] = rec
-                    self._key_of_id[rec["hnsw_id"]] = key
+        pos_path = os.path.join(path, "leveldb_data", "kv_pos.json")
+        if os.path.exists(pos_path):
+            with open(pos_path, "r", encoding="utf-8") as f:
+                self.store.rollback(json.load(f))                 # what came later is re-applied from the WAL
         del_path = os.path.join(path, "deleted_ids.json")
         if os.path.exists(del_path):
             with open(del_path, "r", encoding="utf-8") as f:
                 self.deleted_ids = set(json.load(f))
         with open(os.path.join(path, "wal_pos.txt"), "r") as f:
             checkpoint_ts = int(f.read())
-        self.wal_manager.replay_incremental(self, checkpoint_ts)  # handler.py:218
+        after_seq = None
+        seq_path = os.path.join(path, "wal_seq.txt")
+        if os.path.exists(seq_path):
+            with open(seq_path, "r") as f:
+                after_seq = int(f.read())
+        self.wal_manager.replay_incremental(self, checkpoint_ts, after_seq)  # handler.py:218
 
     # ---- put / delete (handler.py:222-342) -----------------------------------------------------
+    def _ensure_room(self, n_more: int) -> None:
+        """The reference rebuilds the graph without its tombstones when full (:240-251); a flat shard grows in
+        place instead (no copy, searches keep running)."""
+        need = self.hnsw_index.get_current_count() + n_more
+        cap = self.hnsw_index.get_max_elements()
+        if need > cap:
+            self.hnsw_index.resize_index(max(cap * 2, need, 1024))
+
+    def _log(self, fn, *args) -> None:
+        """A WAL failure is logged, not raised: the operation has been applied (reference handler.py:306-311)."""
+        try:
+            fn(*args)
+        except Exception as e:                                    # pragma: no cover - disk errors
+            print(f"[{self.node_id}] WAL write failed: {e!r}")
+
     def put(self, data: VectorData, replay_mode: bool = False) -> Response:
         key = data.key
         vec = np.array(data.vector, dtype=np.float32)                       # :224
@@ -219,72 +250,74 @@ class GpuVectorNodeHandler:
         if vec.ndim != 1 or vec.shape[0] != self.vector_dim:                # :228-232
             return Response(success=False, message=f"vector dim mismatch: expect {self.vector_dim}, got {vec.shape}")
         with self.index_lock:
-            if self.hnsw_index.get_current_count() >= self.hnsw_index.get_max_elements():
-                # the reference rebuilds the graph without its tombstones (:240-251); a flat shard grows instead
-                self.hnsw_index.resize_index(max(self.hnsw_index.get_max_elements() * 2, 1024))
-            old_id = self._get_hnsw_id_by_key(key)                          # :254-261
-            if old_id != -1:
-                self.deleted_ids.add(old_id)
-                self.hnsw_index.mark_deleted([old_id])
-                self._key_of_id.pop(old_id, None)
-                del self._by_key[key]
+            self._ensure_room(1)
             new_id = self.next_hnsw_id                                      # :264
             try:
                 self.hnsw_index.add_items(vec.reshape(1, -1), np.array([new_id], dtype=np.int64))
             except RuntimeError as e:                                       # :272
                 return Response(success=False, message=f"index add failed: {e}")
+            old_id = self._get_hnsw_id_by_key(key)                          # :254-261: overwrite = tombstone + append
+            if old_id != -1:                                                # (after the append: a failed add leaves
+                self.deleted_ids.add(old_id)                                #  the old version in place)
+                self.hnsw_index.mark_deleted([old_id])
             self.next_hnsw_id += 1                                          # :285
-            self._by_key[key] = {"hnsw_id": new_id, "vector": vec.tolist(), "metadata": metadata}   # :288-297
-            self._key_of_id[new_id] = key
+            self.store.put(new_id, key, vec, metadata)                      # :288-297
             if not replay_mode:
-                self.wal_manager.write_log("PUT", key, data.vector if isinstance(data.vector, list) else vec.tolist(), metadata)
+                self._log(self.wal_manager.write_log, "PUT", key,
+                          data.vector if isinstance(data.vector, list) else vec.tolist(), metadata)
                 if self.checkpoint_every and self.next_hnsw_id % self.checkpoint_every == 0:   # :316-317
                     self.save_checkpoint()
         return Response(success=True, message=f"key={key} 写入成功")
 
     def put_batch(self, items: List[VectorData]) -> Response:
-        """Insert path for bulk loads (config 5): one add_items call and one WAL group commit."""
+        """Insert path for bulk loads (config 5): ONE add_items call, one key-store append and one WAL group commit
+        (vectors logged by reference to the key store's raw-vector file, see wal.py)."""
         if not items:
             return Response(success=True, message="empty batch")
-        vecs = np.asarray([d.vector for d in items], dtype=np.float32)
-        if vecs.ndim != 2 or vecs.shape[1] != self.vector_dim:
+        return self.put_arrays([d.key for d in items], np.asarray([d.vector for d in items], dtype=np.float32),
+                               [d.metadata for d in items])
+
+    def put_arrays(self, keys: List[str], vecs: np.ndarray, metas: Optional[List[Optional[dict]]] = None) -> Response:
+        """`put_batch` without the per-item objects: keys [n], float32 [n, dim], optional metadata dicts."""
+        vecs = np.ascontiguousarray(vecs, dtype=np.float32)
+        n = len(keys)
+        if vecs.ndim != 2 or vecs.shape != (n, self.vector_dim):
             return Response(success=False, message=f"vector dim mismatch: expect {self.vector_dim}, got {vecs.shape}")
+        if n == 0:
+            return Response(success=True, message="empty batch")
+        metas = metas if metas is not None else [None] * n
         with self.index_lock:
-            need = self.hnsw_index.get_current_count() + len(items)
-            if need > self.hnsw_index.get_max_elements():
-                self.hnsw_index.resize_index(max(self.hnsw_index.get_max_elements() * 2, need))
-            dead = []
-            for d in items:                                               # overwrite = tombstone + append
-                old = self._get_hnsw_id_by_key(d.key)
-                if old != -1:
-                    dead.append(old)
-                    self._key_of_id.pop(old, None)
-                    del self._by_key[d.key]
-            ids = np.arange(self.next_hnsw_id, self.next_hnsw_id + len(items), dtype=np.int64)
-            # duplicates inside the batch: only the last occurrence stays live
-            last = {}
-            for i, d in enumerate(items):
-                if d.key in last:
-                    dead.append(int(ids[last[d.key]]))
-                last[d.key] = i
+            self._ensure_room(n)
+            first = self.next_hnsw_id
+            ids = np.arange(first, first + n, dtype=np.int64)
             try:
                 self.hnsw_index.add_items(vecs, ids)
-            except RuntimeError as e:
+            except RuntimeError as e:                                     # nothing else has been touched yet
                 return Response(success=False, message=f"index add failed: {e}")
+            # overwrite = tombstone + append; duplicates inside the batch: only the last occurrence stays live
+            dead, last = [], {}
+            for i, key in enumerate(keys):
+                old = self._get_hnsw_id_by_key(key)
+                if old != -1:
+                    dead.append(old)
+                if key in last:
+                    dead.append(first + last[key])
+                last[key] = i
             if dead:
+                dead = sorted(set(dead))
                 self.deleted_ids.update(dead)
                 self.hnsw_index.mark_deleted(dead)
-            for i, d in enumerate(items):
-                if last[d.key] != i:
-                    continue
-                self._by_key[d.key] = {"hnsw_id": int(ids[i]), "vector": vecs[i].tolist(), "metadata": d.metadata or {}}
-                self._key_of_id[int(ids[i])] = d.key
-            before = self.next_hnsw_id
-            self.next_hnsw_id += len(items)
-            self.wal_manager.write_batch(("PUT", d.key, vecs[i].tolist(), d.metadata or {}) for i, d in enumerate(items))
-            if self.checkpoint_every and before // self.checkpoint_every != self.next_hnsw_id // self.checkpoint_every:
+            self.next_hnsw_id += n
+            if len(last) == n:
+                self.store.put_batch(ids.tolist(), keys, vecs, metas)
+            else:
+                keep = sorted(last.values())
+                self.store.put_batch([first + i for i in keep], [keys[i] for i in keep], vecs[keep], [metas[i] for i in keep])
+            self._log(self.wal_manager.write_batch,
+                      [("PUT", keys[i], None, metas[i] or {}, None, first + i) for i in range(n)])
+            if self.checkpoint_every and first // self.checkpoint_every != self.next_hnsw_id // self.checkpoint_every:
                 self.save_checkpoint()
-        return Response(success=True, message=f"{len(items)} keys written")
+        return Response(success=True, message=f"{n} keys written")
 
     def delete(self, key: str, replay_mode: bool = False) -> Response:
         with self.index_lock:
@@ -293,34 +326,34 @@ class GpuVectorNodeHandler:
                 return Response(success=False, message=f"key={key}不存在")
             self.deleted_ids.add(hnsw_id)                                   # :332
             self.hnsw_index.mark_deleted([hnsw_id])
-            self._key_of_id.pop(hnsw_id, None)
-            del self._by_key[key]
+            self.store.delete(key)
             if not replay_mode:
-                self.wal_manager.write_log("DELETE", key)                   # :339
+                self._log(self.wal_manager.write_log, "DELETE", key)        # :339
         return Response(success=True, message=f"key={key}删除成功")
 
     # ---- search / get (handler.py:344-428) -------------------------------------------------------
     def _locked_query(self, queries: np.ndarray, k: int):
-        with self.index_lock:                                                        # writers stay out, as in :348
-            return self.hnsw_index.knn_query_padded(queries, min(k, max(self.hnsw_index.get_current_count(), 1)))
+        # The index is safe for concurrent searches next to one writer (searches snapshot the published row count),
+        # so the query itself runs OUTSIDE the handler lock: a put never waits for a search and the other way round.
+        return self.hnsw_index.knn_query_padded(queries, min(k, max(self.hnsw_index.get_current_count(), 1)))
 
     def search(self, req: SearchRequest) -> Response:
         query_vec = np.array(req.query_vector, dtype=np.float32).reshape(1, -1)     # :345
         top_k = req.top_k if req.top_k and req.top_k > 0 else 5                     # :346
         if self._batcher is not None:
             return self._search_coalesced(query_vec, top_k)
+        current_count = self.hnsw_index.get_current_count()
+        if current_count == 0:                                                       # :353-354
+            return Response(success=True, search_result=SearchResult(keys=[], scores=[], vectors=[]))
+        k = min(top_k, current_count)                                                # :357
+        if self.reference_quirks and 2 * k > current_count:
+            # hnswlib cannot fill k*2 results -> RuntimeError -> the reference answers this (:364-369)
+            return Response(success=False, message="HNSW index corrupted, search aborted")
+        try:
+            labels, distances, counts = self.hnsw_index.knn_query_padded(query_vec, k)
+        except RuntimeError:                                                         # :366
+            return Response(success=False, message="HNSW index corrupted, search aborted")
         with self.index_lock:
-            current_count = self.hnsw_index.get_current_count()
-            if current_count == 0:                                                   # :353-354
-                return Response(success=True, search_result=SearchResult(keys=[], scores=[], vectors=[]))
-            k = min(top_k, current_count)                                            # :357
-            if self.reference_quirks and 2 * k > current_count:
-                # hnswlib cannot fill k*2 results -> RuntimeError -> the reference answers this (:364-369)
-                return Response(success=False, message="HNSW index corrupted, search aborted")
-            try:
-                labels, distances, counts = self.hnsw_index.knn_query_padded(query_vec, k)
-            except RuntimeError:                                                     # :366
-                return Response(success=False, message="HNSW index corrupted, search aborted")
             return self._search_response(labels[0], distances[0], int(counts[0]), top_k)
 
     def _search_response(self, labels, distances, count: int, top_k: int) -> Response:
@@ -333,22 +366,19 @@ class GpuVectorNodeHandler:
             key = self._get_key_by_hnsw_id(hnsw_id)                                  # :382
             if not key:
                 continue
-            rec = self._by_key.get(key)                                              # :387
-            if rec is None:
-                continue
             keys.append(key)
-            vectors.append(VectorData(key=key, vector=rec["vector"], metadata=rec["metadata"]))   # :398
+            vectors.append(VectorData(key=key, vector=self.store.vector(hnsw_id).tolist(),
+                                      metadata=self.store.metadata(hnsw_id)))        # :387-398
             scores.append(float(distances[i]))                                       # :393
             if len(keys) >= top_k:                                                   # :402
                 break
         return Response(success=True, search_result=SearchResult(keys=keys, scores=scores, vectors=vectors))
 
     def _search_coalesced(self, query_vec: np.ndarray, top_k: int) -> Response:
-        """`search` with concurrent requests sharing one index query.  The handler lock is held by the batch
-        leader during the query and again for the key lookups of each request; a put/delete that lands between
-        the two can only remove a label from this request's answer (the lookups skip it)."""
-        with self.index_lock:
-            current_count = self.hnsw_index.get_current_count()
+        """`search` with concurrent requests sharing one index query.  The handler lock is taken only for the key
+        lookups of each request; a put/delete that lands between the query and the lookups can only remove a label
+        from this request's answer (the lookups skip it)."""
+        current_count = self.hnsw_index.get_current_count()
         if current_count == 0:
             return Response(success=True, search_result=SearchResult(keys=[], scores=[], vectors=[]))
         k = min(top_k, current_count)
@@ -361,38 +391,59 @@ class GpuVectorNodeHandler:
         with self.index_lock:
             return self._search_response(labels, distances, count, top_k)
 
+    def search_ids(self, queries, top_k: int):
+        """Array form of `search` for co-located coordinators (coordinator.LocalCoordinator.search_batch): queries
+        float32 [nq, dim] -> (labels int64 [nq, k] (-1 padded), distances float32 [nq, k] (+inf padded)) with
+        k = top_k.  Tombstones are masked on the GPU; ids map to keys with `keys_of`."""
+        q = np.ascontiguousarray(np.asarray(queries, dtype=np.float32))
+        k = int(top_k) if top_k and top_k > 0 else 5
+        nq = len(q)
+        count = self.hnsw_index.get_current_count()
+        if count == 0 or nq == 0:
+            return np.full((nq, k), -1, dtype=np.int64), np.full((nq, k), np.inf, dtype=np.float32)
+        kk = min(k, count)
+        labels, distances, _ = self.hnsw_index.knn_query_padded(q, kk)
+        if kk < k:
+            labels = np.concatenate([labels, np.full((nq, k - kk), -1, dtype=np.int64)], axis=1)
+            distances = np.concatenate([distances, np.full((nq, k - kk), np.inf, dtype=np.float32)], axis=1)
+        return labels, distances
+
+    def keys_of(self, labels) -> List[str]:
+        """ids -> keys ('' for padding / ids deleted since the query)."""
+        with self.index_lock:
+            return [self.store.key_of(int(h)) if h >= 0 and int(h) not in self.deleted_ids else "" for h in labels]
+
     def search_batch(self, queries, top_k: int):
         """Additive (the IDL has one query per SearchRequest, vector_db.thrift:23-28): many queries in one
         call so the tensor-core path is used.  Returns (keys[nq][<=k], scores[nq][<=k])."""
         q = np.asarray(queries, dtype=np.float32)
+        labels, distances = self.search_ids(q, top_k)
+        out_k, out_s = [], []
         with self.index_lock:
-            if self.hnsw_index.get_current_count() == 0:
-                return [[] for _ in range(len(q))], [[] for _ in range(len(q))]
-            k = min(top_k if top_k > 0 else 5, self.hnsw_index.get_current_count())
-            labels, distances, counts = self.hnsw_index.knn_query_padded(q, k)
-            out_k, out_s = [], []
             for r in range(len(q)):
                 ks, ss = [], []
-                for i in range(int(counts[r])):
-                    key = self._key_of_id.get(int(labels[r][i]), "")
+                for h, d in zip(labels[r].tolist(), distances[r].tolist()):
+                    key = self.store.key_of(h) if h >= 0 and h not in self.deleted_ids else ""
                     if key:
                         ks.append(key)
-                        ss.append(float(distances[r][i]))
+                        ss.append(float(d))
                 out_k.append(ks)
                 out_s.append(ss)
-            return out_k, out_s
+        return out_k, out_s
 
     def get(self, key: str) -> Response:                                             # :411-428
         with self.index_lock:
-            rec = self._by_key.get(key)
-            if rec is None:
+            hid = self.store.id_of(key)
+            if hid == -1:
                 return Response(success=False, message=f"key={key}不存在")
-            if rec["hnsw_id"] in self.deleted_ids:
+            if hid in self.deleted_ids:
                 return Response(success=False, message=f"key={key}已被删除")
-            return Response(success=True, vector_data=VectorData(key=key, vector=rec["vector"], metadata=rec["metadata"]))
+            return Response(success=True, vector_data=VectorData(key=key, vector=self.store.vector(hid).tolist(),
+                                                                 metadata=self.store.metadata(hid)))
 
     def close(self) -> None:                                                         # _on_exit, :61-72
         with self.index_lock:
             self.save_checkpoint()
+            self.store.close()
             if hasattr(self.hnsw_index, "close"):
                 self.hnsw_index.close()

@@ -41,8 +41,11 @@ def test_wal_layout_and_record_format(vdb, tmp_path):
     lines = open(tmp_path / "wal" / "data" / files[0], encoding="utf-8").read().splitlines()
     assert len(lines) == 2                                   # a real append: the reference's rename keeps only the last line
     rec = json.loads(lines[0])
-    assert list(rec) == ["op_type", "key", "vector", "metadata", "timestamp", "node_id"]
-    assert rec == {"op_type": "PUT", "key": "a", "vector": [0.5, 0.25], "metadata": {"tag": "t"}, "timestamp": 1000, "node_id": "node_1"}
+    # the reference's six fields in its order (wal_manager.py:91-98), then the additive sequence number
+    assert list(rec) == ["op_type", "key", "vector", "metadata", "timestamp", "node_id", "seq"]
+    assert rec == {"op_type": "PUT", "key": "a", "vector": [0.5, 0.25], "metadata": {"tag": "t"}, "timestamp": 1000,
+                   "node_id": "node_1", "seq": 1}
+    assert json.loads(lines[1])["seq"] == 2
     assert json.loads(lines[1])["vector"] is None and os.path.isdir(tmp_path / "wal" / "checkpoint")
 
 
@@ -134,7 +137,10 @@ def test_handler_recovers_from_wal_and_checkpoint(vdb, tmp_path):
     cps = [d for d in os.listdir(tmp_path / "node_1" / "checkpoint") if d.startswith("checkpoint_")]
     assert len(cps) == 1                                                       # taken at id 5 (handler.py:316-317)
     cp = tmp_path / "node_1" / "checkpoint" / cps[0]
-    assert sorted(os.listdir(cp)) == ["deleted_ids.json", "index.bin", "index.bin.npz", "leveldb_data", "wal_pos.txt"]
+    # the reference's checkpoint layout (handler.py:156-178) + the exact WAL record number the checkpoint contains
+    assert sorted(os.listdir(cp)) == ["deleted_ids.json", "index.bin", "index.bin.npz", "leveldb_data", "wal_pos.txt",
+                                      "wal_seq.txt"]
+    assert os.listdir(cp / "leveldb_data") == ["kv_pos.json"]                  # a position in the append-only store
     # crash: a new handler on the same directory = newest checkpoint + incremental WAL replay (handler.py:181-219)
     h2 = make_handler(vdb, tmp_path, checkpoint_every=5)
     got = h2.search(vdb.SearchRequest(query_vector=vec(2), top_k=10)).search_result
@@ -150,6 +156,69 @@ def test_handler_recovers_from_wal_and_checkpoint(vdb, tmp_path):
                                   index_factory=fake_index.factory, checkpoint_every=0)
     r = h4.search(vdb.SearchRequest(query_vector=vec(0), top_k=4)).search_result
     assert r.keys == ["z0", "z2", "z3", "z1"]                                   # z1 replayed with its LAST vector
+
+
+def test_recovery_is_exact_at_the_checkpoint_boundary(vdb, tmp_path, monkeypatch):
+    """Operations that share the checkpoint's millisecond are neither lost nor applied twice: the checkpoint records
+    the WAL sequence number it contains (the reference compares wall-clock milliseconds, wal_manager.py:214-215)."""
+    import time as _time
+    monkeypatch.setattr(_time, "time", lambda: 1_700_000_000.000)              # every record, and the checkpoint: same ms
+    h = make_handler(vdb, tmp_path, checkpoint_every=3)
+    for i in range(3):
+        h.put(vdb.VectorData(key=f"a{i}", vector=vec(i)))                      # checkpoint taken after the third
+    h.put(vdb.VectorData(key="late", vector=vec(7)))                           # same millisecond, AFTER the checkpoint
+    h.delete("a1")
+    want = h.search(vdb.SearchRequest(query_vector=vec(0), top_k=10)).search_result
+    h2 = make_handler(vdb, tmp_path, checkpoint_every=3)
+    got = h2.search(vdb.SearchRequest(query_vector=vec(0), top_k=10)).search_result
+    assert got.keys == want.keys == ["a0", "a2", "late"] and got.scores == want.scores
+    assert h2.hnsw_index.get_current_count() == 4                              # 3 from the snapshot + 1 replayed put
+
+
+def test_checkpoints_are_pruned_and_bulk_puts_log_by_reference(vdb, tmp_path):
+    h = make_handler(vdb, tmp_path, checkpoint_every=4)
+    keys = [f"b{i}" for i in range(20)]
+    vecs = np.stack([np.array(vec(i), dtype=np.float32) for i in range(20)])
+    for lo in range(0, 20, 5):
+        assert h.put_arrays(keys[lo:lo + 5], vecs[lo:lo + 5], [{"i": str(i)} for i in range(lo, lo + 5)]).success
+    cps = sorted(d for d in os.listdir(tmp_path / "node_1" / "checkpoint"))
+    assert len(cps) == 2                                                       # keep_checkpoints = 2
+    wal_dir = tmp_path / "node_1" / "wal" / "data"
+    recs = [json.loads(l) for f in sorted(os.listdir(wal_dir)) for l in open(wal_dir / f, encoding="utf-8")]
+    assert len(recs) == 20 and all(r["vector"] is None and r["hnsw_id"] == i for i, r in enumerate(recs))
+    h.put(vdb.VectorData(key="b3", vector=vec(33)))                            # inline JSON vector, overwrites b3
+    # recovery reads the by-reference vectors back from the raw-vector file
+    h2 = make_handler(vdb, tmp_path, checkpoint_every=4)
+    assert h2.get("b7").vector_data.vector == vec(7) and h2.get("b7").vector_data.metadata == {"i": "7"}
+    assert h2.get("b3").vector_data.vector == vec(33)
+    r = h2.search(vdb.SearchRequest(query_vector=vec(19), top_k=3)).search_result
+    assert r.keys == ["b19", "b18", "b17"]
+    # full replay (no checkpoint left): same state
+    import shutil
+    shutil.rmtree(tmp_path / "node_1" / "checkpoint")
+    os.makedirs(tmp_path / "node_1" / "checkpoint")
+    h3 = make_handler(vdb, tmp_path, checkpoint_every=0)
+    assert h3.get("b7").vector_data.vector == vec(7) and h3.get("b3").vector_data.vector == vec(33)
+    assert len(h3.store) == 20
+
+
+def test_key_store_roundtrip_and_torn_tail(vdb, tmp_path):
+    KeyStore = vdb.kvstore.KeyStore
+    s = KeyStore(str(tmp_path / "kv"), 8, fsync=False)
+    s.put(0, "x", np.arange(8, dtype=np.float32), {"a": "1"})
+    s.put_batch([1, 2, 5], ["y", "z", "x"], np.ones((3, 8), np.float32) * np.array([[1], [2], [5]], np.float32), [None, {}, {"b": "2"}])
+    assert s.id_of("x") == 5 and s.key_of(0) == "" and s.key_of(5) == "x" and s.metadata(5) == {"b": "2"} and s.metadata(1) == {}
+    assert s.vector(2).tolist() == [2.0] * 8 and len(s) == 3
+    pos = s.position()
+    assert s.delete("y") == 1 and s.delete("y") == -1 and "y" not in s
+    s.close()
+    with open(tmp_path / "kv" / "keys.log", "ab") as f:
+        f.write(b'{"i": 9, "k": "torn')                                        # a crash in the middle of an append
+    s2 = KeyStore(str(tmp_path / "kv"), 8, fsync=False)
+    assert sorted(s2.keys()) == ["x", "z"] and s2.id_of("torn") == -1 and s2.id_of("x") == 5
+    s2.rollback(pos)                                                           # back to before the delete
+    assert sorted(s2.keys()) == ["x", "y", "z"] and s2.id_of("y") == 1
+    s2.close()
 
 
 def test_put_batch_equals_sequential_puts(vdb, tmp_path):
