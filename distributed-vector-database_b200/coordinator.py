@@ -82,13 +82,24 @@ class LocalCoordinator:
         merged = merge_search_results(results, req.top_k)
         return Response(success=True, search_result=merged)
 
-    def search_batch(self, queries, top_k: int) -> Tuple[List[List[str]], List[List[float]]]:
-        """Additive: many queries per call (every node's `search_batch`, i.e. the tensor-core path), merged per
-        query with the coordinator's rule.  Returns (keys[nq][<=k], scores[nq][<=k])."""
+    NODE_SHIFT = 28          # merged labels carry (node index << 28 | node-local id): 16 nodes x 268M rows
+
+    def search_batch(self, queries, top_k: int, gpu_merge: Optional[bool] = None) -> Tuple[List[List[str]], List[List[float]]]:
+        """Additive: many queries per call.  Every node answers with ARRAYS (`search_ids`: the tensor-core path,
+        tombstones masked on the GPU), the G lists of each query are merged on the GPU (`vdb_merge_topk`, kernel K5:
+        ascending (score, node, id) -- the order of the reference's stable sort over the node-ordered concatenation,
+        coordinator/handler.py:200-216) and only the k winners of each query are mapped to keys.  Nodes without
+        `search_ids` (remote / plain handlers), or `gpu_merge=False`, take the per-query Python merge.
+        Returns (keys[nq][<=k], scores[nq][<=k])."""
         nq = len(queries)
         if not self.nodes:
             return [[] for _ in range(nq)], [[] for _ in range(nq)]
         k = top_k if top_k and top_k > 0 else 5
+        array_nodes = all(hasattr(n, "search_ids") and hasattr(n, "keys_of") for n in self.nodes.values())
+        if gpu_merge is None:
+            gpu_merge = array_nodes
+        if gpu_merge and array_nodes and len(self.node_ids) <= (1 << (32 - self.NODE_SHIFT)):
+            return self._search_batch_gpu(np.ascontiguousarray(np.asarray(queries, dtype=np.float32)), k)
 
         def one(node_id):
             try:
@@ -103,6 +114,47 @@ class LocalCoordinator:
             m = merge_search_results(lists, k)
             out_k.append(m.keys)
             out_s.append(m.scores)
+        return out_k, out_s
+
+    def _search_batch_gpu(self, q: np.ndarray, k: int):
+        from .index import merge_topk
+        nq = len(q)
+
+        def one(node_id):
+            try:
+                return self.nodes[node_id].search_ids(q, k)
+            except Exception:                                                      # :198-199 a failed node is skipped
+                return None
+
+        per_node = list(self._pool.map(one, self.node_ids)) if self._pool is not None else [one(n) for n in self.node_ids]
+        live = [(g, pn) for g, pn in enumerate(per_node) if pn is not None]
+        if not live:
+            return [[] for _ in range(nq)], [[] for _ in range(nq)]
+        mask = (1 << self.NODE_SHIFT) - 1
+        ids = np.stack([np.where(pn[0] >= 0, pn[0] + (g << self.NODE_SHIFT), -1) for g, pn in live]).astype(np.int64)
+        if any(int(pn[0].max(initial=-1)) > mask for _, pn in live):
+            raise RuntimeError("node-local ids beyond 2^28: merge on the host instead (gpu_merge=False)")
+        dist = np.stack([pn[1] for _, pn in live]).astype(np.float32)
+        device = getattr(self.nodes[self.node_ids[live[0][0]]], "device", 0)
+        m_d, m_i = merge_topk(dist, ids, k, device=device)                        # [nq, k] ascending (score, node, id)
+        out_k, out_s = [], []
+        # ids -> keys once per node for all winners
+        node_of = np.where(m_i >= 0, m_i >> self.NODE_SHIFT, -1)
+        local = np.where(m_i >= 0, m_i & mask, -1)
+        key_grid = np.full(m_i.shape, "", dtype=object)
+        for g, _ in live:
+            sel = node_of == g
+            if sel.any():
+                key_grid[sel] = self.nodes[self.node_ids[g]].keys_of(local[sel].tolist())
+        for r in range(nq):
+            ks, ss, seen = [], [], set()
+            for key, d in zip(key_grid[r].tolist(), m_d[r].tolist()):
+                if key and key not in seen:                                        # first seen wins (:200-206)
+                    seen.add(key)
+                    ks.append(key)
+                    ss.append(float(d))
+            out_k.append(ks)
+            out_s.append(ss)
         return out_k, out_s
 
     def close(self) -> None:

@@ -898,8 +898,9 @@ struct RerankParams {
     EpsModel em;              // error model of the approximate values
     int f16_range;            // operands were rounded to fp16: norms beyond its range void the certificate
     int64_t* out_ids; float* out_dist; int* out_counts;
-    int* flags;               // [nq] 1 = certificate failed
-    int* n_flagged;
+    int* flags;               // [nq] 1 = certificate failed: exact_fallback_kernel re-searches the query
+    int* n_flagged;           // flagged queries of this batch (zeroed with the batch's other flags)
+    unsigned long long* n_fallback;   // cumulative count of such queries (statistics; never reset)
     const int* cnt;           // [nq] keys in the buffer (may exceed cap: overflow)
     int cap;
     const uint32_t* tomb; uint32_t n_rows;
@@ -996,7 +997,108 @@ __device__ __forceinline__ void exact_keys(const RerankParams& p, const float* q
 //   5. exact distances, two rows in flight per warp   6. results written at their rank (by counting), certificate
 constexpr int RW_MAX_THREADS = 256;            // 128 threads per query for k' <= 64, 256 above
 
+// ------------------------------------------------------------------------------------------
+// Exact re-search of ONE query by its block (the certificate failed or a level buffer overflowed: floods of
+// near-duplicates, values beyond the fp16 range, adversarial insertion orders).  Every live row of the shard is
+// scored in fp32 with the scan kernel's summation order; candidates that beat the current k-th key collect in a
+// shared-memory buffer that is cut back to the k best whenever it fills.  A block streams the shard at a fraction of
+// the HBM rate -- this is the slow, always-correct road; what matters is that it needs no host round trip: the
+// search stays one enqueue on the caller's stream whatever the data looks like.
+//   buf / scratch: [buf_n] keys each in shared memory, buf_n >= k + rows per round
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int block_keep_k_smallest(uint64_t* buf, int n, int k, uint64_t* scratch, int* hist, uint32_t* sh,
+                                                     int* s_a, int* s_b) {
+    // -> number kept (min(n, k)); kept keys end up in buf[0..kept), unordered.  Keys are distinct.
+    const int tid = threadIdx.x, NT = blockDim.x;
+    __syncthreads();
+    if (n <= k) return n;
+    const uint32_t T = block_kth_bits(buf, n, k, hist, sh);       // value bits of the k-th smallest
+    if (tid == 0) { *s_a = 0; *s_b = 0; }
+    __syncthreads();
+    int less = 0;
+    for (int i = tid; i < n; i += NT) less += (uint32_t)(buf[i] >> 32) < T;
+    less = warp_sum_int(less);
+    if ((tid & 31) == 0 && less) atomicAdd(s_a, less);
+    __syncthreads();
+    const int n_less = *s_a, need_eq = k - n_less;               // keys with bits == T to keep: the need_eq smallest
+    __syncthreads();
+    if (tid == 0) *s_a = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += NT) {
+        const uint64_t key = buf[i];
+        const uint32_t v = (uint32_t)(key >> 32);
+        bool keep = v < T;
+        if (v == T) {
+            int r = 0;
+            for (int j = 0; j < n; ++j) { const uint64_t o = buf[j]; r += ((uint32_t)(o >> 32) == T) && o < key; }
+            keep = r < need_eq;
+        }
+        if (keep) scratch[atomicAdd(s_a, 1)] = key;
+    }
+    __syncthreads();
+    const int kept = *s_a;
+    for (int i = tid; i < kept; i += NT) buf[i] = scratch[i];
+    __syncthreads();
+    return kept;
+}
+
 template <typename T>
+__device__ void exact_scan_block(const RerankParams& p, int q, uint64_t* buf, uint64_t* scratch, int buf_n, int* hist, uint32_t* sh) {
+    __shared__ int s_cnt, s_a, s_b;
+    __shared__ unsigned long long s_thr;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5, k = p.k;
+    constexpr int NR = 4;
+    const int per_round = nwarps * NR;
+    if (tid == 0) { s_cnt = 0; s_thr = KEY_SENTINEL; }
+    __syncthreads();
+    const float* qv = p.q + (size_t)q * p.ld;
+    for (uint32_t r0 = 0; r0 < p.n_rows; r0 += per_round) {
+        uint32_t rows[NR];
+        bool live[NR];
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            const uint32_t row = r0 + warp * NR + i;
+            live[i] = row < p.n_rows && !(p.tomb && ((p.tomb[row >> 5] >> (row & 31)) & 1u));
+            rows[i] = row < p.n_rows ? row : p.n_rows - 1;
+        }
+        uint64_t keys[NR];
+        exact_keys<T, NR>(p, qv, rows, lane, keys);
+        if (lane == 0) {
+            const unsigned long long thr = s_thr;
+#pragma unroll
+            for (int i = 0; i < NR; ++i)
+                if (live[i] && keys[i] < thr) buf[atomicAdd(&s_cnt, 1)] = keys[i];
+        }
+        __syncthreads();
+        if (s_cnt + per_round > buf_n) {                          // block-uniform: cut back to the k best
+            const int kept = block_keep_k_smallest(buf, s_cnt, k, scratch, hist, sh, &s_a, &s_b);
+            if (tid == 0) {
+                s_cnt = kept;
+                if (kept == k) {                                  // the k-th best so far bounds what can still matter
+                    unsigned long long mx = 0;
+                    for (int i = 0; i < kept; ++i) mx = buf[i] > mx ? buf[i] : mx;
+                    s_thr = mx;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const int m = block_keep_k_smallest(buf, s_cnt, k, scratch, hist, sh, &s_a, &s_b);
+    for (int i = tid; i < m; i += blockDim.x) {
+        const uint64_t key = buf[i];
+        int rank = 0;
+        for (int j = 0; j < m; ++j) rank += buf[j] < key;
+        p.out_ids[(size_t)q * k + rank] = (int64_t)key_label(key);
+        p.out_dist[(size_t)q * k + rank] = key_dist(key);
+    }
+    for (int i = m + tid; i < k; i += blockDim.x) {
+        p.out_ids[(size_t)q * k + i] = -1;
+        p.out_dist[(size_t)q * k + i] = __int_as_float(0x7f800000);
+    }
+    if (tid == 0 && p.out_counts) p.out_counts[q] = m;
+}
+
+template <typename T, int NRW>
 __global__ void __launch_bounds__(RW_MAX_THREADS) rerank_window_kernel(const RerankParams p, const int kp) {
     pdl_prologue();
     extern __shared__ uint64_t wsm[];
@@ -1089,12 +1191,18 @@ __global__ void __launch_bounds__(RW_MAX_THREADS) rerank_window_kernel(const Rer
     int m = s_m;
     // ---- 5. exact distances -> lk
     const float* qv = p.q + (size_t)q * p.ld;
-    for (int c = 2 * warp; c < m; c += 2 * (RW_THREADS / 32)) {     // an odd tail repeats its row (result discarded)
-        const uint32_t rows[2] = {(uint32_t)sk[c], (uint32_t)sk[min(c + 1, m - 1)]};
-        uint64_t out[2];
-        exact_keys<T, 2>(p, qv, rows, lane, out);
-        if (lane == 0) lk[c] = out[0];
-        if (lane == 1 && c + 1 < m) lk[c + 1] = out[1];
+    // rows in flight per warp.  Measured (B200): 4 rows cost 104 registers -> half the resident blocks of 2 rows;
+    // with k' <= 64 (a dozen window rows per query, 8192 queries) 2 rows win (b8192 x 125k: 0.977 vs 1.029 ms/step),
+    // with k' >= 128 (~130 window rows per query) 4 rows win (config-3 shard: 5.08 vs 5.14 ms/step): the window is a handful of rows per query,
+    for (int c = NRW * warp; c < m; c += NRW * (RW_THREADS / 32)) {   // its time is memory latency (a ragged tail
+        uint32_t rows[NRW];                                          // repeats the last row, result discarded)
+#pragma unroll
+        for (int i = 0; i < NRW; ++i) rows[i] = (uint32_t)sk[min(c + i, m - 1)];
+        uint64_t out[NRW];
+        exact_keys<T, NRW>(p, qv, rows, lane, out);
+#pragma unroll
+        for (int i = 0; i < NRW; ++i)
+            if (lane == i && c + i < m) lk[c + i] = out[i];
     }
     __syncthreads();
     // ---- 6. results at their rank (keys are distinct: labels are), certificate
@@ -1124,7 +1232,30 @@ __global__ void __launch_bounds__(RW_MAX_THREADS) rerank_window_kernel(const Rer
         // an element above the fp16 range became +-inf in the operand plane (|x_i| <= ||x||): no bound holds
         if (p.f16_range && (qn2 >= 4.0e9f || dmax2 >= 4.0e9f)) ok = false;
         p.flags[q] = ok ? 0 : 1;
-        if (!ok) atomicAdd(p.n_flagged, 1);
+        if (!ok) { atomicAdd(p.n_flagged, 1); atomicAdd(p.n_fallback, 1ull); }   // exact_fallback_kernel takes it from here
+    }
+}
+
+// K4x: exact re-search of the queries K4w flagged, launched after it on every batch.  Almost always there are none:
+// every block reads one counter and leaves (the launch overlaps K4w's tail through programmatic dependent launch).
+// Otherwise the flagged queries are dealt round-robin to the blocks of the grid.
+constexpr int XF_THREADS = 256;
+constexpr int XF_BUF = 1024;
+template <typename T>
+__global__ void __launch_bounds__(XF_THREADS) exact_fallback_kernel(const RerankParams p, const int nq) {
+    pdl_prologue();
+    if (*reinterpret_cast<const volatile int*>(p.n_flagged) == 0) return;
+    __shared__ uint64_t buf[XF_BUF], scratch[XF_BUF];
+    __shared__ int hist[256];
+    __shared__ uint32_t sh[8];
+    int ord = 0;
+    for (int q = 0; q < nq; ++q) {
+        if (p.flags[q] == 0) continue;                            // block-uniform
+        if (ord % (int)gridDim.x == (int)blockIdx.x) {
+            exact_scan_block<T>(p, q, buf, scratch, XF_BUF, hist, sh);
+            __syncthreads();
+        }
+        ++ord;
     }
 }
 
@@ -1147,7 +1278,7 @@ struct GemmWsImpl {
     __half* q16 = nullptr; size_t q16_cap = 0;
     int* flags = nullptr; size_t flags_cap = 0;
     int* n_flagged = nullptr;
-    int* h_n_flagged = nullptr;   // pinned
+    unsigned long long* n_fallback = nullptr;     // cumulative, read by gemm_workspace_fallbacks
 };
 struct GemmPlanImpl {
     long fallbacks = 0;
@@ -1193,7 +1324,14 @@ static int probe_tiles(int rank) {
     static const int v = env_int("VDB_PROBE_TILES", 0);
     return std::max(v > 0 ? v : GT_PROBE_TILES, (rank + 1) / 2);
 }
-static int level_growth() { static const int v = std::max(2, env_int("VDB_GROWTH", GT_LEVEL_GROWTH)); return v; }
+// each level covers `growth` x the rows that informed its threshold.  Survivors per level ~ threshold rank x growth:
+// for large k (k' = 256, ~1300 survivors per query and level at growth 8) the epilogue's slow path and the selects
+// dominate, and a level more with half the survivors wins (measured on 1.25M x 512, L2, k = 100, batch 4096:
+// growth 8 5.61 ms/step, growth 4 5.15; k = 10 on 1M rows: growth 8 is the best that keeps the buffers half empty)
+static int level_growth(int k) {
+    static const int v = env_int("VDB_GROWTH", 0);
+    return v >= 2 ? v : (k >= 64 ? 4 : GT_LEVEL_GROWTH);
+}
 // keys a query's level buffer holds: 16 k' (the levels are planned for <= 55 % of that); a shard of at most 32 k'
 // rows gets a buffer that holds every row, because its probe may see fewer live chunks than the threshold rank
 // and then publishes no threshold (the single level that follows keeps everything)
@@ -1251,11 +1389,13 @@ static cudaError_t launch_rerank_window(int kp, const RerankParams& rp, size_t n
     static size_t configured[MAX_DEVICES] = {};
     const int slot = current_device_slot();
     if (smem > configured[slot]) {
-        cudaError_t e = cudaFuncSetAttribute(rerank_window_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(rerank_window_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(rerank_window_kernel<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured[slot] = smem;
     }
-    cudaError_t le = launch_pdl(rerank_window_kernel<T>, dim3((unsigned)nq), dim3(kp <= 64 ? 128 : RW_MAX_THREADS), smem, st, rp, kp);
+    cudaError_t le = kp <= 64 ? launch_pdl(rerank_window_kernel<T, 2>, dim3((unsigned)nq), dim3(128), smem, st, rp, kp)
+                              : launch_pdl(rerank_window_kernel<T, 4>, dim3((unsigned)nq), dim3(RW_MAX_THREADS), smem, st, rp, kp);
     count_launch();
     return le != cudaSuccess ? le : cudaGetLastError();
 }
@@ -1279,7 +1419,8 @@ static cudaError_t ensure_ws(GemmWorkspace& ws) {
     if (ws.impl) return cudaSuccess;
     auto* w = new GemmWsImpl();
     cudaError_t e = cudaMalloc((void**)&w->n_flagged, sizeof(int));
-    if (e == cudaSuccess) e = cudaMallocHost((void**)&w->h_n_flagged, sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&w->n_fallback, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(w->n_fallback, 0, sizeof(unsigned long long));
     if (e != cudaSuccess) { delete w; return e; }
     ws.impl = w;
     return cudaSuccess;
@@ -1319,7 +1460,7 @@ LevelPlan gemm_topk_level_plan(size_t nq, size_t n_rows, int k) {
     lp.kq = std::max(lp.kp / 2, std::min(lp.kp, (16 * k + 9) / 10));
     lp.query_blocks = (int)((nq + 2 * GT_BM - 1) / (2 * GT_BM));       // 256-query blocks, one per CTA pair
     lp.small_batch = lp.query_blocks <= 2 && env_int("VDB_SMALL_PLAN", 1) != 0;
-    lp.growth = lp.small_batch ? std::max(level_growth(), std::min(64, 8192 / (3 * lp.kq))) : level_growth();
+    lp.growth = lp.small_batch ? std::max(level_growth(k), std::min(64, 8192 / (3 * lp.kq))) : level_growth(k);
     lp.cap = cap_for(lp.kp, n_rows);
     if (lp.small_batch)
         while (lp.cap < 3 * lp.kq * lp.growth && lp.cap < 8192) lp.cap <<= 1;
@@ -1469,46 +1610,28 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
     rp.em = em;
     rp.f16_range = g16 ? 1 : 0;
     rp.out_ids = a.out_ids; rp.out_dist = a.out_dist; rp.out_counts = a.out_counts;
-    rp.flags = w->flags; rp.n_flagged = w->n_flagged;
+    rp.flags = w->flags; rp.n_flagged = w->n_flagged; rp.n_fallback = w->n_fallback;
     rp.cnt = w->cnt; rp.cap = cap; rp.tomb = a.tomb; rp.n_rows = a.n_rows;
     e = a.f16 ? launch_rerank_window<__half>(kp, rp, a.nq, st) : launch_rerank_window<float>(kp, rp, a.nq, st);
     if (e != cudaSuccess) return e;
-    return cudaSuccess;
+    // K4x: queries whose certificate failed are re-searched exactly ON THE DEVICE -- no host round trip, the whole
+    // search is one enqueue.  Without flagged queries (the normal case) its blocks read one counter and leave.
+    const unsigned xgrid = (unsigned)std::min<size_t>(a.nq, (size_t)a.num_sms * 2);
+    e = a.f16 ? launch_pdl(exact_fallback_kernel<__half>, dim3(xgrid), dim3(XF_THREADS), 0, st, rp, (int)a.nq)
+              : launch_pdl(exact_fallback_kernel<float>, dim3(xgrid), dim3(XF_THREADS), 0, st, rp, (int)a.nq);
+    count_launch();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
-// After gemm_topk_search: how many queries failed the certificate, and which.  Split in two so that a caller
-// that synchronises the stream anyway (vdb_search copies the results to the host) pays no extra round trip:
-//   _enqueue: async copy of the counter to pinned host memory on `st`
-//   _collect: after `st` has been synchronised; lists the flagged queries (one more copy only when there are any)
-cudaError_t gemm_topk_flagged_enqueue(GemmWorkspace& ws, cudaStream_t st) {
+// Queries this workspace has re-searched exactly so far (synchronises the device: statistics only).
+long gemm_workspace_fallbacks(const GemmWorkspace& ws) {
     auto* w = static_cast<GemmWsImpl*>(ws.impl);
-    return cudaMemcpyAsync(w->h_n_flagged, w->n_flagged, sizeof(int), cudaMemcpyDeviceToHost, st);
-}
-cudaError_t gemm_topk_flagged_collect(GemmWorkspace& ws, size_t nq, std::vector<int>& flagged, cudaStream_t st) {
-    auto* w = static_cast<GemmWsImpl*>(ws.impl);
-    flagged.clear();
-    if (*w->h_n_flagged == 0) return cudaSuccess;
-    std::vector<int> f(nq);
-    cudaError_t e = cudaMemcpyAsync(f.data(), w->flags, nq * sizeof(int), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) return e;
-    for (size_t i = 0; i < nq; ++i)
-        if (f[i]) flagged.push_back((int)i);
-    return cudaSuccess;
-}
-cudaError_t gemm_topk_flagged(GemmWorkspace& ws, size_t nq, std::vector<int>& flagged, cudaStream_t st) {
-    cudaError_t e = gemm_topk_flagged_enqueue(ws, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) return e;
-    return gemm_topk_flagged_collect(ws, nq, flagged, st);
+    if (!w || !w->n_fallback) return 0;
+    unsigned long long v = 0;
+    if (cudaMemcpy(&v, w->n_fallback, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return (long)v;
 }
 
-void gemm_plan_note_fallbacks(GemmPlan& plan, long n) {
-    if (!plan.impl) plan.impl = new GemmPlanImpl();
-    static std::mutex mu;
-    std::lock_guard<std::mutex> lk(mu);
-    static_cast<GemmPlanImpl*>(plan.impl)->fallbacks += n;
-}
 void gemm_plan_free(GemmPlan& plan) {
     delete static_cast<GemmPlanImpl*>(plan.impl);
     plan.impl = nullptr;
@@ -1523,12 +1646,8 @@ void gemm_workspace_free(GemmWorkspace& ws) {
     if (w->q16) cudaFree(w->q16);
     if (w->flags) cudaFree(w->flags);
     if (w->n_flagged) cudaFree(w->n_flagged);
-    if (w->h_n_flagged) cudaFreeHost(w->h_n_flagged);
+    if (w->n_fallback) cudaFree(w->n_fallback);
     delete w;
     ws.impl = nullptr;
 }
-long gemm_plan_fallbacks(const GemmPlan& plan) {
-    return plan.impl ? static_cast<GemmPlanImpl*>(plan.impl)->fallbacks : 0;
-}
-
 }  // namespace vdbk

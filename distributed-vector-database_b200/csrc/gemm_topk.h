@@ -51,14 +51,10 @@ LevelPlan gemm_topk_level_plan(size_t nq, size_t n_rows, int k);
 
 bool gemm_topk_supported(int dim, int ld, bool f16, int k, size_t n_rows);
 cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearchArgs& a, cudaStream_t st, std::string& err);
-// after gemm_topk_search: synchronises `st` and lists the queries whose certificate failed
-cudaError_t gemm_topk_flagged(GemmWorkspace& ws, size_t nq, std::vector<int>& flagged, cudaStream_t st);
-// the same in two halves for callers that synchronise `st` themselves between them
-cudaError_t gemm_topk_flagged_enqueue(GemmWorkspace& ws, cudaStream_t st);
-cudaError_t gemm_topk_flagged_collect(GemmWorkspace& ws, size_t nq, std::vector<int>& flagged, cudaStream_t st);
-void gemm_plan_note_fallbacks(GemmPlan& plan, long n);
+// queries this workspace has re-searched exactly on the device so far (certificate failed / buffer overflowed);
+// synchronises the device -- statistics only
+long gemm_workspace_fallbacks(const GemmWorkspace& ws);
 void gemm_plan_free(GemmPlan& plan);
 void gemm_workspace_free(GemmWorkspace& ws);
-long gemm_plan_fallbacks(const GemmPlan& plan);
 
 }  // namespace vdbk

@@ -66,11 +66,6 @@ struct Workspace {
     float* h_q = nullptr; size_t h_q_cap = 0;
     uint8_t* h_out = nullptr; size_t h_out_cap = 0;
     GemmWorkspace gemm;
-    // exact re-search of queries that failed the tensor path's certificate
-    float* d_fq = nullptr; size_t fq_cap = 0;
-    int64_t* d_fids = nullptr; size_t fids_cap = 0;
-    float* d_fdist = nullptr; size_t fdist_cap = 0;
-    int* d_fcnt = nullptr; size_t fcnt_cap = 0;
 };
 
 template <typename T>
@@ -244,10 +239,6 @@ void free_workspace(Workspace* w) {
     if (w->d_cnt) cudaFree(w->d_cnt);
     if (w->h_q) cudaFreeHost(w->h_q);
     if (w->h_out) cudaFreeHost(w->h_out);
-    if (w->d_fq) cudaFree(w->d_fq);
-    if (w->d_fids) cudaFree(w->d_fids);
-    if (w->d_fdist) cudaFree(w->d_fdist);
-    if (w->d_fcnt) cudaFree(w->d_fcnt);
     gemm_workspace_free(w->gemm);
     if (w->done) cudaEventDestroy(w->done);
     if (w->stream) cudaStreamDestroy(w->stream);
@@ -362,36 +353,10 @@ int scan_prepared(vdb* db, Workspace* ws, const float* d_qp, size_t nq, int k, i
     return VDB_OK;
 }
 
-// Queries whose coverage certificate failed are re-searched with the exact scan and patched into the outputs.
-int rescan_flagged(vdb* db, Workspace* ws, const std::vector<int>& flagged, size_t nq, int k, int64_t* d_ids,
-                   float* d_dist, int* d_cnt, cudaStream_t st, size_t n) {
-    (void)nq;
-    if (flagged.empty()) return VDB_OK;
-    const size_t nf = flagged.size();
-    gemm_plan_note_fallbacks(db->gemm_plan, (long)nf);
-    CU_TRY(grow(ws->d_fq, ws->fq_cap, nf * (size_t)db->ld));
-    CU_TRY(grow(ws->d_fids, ws->fids_cap, nf * (size_t)k));
-    CU_TRY(grow(ws->d_fdist, ws->fdist_cap, nf * (size_t)k));
-    CU_TRY(grow(ws->d_fcnt, ws->fcnt_cap, nf));
-    for (size_t i = 0; i < nf; ++i)
-        CU_TRY(cudaMemcpyAsync(ws->d_fq + i * (size_t)db->ld, ws->d_q + (size_t)flagged[i] * db->ld,
-                               (size_t)db->ld * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    int rc = scan_prepared(db, ws, ws->d_fq, nf, k, ws->d_fids, ws->d_fdist, ws->d_fcnt, st, n);
-    if (rc) return rc;
-    for (size_t i = 0; i < nf; ++i) {
-        const size_t qi = (size_t)flagged[i];
-        CU_TRY(cudaMemcpyAsync(d_ids + qi * k, ws->d_fids + i * k, (size_t)k * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
-        CU_TRY(cudaMemcpyAsync(d_dist + qi * k, ws->d_fdist + i * k, (size_t)k * sizeof(float), cudaMemcpyDeviceToDevice, st));
-        if (d_cnt) CU_TRY(cudaMemcpyAsync(d_cnt + qi, ws->d_fcnt + i, sizeof(int), cudaMemcpyDeviceToDevice, st));
-    }
-    return VDB_OK;
-}
-
-// Enqueue a search of nq device-resident raw queries on `st`.  Outputs are device pointers.
-// deferred != null: the tensor path does not wait for its certificate; *deferred tells the caller to synchronise
-// `st` and then run gemm_topk_flagged_collect + rescan_flagged (vdb_search does, saving a host round trip).
+// Enqueue a search of nq device-resident raw queries on `st`.  Outputs are device pointers.  Nothing here waits for
+// the device: a query whose tensor-path certificate fails is re-searched exactly by a kernel of the same enqueue.
 int search_core(vdb* db, Workspace* ws, const float* d_q_raw, size_t nq, int k, int64_t* d_ids, float* d_dist,
-                int* d_cnt, cudaStream_t st, size_t n, bool* deferred = nullptr) {
+                int* d_cnt, cudaStream_t st, size_t n) {
     const bool f16 = db->dtype == VDB_F16;
     MergeParams mp{};
     mp.nq = nq;
@@ -444,15 +409,7 @@ int search_core(vdb* db, Workspace* ws, const float* d_q_raw, size_t nq, int k, 
             return fail(VDB_ECUDA, "gemm_topk_search: " + (err.empty() ? std::string(cudaGetErrorString(e)) : err));
         }
         db->stat_tensor_batches.fetch_add(1);
-        if (deferred) {     // the caller synchronises the stream once and then calls finish_tensor_search
-            CU_TRY(gemm_topk_flagged_enqueue(ws->gemm, st));
-            *deferred = true;
-            return VDB_OK;
-        }
-        // queries whose coverage certificate failed are re-searched with the exact scan
-        std::vector<int> flagged;
-        CU_TRY(gemm_topk_flagged(ws->gemm, nq, flagged, st));
-        return rescan_flagged(db, ws, flagged, nq, k, d_ids, d_dist, d_cnt, st, n);
+        return VDB_OK;
     }
 
     return fail(VDB_ECUDA, "internal: unreachable search path");
@@ -757,9 +714,7 @@ int vdb_search(vdb_t* db, const float* queries, size_t nq, int k, int64_t* out_l
     const bool out_pinned = is_pinned_host(out_labels) && is_pinned_host(out_dist) && (!out_counts || is_pinned_host(out_counts));
     if (!q_pinned) memcpy(ws->h_q, queries, qelems * sizeof(float));
     CU_TRY(cudaMemcpyAsync(ws->d_q_in, q_pinned ? queries : ws->h_q, qelems * sizeof(float), cudaMemcpyHostToDevice, st));
-    bool deferred = false;
-    static const bool defer_ok = [] { const char* e = getenv("VDB_DEFER"); return !(e && e[0] == '0'); }();
-    rc = search_core(db, ws, ws->d_q_in, nq, k, ws->d_ids, ws->d_dist, ws->d_cnt, st, n, defer_ok ? &deferred : nullptr);
+    rc = search_core(db, ws, ws->d_q_in, nq, k, ws->d_ids, ws->d_dist, ws->d_cnt, st, n);
     if (rc) { cudaStreamSynchronize(st); return rc; }
     int64_t* h_ids = reinterpret_cast<int64_t*>(ws->h_out);
     float* h_dist = reinterpret_cast<float*>(ws->h_out + nout * sizeof(int64_t));
@@ -769,18 +724,6 @@ int vdb_search(vdb_t* db, const float* queries, size_t nq, int k, int64_t* out_l
     CU_TRY(cudaMemcpyAsync(h_dist, ws->d_dist, nout * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (h_cnt) CU_TRY(cudaMemcpyAsync(h_cnt, ws->d_cnt, nq * sizeof(int), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
-    if (deferred) {     // certificate verdicts arrived with the results: almost always nothing to do
-        std::vector<int> flagged;
-        CU_TRY(gemm_topk_flagged_collect(ws->gemm, nq, flagged, st));
-        if (!flagged.empty()) {
-            rc = rescan_flagged(db, ws, flagged, nq, k, ws->d_ids, ws->d_dist, ws->d_cnt, st, n);
-            if (rc) { cudaStreamSynchronize(st); return rc; }
-            CU_TRY(cudaMemcpyAsync(h_ids, ws->d_ids, nout * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-            CU_TRY(cudaMemcpyAsync(h_dist, ws->d_dist, nout * sizeof(float), cudaMemcpyDeviceToHost, st));
-            if (h_cnt) CU_TRY(cudaMemcpyAsync(h_cnt, ws->d_cnt, nq * sizeof(int), cudaMemcpyDeviceToHost, st));
-            CU_TRY(cudaStreamSynchronize(st));
-        }
-    }
     if (!out_pinned) {
         memcpy(out_labels, h_ids, nout * sizeof(int64_t));
         memcpy(out_dist, h_dist, nout * sizeof(float));
@@ -1163,7 +1106,13 @@ int vdb_set_option(vdb_t* db, const char* name, long value) {
 }
 long vdb_get_stat(vdb_t* db, const char* name) {
     if (!db || !name) return -1;
-    if (!strcmp(name, "fallback_queries")) return db->stat_fallback.load() + gemm_plan_fallbacks(db->gemm_plan);
+    if (!strcmp(name, "fallback_queries")) {      // counted on the device, per workspace (synchronises)
+        long total = db->stat_fallback.load();
+        cudaSetDevice(db->device);
+        std::lock_guard<std::mutex> lk(db->ws_mu);
+        for (auto& w : db->ws_all) total += gemm_workspace_fallbacks(w->gemm);
+        return total;
+    }
     if (!strcmp(name, "tensor_batches")) return db->stat_tensor_batches.load();
     if (!strcmp(name, "scan_passes")) return db->stat_scan_passes.load();
     if (!strcmp(name, "num_sms")) return db->num_sms;

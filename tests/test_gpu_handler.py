@@ -145,3 +145,127 @@ def test_micro_batched_handler_on_the_gpu(vdb, tmp_path):
         assert resp.search_result.scores == want[j].scores
     assert fast._batcher.requests == 8 * 24 and fast._batcher.batches < 8 * 24
     assert fast.hnsw_index.get_stat("tensor_batches") >= 1
+
+
+def test_coordinator_search_batch_gpu_merge_equals_host_merge(vdb, tmp_path):
+    """LocalCoordinator.search_batch: per-node [nq, k] arrays merged by the GPU merge kernel (vdb_merge_topk), ids
+    mapped to keys once -- against the reference's merge rule in Python (coordinator/handler.py:200-225) and the
+    single-node model."""
+    nodes = {f"n{i}": vdb.GpuVectorNodeHandler(f"n{i}", storage_root=str(tmp_path), space="cosine", dim=DIM,
+                                               max_elements=2048, checkpoint_every=0, fsync=False) for i in range(4)}
+    coord = vdb.LocalCoordinator(nodes)
+    model = R.DatanodeModel(dim=DIM, metric="cosine")
+    rows = vecs(1500)
+    keys = [f"img_{i}" for i in range(1500)]
+    by_node = {}
+    for i, key in enumerate(keys):
+        by_node.setdefault(coord.mapping[vdb.get_shard_id(key, coord.shard_count)]["master"], []).append(i)
+        model.put(key, rows[i].tolist())
+    for node_id, idx in by_node.items():
+        assert nodes[node_id].put_arrays([keys[i] for i in idx], rows[idx]).success
+    for i in (3, 77, 500):                                   # tombstones on several shards
+        coord.delete(keys[i]); model.delete(keys[i])
+    qs = R.synth_rows(R.SEED_QUERY, 0, 40, DIM)
+    qs[0] = rows[9]
+    for k in (1, 10, 50):
+        gk, gs = coord.search_batch(qs, k)                    # GPU merge
+        hk, hs = coord.search_batch(qs, k, gpu_merge=False)   # the reference's merge in Python
+        assert gk == hk
+        for a, b in zip(gs, hs):
+            np.testing.assert_allclose(a, b, rtol=0, atol=0)
+        for r in (0, 7, 39):
+            ok, mk, ms = R.datanode_search_exact_live(model, qs[r].tolist(), k)
+            assert gk[r] == mk
+            np.testing.assert_allclose(gs[r], ms, rtol=1e-5, atol=1e-6)
+    assert gk[0][0] == "img_9"
+    # a node that fails is skipped (coordinator/handler.py:198-199)
+    class Down:
+        device = 0
+        def search_ids(self, q, k): raise ConnectionError("down")
+        def keys_of(self, ids): return []
+    flaky = vdb.LocalCoordinator({**nodes, "zz": Down()}, shard_count=4)
+    fk, fs = flaky.search_batch(qs[:3], 10)
+    assert fk == gk_ref(coord, qs[:3], 10)
+
+
+def gk_ref(coord, qs, k):
+    return coord.search_batch(qs, k, gpu_merge=False)[0]
+
+
+def test_shard_grows_in_place_while_searches_run(vdb):
+    """resize_index maps more memory behind the same base pointers (no copy, no exclusive lock): searches that run
+    during the growth and the appends stay correct; growing past the address reservation (8x) re-bases without
+    copying; the content survives both."""
+    import threading
+    ix = vdb.Index("l2", DIM)
+    ix.init_index(1000)
+    raw = R.synth_rows(R.SEED_DB, 0, 1000, DIM)
+    ix.add_items(raw, np.arange(1000))
+    q = R.synth_rows(R.SEED_QUERY, 0, 3, DIM)
+    base = ix.knn_query_padded(q, 10)
+    errs, stop = [], threading.Event()
+
+    def searcher():
+        try:
+            while not stop.is_set():
+                l, d, c = ix.knn_query_padded(q, 10)
+                assert (np.diff(d, axis=1) >= 0).all() and (d[:, 0] <= base[1][:, 0] + 1e-6).all() and (c == 10).all()
+        except Exception as e:      # noqa
+            errs.append(e)
+
+    ts = [threading.Thread(target=searcher) for _ in range(3)]
+    [t.start() for t in ts]
+    try:
+        with pytest.raises(RuntimeError):                     # full, as hnswlib
+            ix.add_items(raw[:1], [5000])
+        for cap in (3000, 9000, 1_200_000, 9_000_000):        # the last one is beyond the reservation: re-base
+            ix.resize_index(cap)
+            assert ix.get_max_elements() == cap
+            n0 = ix.get_current_count()
+            ix.add_synthetic(R.SEED_DB, n0, 1500)
+    finally:
+        stop.set()
+        [t.join() for t in ts]
+    assert not errs, errs
+    n = ix.get_current_count()
+    assert n == 7000
+    stored = R.synth_rows(R.SEED_DB, 0, n, DIM)
+    got_l, got_d, cnt = ix.knn_query_padded(q, 10)
+    for i in range(len(q)):
+        msg = R.check_topk(got_l[i], got_d[i], q[i], stored, np.arange(n), 10, "l2", rtol=1e-5)
+        assert msg is None, msg
+    ix.resize_index(8000)                                     # shrinking the limit (>= count) is allowed
+    assert ix.get_max_elements() == 8000
+    with pytest.raises(RuntimeError):
+        ix.resize_index(10)
+
+
+def test_handler_bulk_load_and_recovery(vdb, tmp_path):
+    """put_arrays: one add_items + one key-store append + one WAL group commit per batch (vectors logged by reference),
+    the shard grows in place past max_elements, and a restart restores keys, vectors and metadata."""
+    h = vdb.GpuVectorNodeHandler("bulk", storage_root=str(tmp_path), space="cosine", dim=DIM, max_elements=1000,
+                                 checkpoint_every=2500, fsync=False)
+    rows = vecs(4000)
+    keys = [f"b{i}" for i in range(4000)]
+    for lo in range(0, 4000, 1000):
+        assert h.put_arrays(keys[lo:lo + 1000], rows[lo:lo + 1000], [{"i": str(i)} if i % 7 == 0 else None
+                                                                     for i in range(lo, lo + 1000)]).success
+    assert h.hnsw_index.get_current_count() == 4000 and h.hnsw_index.get_max_elements() >= 4000
+    extra = vecs(3, start=100_000)
+    assert h.put_arrays(["b5", "b5", "new"], extra).success                          # overwrite + in-batch duplicate
+    qs = np.stack([extra[1], rows[1234], extra[2], rows[5], extra[0]])
+    want = h.search_batch(qs, 5)
+    assert [w[0] for w in want[0][:3]] == ["b5", "b1234", "new"]
+    assert "b5" not in want[0][3][:1] and want[1][3][0] > 1e-3                       # the old b5 row is tombstoned
+    assert want[1][4][0] > 1e-3                                                      # and so is the in-batch duplicate
+    g = h.get("b7")
+    assert g.vector_data.metadata == {"i": "7"} and np.allclose(g.vector_data.vector, rows[7])
+    h.store.close()                                           # crash: no final checkpoint
+    h2 = vdb.GpuVectorNodeHandler("bulk", storage_root=str(tmp_path), space="cosine", dim=DIM, max_elements=1000,
+                                  checkpoint_every=2500, fsync=False)
+    got = h2.search_batch(qs, 5)
+    assert got[0] == want[0]
+    np.testing.assert_allclose(np.array(got[1]), np.array(want[1]), rtol=1e-6, atol=1e-7)
+    g = h2.get("b7")
+    assert g.vector_data.metadata == {"i": "7"} and np.allclose(g.vector_data.vector, rows[7])
+    assert np.allclose(h2.get("b5").vector_data.vector, extra[1]) and len(h2.store) == 4001

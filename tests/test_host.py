@@ -265,7 +265,7 @@ def test_coordinator_merge_and_routing(vdb, tmp_path):
             a = coord.search(vdb.SearchRequest(query_vector=vec(x), top_k=k)).search_result
             b = serial.search(vdb.SearchRequest(query_vector=vec(x), top_k=k)).search_result
             assert a.keys == b.keys == R.datanode_search_exact_live(model, vec(x), k)[1] and a.scores == b.scores
-    ks, ss = coord.search_batch([vec(1.4), vec(7.3)], 5)
+    ks, ss = coord.search_batch([vec(1.4), vec(7.3)], 5, gpu_merge=False)      # host merge (the GPU merge: tests/test_gpu_handler.py)
     assert ks == [R.datanode_search_exact_live(model, vec(x), 5)[1] for x in (1.4, 7.3)]
     assert ss[0] == coord.search(vdb.SearchRequest(query_vector=vec(1.4), top_k=5)).search_result.scores
 

@@ -8,10 +8,12 @@ commit per shard); after every growth step a batch of 256 queries is searched on
 queries/s against N, insert rows/s and WAL bytes/s, then checks the final state against the CPU oracle and a
 cold restart (checkpoint + WAL replay) against the live state.
 
-The reference's record keeps every vector as a JSON list in the WAL and as Python objects in the key table
-(~16 KB per row in CPython), so the full 1M -> 5M run is a memory exercise for the host; the default here is
-1/20 scale.  `--level index` runs the same growth/search schedule on bare `Index` shards (no per-key Python
-objects, no WAL) at any size."""
+Handler level: `put_arrays` (one add_items + one key-store append + one WAL group commit per shard, vectors logged
+by reference), shards that start small and grow in place, `LocalCoordinator.search_batch` (GPU merge), a searcher
+thread that keeps searching WHILE the inserts run (p50 latency against the idle p50), a sampled oracle check of
+the final state and a checkpoint + WAL-tail restart of one shard.  Default 1/20 scale; `--start 1000000 --end
+5000000 --insert-batch 200000` is BASELINE config 5 at full size (needs ~12 GB of disk for the raw-vector files).
+`--level index` runs the same growth/search schedule on bare `Index` shards."""
 import argparse, json, os, shutil, sys, tempfile, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -29,6 +31,8 @@ ap.add_argument("--dim", type=int, default=512)
 ap.add_argument("--k", type=int, default=10)
 ap.add_argument("--level", default="handler", choices=["handler", "index"])
 ap.add_argument("--searches-per-step", type=int, default=5)
+ap.add_argument("--tmp", default="", help="directory for the datanode storage roots (default: the system temp dir)")
+ap.add_argument("--fsync", action="store_true", help="fsync the WAL / key store on every commit")
 a = ap.parse_args()
 
 keys_of = lambda lo, hi: [f"k{r:09d}" for r in range(lo, hi)]
@@ -51,72 +55,95 @@ def merged_search(search_fns, nq):
 
 
 if a.level == "handler":
-    root = tempfile.mkdtemp(prefix="vdb_mixed_")
+    import importlib.util, statistics, threading
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec); sys.modules["bench_mod"] = bench; spec.loader.exec_module(bench)
+    c_ref.set_threads(c_ref.host_cores())
+    root = tempfile.mkdtemp(prefix="vdb_mixed_", dir=a.tmp or None)
     try:
         handlers = {f"node_{s}": vdb.GpuVectorNodeHandler(f"node_{s}", root, space="cosine", dim=a.dim,
-                                                          max_elements=a.end, checkpoint_every=0, fsync=False)
+                                                          max_elements=max(a.start // a.shards, 1024), checkpoint_every=0,
+                                                          fsync=a.fsync)
                     for s in range(a.shards)}
-        node_ids = list(handlers)
-        mapping = vdb.assign_shards_to_nodes(node_ids, a.shards)
-        # global row id <-> (shard, local hnsw id): results are compared through keys
+        coord = vdb.LocalCoordinator(handlers, shard_count=a.shards)
+        node_ids = coord.node_ids
+
         def put_rows(lo, hi):
+            """one put_arrays per shard: add_items + key-store append + WAL group commit (vectors by reference)"""
             rows = c_ref.synth_rows(R.SEED_DB, lo, hi - lo, a.dim)
-            per = {n: [] for n in node_ids}
-            for r, key in enumerate(keys_of(lo, hi)):
-                per[mapping[vdb.get_shard_id(key, a.shards)]["master"]].append(
-                    vdb.VectorData(key=key, vector=rows[r].tolist(), metadata={"row": lo + r}))
+            keys = keys_of(lo, hi)
+            owner = np.array([node_ids.index(coord.mapping[vdb.get_shard_id(k, a.shards)]["master"]) for k in keys])
             t = time.perf_counter()
-            for n, items in per.items():
-                resp = handlers[n].put_batch(items)
+            for s, n in enumerate(node_ids):
+                sel = np.nonzero(owner == s)[0]
+                resp = handlers[n].put_arrays([keys[i] for i in sel], rows[sel])
                 assert resp.success, resp.message
             return time.perf_counter() - t
 
-        def search_all():
-            outs = [handlers[n].search_batch(queries, a.k) for n in node_ids]
-            merged = []
-            for qi in range(a.batch):
-                cand = [(s, k) for ks, ss in outs for k, s in zip(ks[qi], ss[qi])]
-                cand.sort()
-                merged.append(cand[:a.k])
-            return merged
+        lat_busy, lat_idle, stop = [], [], threading.Event()
+
+        def searcher(sink):
+            while not stop.is_set():
+                t = time.perf_counter()
+                coord.search_batch(queries, a.k)
+                sink.append(time.perf_counter() - t)
 
         n = 0
         wal0 = 0
         while n < a.end:
             hi = min(a.end, n + (a.start if n == 0 else a.insert_batch))
+            sink = []
+            stop.clear()
+            th = threading.Thread(target=searcher, args=(sink,)) if n else None    # searches DURING the inserts
+            if th: th.start()
             dt_ins = put_rows(n, hi)
+            stop.set()
+            if th: th.join()
             wal1 = sum(dir_bytes(handlers[x].wal_dir) for x in node_ids)
-            search_all()
-            t = time.perf_counter()
+            coord.search_batch(queries, a.k)
+            idle = []
             for _ in range(a.searches_per_step):
-                res = search_all()
-            dt_s = (time.perf_counter() - t) / a.searches_per_step
-            report["steps"].append({"rows": hi, "insert_rows_per_s": (hi - n) / dt_ins, "wal_MB_per_s": (wal1 - wal0) / dt_ins / 1e6,
-                                    "search_qps": a.batch / dt_s, "search_ms": 1e3 * dt_s})
+                t = time.perf_counter()
+                res = coord.search_batch(queries, a.k)
+                idle.append(time.perf_counter() - t)
+            dt_s = statistics.median(idle)
+            step = {"rows": hi, "insert_rows_per_s": (hi - n) / dt_ins, "wal_MB_per_s": (wal1 - wal0) / dt_ins / 1e6,
+                    "search_qps": a.batch / dt_s, "search_ms_p50_idle": 1e3 * dt_s}
+            if sink:
+                step["search_ms_p50_during_inserts"] = 1e3 * statistics.median(sink)
+                step["searches_during_inserts"] = len(sink)
+            report["steps"].append(step)
             n, wal0 = hi, wal1
-        # final state against the oracle
-        stored = c_ref.normalize(c_ref.synth_rows(R.SEED_DB, 0, a.end, a.dim))
-        want_l, want_d, _ = c_ref.knn(queries, stored, None, a.k, "cosine")
+        report["capacity_per_shard"] = [handlers[x].hnsw_index.get_max_elements() for x in node_ids]
+        # final state against the oracle: sampled queries, exact CPU scan of the whole set (chunked)
+        q_idx = np.unique(np.linspace(0, a.batch - 1, min(64, a.batch)).astype(np.int64))
+        wl = bench.Workload("config5", a.end, a.dim, a.k, "cosine", "f32", a.batch)
+        want_l, want_d, info = bench.oracle_topk(wl, q_idx, budget_s=600.0)
+        got_keys, got_scores = res
         bad = 0
-        for qi in range(a.batch):
-            got = [int(k[1:]) for _, k in res[qi]]
-            if got != want_l[qi].tolist():
+        for j, qi in enumerate(q_idx):
+            got = [int(k[1:]) for k in got_keys[qi]]
+            if got != want_l[j].tolist():
                 bad += 1
-                gd = np.array([s for s, _ in res[qi]], np.float32)
-                assert np.allclose(gd, want_d[qi], rtol=1e-5, atol=1e-6), f"query {qi}: {got} vs {want_l[qi]}"
-        report["oracle_parity"] = f"{a.batch} queries, {bad} differ only by distance ties within 1e-5"
-        # cold restart: checkpoint half-way is not used here (checkpoint_every=0) -> full WAL replay
+            assert np.allclose(np.array(got_scores[qi], np.float32), want_d[j], rtol=1e-5, atol=1e-6), f"query {qi}"
+        report["oracle_parity"] = f"{len(q_idx)} sampled queries vs exact CPU scan of {a.end} rows: {bad} with a different id order (distance ties within 1e-5), all distances within 1e-5"
+        # cold restart of shard 0: checkpoint + WAL tail
         h0 = handlers[node_ids[0]]
-        live_keys = sorted(h0._by_key)
+        live = len(h0.store)
+        t = time.perf_counter(); h0.save_checkpoint(); report["checkpoint_s"] = time.perf_counter() - t
+        extra = c_ref.synth_rows(R.SEED_DB, a.end, 1000, a.dim)
+        h0.put_arrays([f"tail{i}" for i in range(1000)], extra)                    # after the checkpoint: replayed from the WAL
+        k0, s0 = h0.search_batch(queries[:16], a.k)
+        h0.store.close(); h0.hnsw_index.close()
         t = time.perf_counter()
-        h0.hnsw_index.close()
-        h0b = vdb.GpuVectorNodeHandler(node_ids[0], root, space="cosine", dim=a.dim, max_elements=a.end,
-                                       checkpoint_every=0, fsync=False)
-        report["wal_replay_s"] = time.perf_counter() - t
-        assert sorted(h0b._by_key) == live_keys, "WAL replay lost or invented keys"
+        h0b = vdb.GpuVectorNodeHandler(node_ids[0], root, space="cosine", dim=a.dim, max_elements=1024, checkpoint_every=0,
+                                       fsync=a.fsync)
+        report["restart_s"] = time.perf_counter() - t
+        assert len(h0b.store) == live + 1000, "restart lost or invented keys"
         k1, s1 = h0b.search_batch(queries[:16], a.k)
-        k0 = [[k for _, k in r] for r in res[:16]]
-        report["wal_replay"] = f"{len(live_keys)} keys restored on shard 0"
+        assert k1 == k0 and np.allclose(np.array(s1), np.array(s0), rtol=1e-6, atol=1e-7)
+        report["restart"] = f"shard 0: {live} keys from the checkpoint + 1000 from the WAL tail, searches identical"
+        report["disk_bytes"] = dir_bytes(root)
     finally:
         shutil.rmtree(root, ignore_errors=True)
 else:
