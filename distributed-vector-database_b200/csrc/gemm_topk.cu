@@ -788,6 +788,27 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectParams p) {
         if (threadIdx.x == 0) { p.cnt[q] = 0; p.thr[q] = __int_as_float(0x7f800000); }   // too few live rows probed
         return;
     }
+    if (probe && n <= SELECT_COUNT_MAX) {
+        // the probe's chunk minima (128 per query with 16 probe tiles): ranks by counting, as for the levels below
+        const bool tight = p.margin > 0.0f && n_valid >= p.k && p.k < want;
+        for (int i = threadIdx.x; i < n; i += THREADS) {
+            const uint64_t key = sk[i];
+            if (key == KEY_SENTINEL) continue;
+            int rank = 0;
+#pragma unroll 8
+            for (int j = 0; j < n; ++j) rank += sk[j] < key;
+            if (rank == want - 1) s_tr = (uint32_t)(key >> 32);
+            if (rank == p.k - 1) s_ak = (uint32_t)(key >> 32);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float thr = ordered_to_float(s_tr);
+            if (tight) thr = fminf(thr, tight_thr(s_ak));
+            p.cnt[q] = 0;
+            p.thr[q] = thr;
+        }
+        return;
+    }
     if (!probe && n_valid <= p.kp) {
         // everything valid is kept
         for (int i = threadIdx.x; i < n; i += THREADS) {
@@ -904,63 +925,6 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectParams p) {
         if (tight) thr = fminf(thr, tight_thr(s_ak));
         p.thr[q] = thr;
     }
-}
-
-// K2s, probe form: one WARP per query.  The probe wrote probe_cnt chunk minima per query at fixed positions (128 for
-// the default 16 probe tiles); the first threshold is min(thr_rank-th smallest, k-th smallest + margin * eps).  The
-// values sit in registers (up to 32 per lane); a rank is found by a bitwise binary search on the 32 value bits (32
-// rounds of compare + warp add) -- no shared memory, no barriers; 8192 queries take a few microseconds instead of the
-// ~35 of the block-per-query radix select.
-constexpr int PROBE_WARP_MAX_PER_LANE = 32;
-__device__ __forceinline__ uint32_t warp_kth_smallest(const uint32_t (&v)[PROBE_WARP_MAX_PER_LANE], int per_lane, int rank) {
-    // smallest value x with #(values <= x) >= rank, values spread over the lanes' registers (invalid = 0xFFFFFFFF)
-    uint32_t ans = 0;
-#pragma unroll 1
-    for (int bit = 31; bit >= 0; --bit) {
-        const uint32_t t = ans | (1u << bit);
-        int c = 0;
-#pragma unroll
-        for (int j = 0; j < PROBE_WARP_MAX_PER_LANE; ++j)
-            if (j < per_lane) c += v[j] < t;
-        c = __reduce_add_sync(0xffffffffu, c);
-        if (c < rank) ans = t;
-    }
-    return ans;
-}
-
-__global__ void __launch_bounds__(256) probe_select_warp_kernel(const SelectParams p, const int nq) {
-    pdl_prologue();
-    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (q >= nq) return;
-    const uint64_t* b = p.buf + (size_t)q * p.cap;
-    const int n = min(p.probe_cnt, p.cap), per_lane = (n + 31) >> 5;
-    uint32_t v[PROBE_WARP_MAX_PER_LANE];
-    int valid = 0;
-#pragma unroll
-    for (int j = 0; j < PROBE_WARP_MAX_PER_LANE; ++j) {
-        v[j] = 0xFFFFFFFFu;
-        const int i = j * 32 + lane;
-        if (j < per_lane && i < n) {
-            const uint64_t key = b[i];
-            if (key != KEY_SENTINEL) {
-                const uint32_t row = (uint32_t)key;
-                if (row < p.n_rows && !(p.tomb && ((p.tomb[row >> 5] >> (row & 31)) & 1u))) { v[j] = (uint32_t)(key >> 32); ++valid; }
-            }
-        }
-    }
-    const int n_valid = __reduce_add_sync(0xffffffffu, valid);
-    float thr = __int_as_float(0x7f800000);                       // too few live rows probed: no threshold
-    if (n_valid >= p.min_rank) {
-        const int want = n_valid >= p.thr_rank ? p.thr_rank : n_valid;
-        thr = ordered_to_float(warp_kth_smallest(v, per_lane, want));
-        if (p.margin > 0.0f && n_valid >= p.k && p.k < want) {
-            const float a = ordered_to_float(warp_kth_smallest(v, per_lane, p.k));
-            const float off = p.em.metric == 0 ? p.qn2[q] : 1.0f;
-            const float t = a + p.margin * approx_eps(p.em, p.qn2[q], __uint_as_float(*p.max_sqnorm_bits), a + off);
-            if (t == t) thr = fminf(thr, t);
-        }
-    }
-    if (lane == 0) { p.cnt[q] = 0; p.thr[q] = thr; }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1257,7 +1221,20 @@ __global__ void __launch_bounds__(RW_MAX_THREADS) rerank_window_kernel(const Rer
     const int m1 = s_m1;
     // ---- 3. a_k and the final window
     uint32_t w2 = w1;
-    if (m1 > k) w2 = min(w1, window_bits(block_kth_bits(lk, m1, k, hist, sh)));
+    if (m1 > k) {
+        if (m1 <= 512) {                       // a few dozen keys as a rule: rank by counting (one barrier) instead of
+            for (int t = tid; t < m1; t += RW_THREADS) {                       // a radix select (up to twelve)
+                const uint64_t key = lk[t];
+                int rank = 0;
+                for (int j = 0; j < m1; ++j) rank += lk[j] < key;
+                if (rank == k - 1) sh[5] = (uint32_t)(key >> 32);
+            }
+            __syncthreads();
+            w2 = min(w1, window_bits(sh[5]));
+        } else {
+            w2 = min(w1, window_bits(block_kth_bits(lk, m1, k, hist, sh)));
+        }
+    }
     // ---- 4. window keys -> sk (stage 2 has finished reading it: barriers above)
     for (int i0 = 0; i0 < m1; i0 += RW_THREADS) {
         const int i = i0 + tid;
@@ -1660,11 +1637,6 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
     };
     auto run_select = [&](int probe_cnt, int thr_rank) -> cudaError_t {
         sp.probe_cnt = probe_cnt; sp.thr_rank = thr_rank; sp.min_rank = std::min(kq, thr_rank);
-        if (probe_cnt > 0 && probe_cnt <= 32 * PROBE_WARP_MAX_PER_LANE && env_int("VDB_PROBE_WARP", 1)) {
-            cudaError_t le = launch_pdl(probe_select_warp_kernel, dim3((unsigned)((a.nq + 7) / 8)), dim3(256), 0, st, sp, (int)a.nq);
-            count_launch();
-            return le != cudaSuccess ? le : cudaGetLastError();
-        }
         // one block per query; thousands of queries with a few hundred keys each: small blocks, so that more
         // of them are resident and the barrier chain of a block is short
         cudaError_t le;
