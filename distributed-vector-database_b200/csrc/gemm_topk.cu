@@ -43,6 +43,7 @@
 #include <mutex>
 #include <vector>
 
+#include "block_select.cuh"
 #include "common.cuh"
 #include "gemm_topk.h"
 #include "kernels.h"
@@ -636,78 +637,6 @@ struct SelectParams {
     const float* qn2; const unsigned int* max_sqnorm_bits;
     EpsModel em;
 };
-
-// value bits of the `rank`-th smallest (1-based) of the n >= rank keys in sk[].  Radix select
-// from the highest byte in which the values differ: the bytes above it are common to all keys and would send every
-// atomicAdd of a pass to ONE histogram bin.  Stops as soon as the bin that holds the rank has a single key.
-__device__ __forceinline__ uint32_t block_kth_bits(const uint64_t* sk, int n, int rank, int* hist, uint32_t* sh) {
-    // sh[0] = min, sh[1] = max, sh[2] = prefix, sh[3] = rank, sh[4] = count in the chosen bin
-    const int tid = threadIdx.x, RW_THREADS = blockDim.x;
-    if (tid == 0) { sh[0] = 0xFFFFFFFFu; sh[1] = 0u; }
-    __syncthreads();
-    uint32_t lo = 0xFFFFFFFFu, hi = 0u;
-    for (int i = tid; i < n; i += RW_THREADS) {
-        const uint32_t v = (uint32_t)(sk[i] >> 32);
-        lo = min(lo, v); hi = max(hi, v);
-    }
-    lo = __reduce_min_sync(0xffffffffu, lo);
-    hi = __reduce_max_sync(0xffffffffu, hi);
-    if ((tid & 31) == 0) { atomicMin(&sh[0], lo); atomicMax(&sh[1], hi); }
-    __syncthreads();
-    lo = sh[0]; hi = sh[1];
-    if (lo == hi) return lo;
-    int shift = ((31 - __clz(lo ^ hi)) >> 3) << 3;          // byte of the highest differing bit
-    uint32_t mask = shift == 24 ? 0u : ~((1u << (shift + 8)) - 1u);
-    if (tid == 0) { sh[2] = lo & mask; sh[3] = (uint32_t)rank; sh[4] = 0u; }
-    for (; shift >= 0; shift -= 8) {
-        for (int i = tid; i < 256; i += RW_THREADS) hist[i] = 0;
-        __syncthreads();
-        const uint32_t prefix = sh[2];
-        for (int i = tid; i < n; i += RW_THREADS) {
-            const uint32_t v = (uint32_t)(sk[i] >> 32);
-            if ((v & mask) == prefix) atomicAdd(&hist[(v >> shift) & 255], 1);
-        }
-        __syncthreads();
-        if (tid < 32) {
-            int local[8], sum = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { local[i] = hist[tid * 8 + i]; sum += local[i]; }
-            int incl = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (tid >= o) incl += t;
-            }
-            const int excl = incl - sum;
-            const int r = (int)sh[3];
-            if (r > excl && r <= incl) {
-                int run = excl;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (r > run && r <= run + local[i]) {
-                        sh[2] = prefix | ((uint32_t)(tid * 8 + i) << shift);
-                        sh[3] = (uint32_t)(r - run);
-                        sh[4] = (uint32_t)local[i];
-                    }
-                    run += local[i];
-                }
-            }
-        }
-        mask |= 0xFFu << shift;
-        __syncthreads();
-        if (sh[4] == 1u && shift > 0) {            // one key left under this prefix: it is the answer
-            const uint32_t prefix1 = sh[2];
-            __syncthreads();
-            for (int i = tid; i < n; i += RW_THREADS) {
-                const uint32_t v = (uint32_t)(sk[i] >> 32);
-                if ((v & mask) == prefix1) sh[2] = v;
-            }
-            __syncthreads();
-            break;
-        }
-    }
-    return sh[2];
-}
 
 // Radix select on the 32 distance bits (4 passes of 8 bits): O(n) instead of a full sort.  Keys whose
 // distance bits equal the KP-th value are taken in arrival order until KP are kept.  Output unordered.
@@ -1395,7 +1324,8 @@ static int level_growth(int k) {
 // rows gets a buffer that holds every row, because its probe may see fewer live chunks than the threshold rank
 // and then publishes no threshold (the single level that follows keeps everything)
 static int cap_for(int kp, size_t n_rows) {
-    int cap = 16 * kp;
+    static const int mult = std::max(8, env_int("VDB_CAP_MULT", 16));
+    int cap = mult * kp;
     if (n_rows <= (size_t)32 * kp)
         while ((size_t)cap < n_rows) cap <<= 1;
     return cap;

@@ -12,7 +12,8 @@ struct ScanParams {
     uint32_t row_bytes;      // ld * sizeof(T), multiple of 512
     uint32_t ld;             // padded row length in elements
     uint32_t n_rows;
-    const uint32_t* labels;  // [n_rows] or null (label == row)
+    const uint32_t* labels;  // [n_rows], or null: label == label_base + row (the usual case: ids handed out in insertion
+    uint32_t label_base;     // order).  A row that passes the threshold then costs the consumers no global load.
     const uint32_t* tomb;    // bitmap, 1 = deleted, or null
     const float* q;          // [nq][ld] prepared queries (fp32, zero padded) -- or:
     const float* q_raw;      // [nq][dim] raw queries, prepared inside the kernel (saves a launch)
@@ -23,8 +24,17 @@ struct ScanParams {
     int stages, ring;        // filled by the launcher (copy-ring stages, candidate-ring slots)
     int dbg;                 // experiments (VDB_SCAN_DBG): 1 = no FMA loop, 2 = no L2 policy hint, 4 = no select
     uint64_t* out_keys;      // [nq][grid][k]
+    // In-kernel merge (merge_group > 0): the last CTA of every group of `merge_group` CTAs reduces the group's lists,
+    // the last group to finish reduces the group results and writes the final answer -- no merge launch after the scan.
+    int merge_group;         // CTAs per group (>= grid: one level); 0 = leave the per-CTA lists to the merge kernel
+    unsigned int* merge_ctr; // [1 + groups] arrival counters, zero before the launch; the kernel leaves them zero
+    uint64_t* group_keys;    // [nq][groups][k] group results (two levels only)
+    int64_t* out_ids;        // [nq][k] final results (-1 / +inf padded), out_counts optional
+    float* out_dist;
+    int* out_counts;
 };
-struct ScanPlan { int grid, ctas_per_sm, stages; size_t smem; };   // grid == 0: does not fit
+struct ScanPlan { int grid, ctas_per_sm, stages; size_t smem; int merge_group, merge_groups; };   // grid == 0: does not fit
+constexpr int SCAN_MERGE_KEYS = 4096;    // keys one in-kernel merge step holds in shared memory
 ScanPlan scan_plan(int nq, uint32_t ld, uint32_t row_bytes, int k, uint32_t n_rows, int num_sms);
 cudaError_t launch_scan_topk(ScanParams p, bool f16, const ScanPlan& pl, cudaStream_t st);
 int scan_max_k(int nq_t, int ld, uint32_t row_bytes);

@@ -16,8 +16,10 @@
 //                 wait for an insert (measured: inserts under a lock on the consumer path cost 50 us of a
 //                 335 us scan; with the selector the scan runs at the speed of the bare copy ring).
 // Each CTA leaves a sorted list of k keys per query; merge_topk.cu reduces grid lists to one.
+#include <algorithm>
 #include <cstdlib>
 
+#include "block_select.cuh"
 #include "common.cuh"
 #include "kernels.h"
 
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_topk_kernel(const ScanPa
             // high word (distance bits) of the list tail = current threshold of query qi
             const uint32_t tail_hi = reinterpret_cast<volatile uint32_t*>(lists + (size_t)qi * k + (k - 1))[1];
             bool pass = valid && float_to_ordered(dist) <= tail_hi;
-            uint32_t label = row;
+            uint32_t label = p.label_base + row;
             if (pass) {
                 if (p.tomb && ((p.tomb[row >> 5] >> (row & 31)) & 1u)) pass = false;
                 else if (p.labels) label = p.labels[row];
@@ -306,6 +308,66 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_topk_kernel(const ScanPa
         const int qi = i / k, j = i - qi * k;
         p.out_keys[((size_t)qi * gridDim.x + blockIdx.x) * k + j] = lists[i];
     }
+    if (p.merge_group <= 0) return;
+
+    // ---------------- in-kernel merge: last CTA of a group, then last group ----------------
+    // The copy ring (>= 64 KB, idle now) holds the keys of one merge step and its scratch; the candidate ring
+    // (>= 4 KB) holds the histogram.  Lists written by other CTAs are read with L1-bypassing loads after the
+    // counter handshake (fence + atomic on both sides).
+    __shared__ int s_last;
+    uint64_t* m_in = reinterpret_cast<uint64_t*>(stage_base);
+    uint64_t* m_tmp = m_in + SCAN_MERGE_KEYS;
+    int* hist = reinterpret_cast<int*>(ring);
+    uint32_t* sh = reinterpret_cast<uint32_t*>(hist + 256);
+    uint64_t* m_out = reinterpret_cast<uint64_t*>(sh + 8);          // [k] behind the histogram (k <= 384 with the 4 KB ring)
+    const int grid = (int)gridDim.x, groups = (grid + p.merge_group - 1) / p.merge_group;
+    const int group = (int)blockIdx.x / p.merge_group;
+    const int g0 = group * p.merge_group, g1 = min(grid, g0 + p.merge_group);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&p.merge_ctr[1 + group], 1u) == (unsigned)(g1 - g0 - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    auto emit = [&](int qi, int cnt) {      // m_out[0..k) -> final outputs of query qi
+        for (int j = threadIdx.x; j < k; j += SCAN_THREADS) {
+            const uint64_t key = m_out[j];
+            const bool real = key != KEY_SENTINEL;
+            p.out_ids[(size_t)qi * k + j] = real ? (int64_t)key_label(key) : -1;
+            p.out_dist[(size_t)qi * k + j] = real ? key_dist(key) : __int_as_float(0x7f800000);
+        }
+        if (threadIdx.x == 0 && p.out_counts) p.out_counts[qi] = cnt;
+    };
+    for (int qi = 0; qi < p.nq; ++qi) {
+        const uint64_t* src = p.out_keys + ((size_t)qi * grid + g0) * k;      // the group's lists are contiguous
+        const int n = (g1 - g0) * k;
+        for (int i = threadIdx.x; i < n; i += SCAN_THREADS) m_in[i] = __ldcg(src + i);
+        __syncthreads();
+        const int cnt = block_topk_sorted(m_in, n, k, m_tmp, m_out, hist, sh);
+        if (groups == 1) emit(qi, cnt);
+        else for (int j = threadIdx.x; j < k; j += SCAN_THREADS) p.group_keys[((size_t)qi * groups + group) * k + j] = m_out[j];
+        __syncthreads();
+    }
+    if (groups == 1) {
+        if (threadIdx.x == 0) p.merge_ctr[1] = 0;                  // leave the counters zero for the next launch
+        return;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&p.merge_ctr[0], 1u) == (unsigned)(groups - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int qi = 0; qi < p.nq; ++qi) {
+        const uint64_t* src = p.group_keys + (size_t)qi * groups * k;
+        const int n = groups * k;
+        for (int i = threadIdx.x; i < n; i += SCAN_THREADS) m_in[i] = __ldcg(src + i);
+        __syncthreads();
+        const int cnt = block_topk_sorted(m_in, n, k, m_tmp, m_out, hist, sh);
+        emit(qi, cnt);
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i <= groups; i += SCAN_THREADS) p.merge_ctr[i] = 0;
 }
 
 static int scan_ring_slots(int k) { return k > 32 ? SCAN_RING_LARGE : SCAN_RING_SMALL; }
@@ -319,8 +381,12 @@ static cudaError_t launch_t(const ScanParams& p, int grid, size_t smem, cudaStre
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(scan_topk_kernel<T, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             227 * 1024);
+        cudaFuncAttributes fa{};
+        cudaError_t e = cudaFuncGetAttributes(&fa, scan_topk_kernel<T, NQ>);
+        if (e != cudaSuccess) return e;
+        // static + dynamic shared memory of a block may not exceed 227 KB
+        e = cudaFuncSetAttribute(scan_topk_kernel<T, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 227 * 1024 - (int)fa.sharedSizeBytes);
         if (e != cudaSuccess) return e;
         configured[dev & 63] = true;
     }
@@ -330,7 +396,7 @@ static cudaError_t launch_t(const ScanParams& p, int grid, size_t smem, cudaStre
 }
 
 int scan_max_k(int nq_t, int ld, uint32_t row_bytes) {
-    const size_t budget = 227 * 1024;
+    const size_t budget = 227 * 1024 - 256;      // 256 bytes: the kernel's static shared memory
     const size_t min_stage = (size_t)2 * row_bytes * SCAN_STAGE_ROWS;
     // conservative: counted with the large candidate ring whatever k turns out to be
     const size_t fixed0 = scan_fixed_smem(nq_t, ld, 0, 8) + (size_t)(SCAN_RING_LARGE - SCAN_RING_SMALL) * 9;
@@ -346,7 +412,7 @@ ScanPlan scan_plan(int nq, uint32_t ld, uint32_t row_bytes, int k, uint32_t n_ro
     ScanPlan pl{};
     const int nq_t = nq <= 1 ? 1 : nq <= 2 ? 2 : nq <= 4 ? 4 : 8;
     const size_t stage_bytes = (size_t)row_bytes * SCAN_STAGE_ROWS;
-    const size_t sm_budget = 227 * 1024;
+    const size_t sm_budget = 227 * 1024 - 256;   // 256 bytes: the kernel's static shared memory
     int ctas = 2, stages = 0;
     if (const char* e = getenv("VDB_SCAN_CTAS")) ctas = atoi(e);
     if (ctas < 1) ctas = 1;
@@ -368,6 +434,17 @@ ScanPlan scan_plan(int nq, uint32_t ld, uint32_t row_bytes, int k, uint32_t n_ro
     const uint32_t nchunks = (n_rows + SCAN_STAGE_ROWS - 1) / SCAN_STAGE_ROWS;
     pl.grid = (int)min((uint32_t)(num_sms * ctas), nchunks);
     if (pl.grid < 1) pl.grid = 1;
+    // In-kernel merge for one or two queries (their merges run one after the other on the last CTA; wider passes keep
+    // the merge kernel, one block per query): groups of CTAs whose lists fit one merge step, at most two levels.
+    pl.merge_group = pl.merge_groups = 0;
+    static const bool fuse = [] { const char* e = getenv("VDB_SCAN_FUSED_MERGE"); return !(e && e[0] == '0'); }();
+    const size_t merge_bytes = 2 * (size_t)SCAN_MERGE_KEYS * sizeof(uint64_t);
+    if (fuse && nq_t <= 2 && k <= SCAN_MERGE_KEYS && (size_t)stages * stage_bytes >= merge_bytes &&
+        (size_t)scan_ring_slots(k) * 8 >= 256 * 4 + 32 + (size_t)k * 8) {
+        const int per_group = std::max(1, SCAN_MERGE_KEYS / k);
+        const int groups = (pl.grid + per_group - 1) / per_group;
+        if ((size_t)groups * k <= (size_t)SCAN_MERGE_KEYS) { pl.merge_group = per_group; pl.merge_groups = groups; }
+    }
     return pl;
 }
 

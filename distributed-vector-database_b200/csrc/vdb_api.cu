@@ -59,6 +59,8 @@ struct Workspace {
     float* d_q = nullptr;     size_t q_cap = 0;        // prepared queries [nq][ld]
     float* d_qn2 = nullptr;   size_t qn2_cap = 0;
     uint64_t* d_keys = nullptr; size_t keys_cap = 0;   // per-CTA candidate lists
+    unsigned int* d_scan_ctr = nullptr;                // arrival counters of the scan kernel's in-kernel merge (kept zero)
+    uint64_t* d_group_keys = nullptr;                  // its group results: 2 queries x SCAN_MERGE_KEYS keys
     int64_t* d_ids = nullptr; size_t ids_cap = 0;      // [nq*k]
     float* d_dist = nullptr;  size_t dist_cap = 0;
     int* d_cnt = nullptr;     size_t cnt_cap = 0;
@@ -123,7 +125,7 @@ struct vdb {
     mutable std::shared_mutex mu;
     std::mutex wmu;                   // writers, one at a time (lock order: wmu, then mu)
     // label -> row
-    bool affine = true;
+    std::atomic<bool> affine{true};   // labels are label_base + row: kernels need no label array for the rows they see
     int64_t label_base = 0;
     std::unordered_map<int64_t, uint32_t> map;
     std::vector<uint64_t> h_dead;     // host mirror of the tombstone bitmap (writers only)
@@ -234,6 +236,8 @@ void free_workspace(Workspace* w) {
     if (w->d_q) cudaFree(w->d_q);
     if (w->d_qn2) cudaFree(w->d_qn2);
     if (w->d_keys) cudaFree(w->d_keys);
+    if (w->d_scan_ctr) cudaFree(w->d_scan_ctr);
+    if (w->d_group_keys) cudaFree(w->d_group_keys);
     if (w->d_ids) cudaFree(w->d_ids);
     if (w->d_dist) cudaFree(w->d_dist);
     if (w->d_cnt) cudaFree(w->d_cnt);
@@ -314,7 +318,11 @@ int scan_prepared(vdb* db, Workspace* ws, const float* d_qp, size_t nq, int k, i
     sp.row_bytes = (uint32_t)db->row_bytes();
     sp.ld = db->ld;
     sp.n_rows = (uint32_t)n;
-    sp.labels = db->labels;
+    // a search's snapshot [0, n) is affine if the shard is when the search starts: rows that break the pattern are
+    // appended behind it
+    const bool affine = db->affine.load();
+    sp.labels = affine ? nullptr : db->labels;
+    sp.label_base = affine ? (uint32_t)db->label_base : 0u;
     sp.tomb = db->any_dead.load() ? db->tomb : nullptr;
     sp.k = k;
     sp.metric = db->metric == VDB_L2 ? 0 : 1;
@@ -325,6 +333,18 @@ int scan_prepared(vdb* db, Workspace* ws, const float* d_qp, size_t nq, int k, i
     if (pl.grid == 0) return fail(VDB_EINVAL, "k too large for the scan kernel at this dimension");
     const int grid = pl.grid;
     CU_TRY(grow(ws->d_keys, ws->keys_cap, nq * (size_t)grid * k));
+    const bool fused_merge = pl.merge_group > 0 && nq <= 2;     // one pass whose last CTAs also merge the lists
+    if (fused_merge) {
+        if (!ws->d_scan_ctr) {
+            CU_TRY(cudaMalloc((void**)&ws->d_scan_ctr, (SCAN_MERGE_KEYS + 1) * sizeof(unsigned int)));
+            CU_TRY(cudaMemsetAsync(ws->d_scan_ctr, 0, (SCAN_MERGE_KEYS + 1) * sizeof(unsigned int), st));
+            CU_TRY(cudaMalloc((void**)&ws->d_group_keys, 2 * (size_t)SCAN_MERGE_KEYS * sizeof(uint64_t)));
+        }
+        sp.merge_group = pl.merge_group;
+        sp.merge_ctr = ws->d_scan_ctr;
+        sp.group_keys = ws->d_group_keys;
+        sp.out_ids = d_ids; sp.out_dist = d_dist; sp.out_counts = d_cnt;
+    }
     for (size_t g = 0; g < nq; g += (size_t)group) {
         sp.nq = (int)std::min<size_t>((size_t)group, nq - g);
         if (raw) {   // queries as the caller gave them: normalised / padded inside the kernel
@@ -341,6 +361,7 @@ int scan_prepared(vdb* db, Workspace* ws, const float* d_qp, size_t nq, int k, i
         }
         db->stat_scan_passes.fetch_add(1);
     }
+    if (fused_merge) return VDB_OK;
     MergeParams mp{};
     mp.nq = nq;
     mp.k_out = k;
