@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_topk_kernel(const ScanPa
                 continue;
             }
             __threadfence_block();
-            const int q = lane < n ? reinterpret_cast<volatile uint8_t*>(ring_q)[slot] : 0;
+            const int q = (NQ > 1 && lane < n) ? reinterpret_cast<volatile uint8_t*>(ring_q)[slot] : 0;
             if (lane < n) vring[slot] = KEY_SENTINEL;
             __syncwarp();
             head += n;
@@ -291,8 +291,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_topk_kernel(const ScanPa
                 }
                 if (pass) {
                     const uint32_t slot = (base + __popc(m & ((1u << lane) - 1))) & ring_mask;
-                    ring_q[slot] = (uint8_t)qi;
-                    __threadfence_block();
+                    if constexpr (NQ > 1) {     // which query the key belongs to, visible before the key itself
+                        ring_q[slot] = (uint8_t)qi;
+                        __threadfence_block();
+                    }
                     reinterpret_cast<volatile uint64_t*>(ring)[slot] = make_key(dist, label);
                 }
             }
