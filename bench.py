@@ -487,17 +487,39 @@ class Arm:
                 sl = nq // world
                 pin_q = torch.from_numpy(qh[rank * sl:(rank + 1) * sl] if even else qh).pin_memory()
                 out = [None]
+                if even:
+                    # the serving steady state: two batches in flight (ShardedIndex.submit_host / collect) -- the upload
+                    # + all-gather of batch i+1 overlap the search of batch i; every step still uploads its queries
+                    # from page-locked host memory and reads its results back
+                    pending = []
 
-                def step():
-                    out[0] = sx.search_host(pin_q, k, whole_batch=not even, out=out[0])
-                    return out[0]
+                    def step():
+                        pending.append(sx.submit_host(pin_q, k))
+                        if len(pending) == 2:
+                            out[0] = sx.collect(pending.pop(0))
+                        return out[0]
+
+                    def drain():
+                        while pending:
+                            out[0] = sx.collect(pending.pop(0))
+                else:
+                    def step():
+                        out[0] = sx.search_host(pin_q, k, whole_batch=True, out=out[0])
+                        return out[0]
+
+                    def drain():
+                        pass
 
             for _ in range(nwarm):
                 step()
+            if sx is not None:
+                drain()
             self.barrier()
             t0 = time.perf_counter()
             for _ in range(nsteps):
                 step()
+            if sx is not None:
+                drain()                                     # the last results are on the host before the clock stops
             torch.cuda.synchronize()
             dt = torch.tensor([time.perf_counter() - t0], device=dev)
             if world > 1:

@@ -361,6 +361,58 @@ class ShardedIndex:
                                            a_ids.data_ptr(), 1, self.ix.device, stream), "merge")
         return a_dd[lo:hi], a_ids[lo:hi]
 
+    # ---- pipelined client calls: upload of batch i+1 overlaps the search of batch i ---------------------------
+    def submit_host(self, q, k: int):
+        """Asynchronous `search_host` for even batches (every rank passes ITS rows of the batch, page-locked): the
+        upload + NVLink all-gather of the queries runs on a copy stream into one of two query buffers, the search,
+        the exchange + merge and the download of the results are enqueued on the current stream behind it.  Returns
+        a ticket for `collect`.  With two batches in flight the host<->device copies and the all-gather of one batch
+        hide behind the search of the other (a server's steady state); at most two tickets may be outstanding."""
+        torch, dist = self._torch, self._dist
+        if not torch.is_tensor(q):
+            q = torch.from_numpy(q)
+        n = int(q.shape[0])
+        if n * self.world > self.max_batch:
+            raise ValueError("batch beyond what this ShardedIndex was sized for")
+        if not hasattr(self, "_pipe"):
+            e = lambda *shape, dtype: torch.empty(shape, dtype=dtype, device=self.dev)          # noqa: E731
+            self._pipe = {"stream": torch.cuda.Stream(device=self.dev), "slot": 0,
+                          "q": [self._q, e(self.max_batch, self.ix.dim, dtype=torch.float32)],
+                          "free": [torch.cuda.Event(), torch.cuda.Event()], "out": [None, None]}
+        P = self._pipe
+        slot = P["slot"]
+        P["slot"] ^= 1
+        cur = torch.cuda.current_stream()
+        up = P["stream"]
+        up.wait_event(P["free"][slot])                     # the search that last read this query buffer has finished
+        d_q = P["q"][slot][:n * self.world]
+        with torch.cuda.stream(up):
+            mine = d_q[self.rank * n:(self.rank + 1) * n]
+            mine.copy_(q, non_blocking=True)
+            if self.world > 1:
+                dist.all_gather_into_tensor(d_q, mine, group=self.group)
+            ready = torch.cuda.Event()
+            ready.record(up)
+        cur.wait_event(ready)
+        dd, ids = self.search_device(d_q, k)
+        P["free"][slot].record(cur)
+        out = P["out"][slot]
+        if out is None or tuple(out[0].shape) != tuple(ids.shape):
+            out = P["out"][slot] = (torch.empty(tuple(ids.shape), dtype=torch.int64).pin_memory(),
+                                    torch.empty(tuple(dd.shape), dtype=torch.float32).pin_memory())
+        out[0].copy_(ids, non_blocking=True)
+        out[1].copy_(dd, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(cur)
+        return (done, out)
+
+    def collect(self, ticket):
+        """Waits for a `submit_host` ticket: (ids int64 [m, k], dist float32 [m, k]) page-locked host tensors with the
+        results of the rows this rank owns; valid until the ticket after next is submitted."""
+        done, out = ticket
+        done.synchronize()
+        return out
+
     def search_host(self, q, k: int, *, whole_batch: bool = False, out=None):
         """The client call.  `q`: float32 [n, dim] in page-locked host memory (torch pinned tensor; a numpy array is
         wrapped) -- this rank's rows of the batch (every rank passes the same number of rows; the batch is their

@@ -200,6 +200,28 @@ def _worker_sharded_index(rank, world, port, n, dim, k, exchange, out):
                 ids, dd = sx.search_host(torch.from_numpy(q).pin_memory(), k, whole_batch=True)
             assert (lo_hi := sx.slice_of(nq)) and ids.shape[0] == lo_hi[1] - lo_hi[0]
             res[nq] = (lo_hi, ids.numpy().copy(), dd.numpy().copy())
+        # pipelined form (submit_host / collect, two batches in flight) == one batch at a time
+        batches = []
+        for b in range(5):
+            q = R.synth_rows(R.SEED_QUERY, 500 + 64 * b, 64, dim)
+            sl = 64 // world
+            batches.append(torch.from_numpy(q[rank * sl:(rank + 1) * sl].copy()).pin_memory())
+        want = []
+        for qb in batches:
+            i1, d1 = sx.search_host(qb, k)
+            want.append((i1.numpy().copy(), d1.numpy().copy()))
+        got, pending = [], []
+        for qb in batches:
+            pending.append(sx.submit_host(qb, k))
+            if len(pending) == 2:
+                i2, d2 = sx.collect(pending.pop(0))
+                got.append((i2.numpy().copy(), d2.numpy().copy()))
+        while pending:
+            i2, d2 = sx.collect(pending.pop(0))
+            got.append((i2.numpy().copy(), d2.numpy().copy()))
+        assert len(got) == len(want)
+        for (gi, gd), (wi, wd) in zip(got, want):
+            assert np.array_equal(gi, wi) and np.array_equal(gd, wd)
         out.put((rank, res))
         dist.barrier()
     finally:
