@@ -520,3 +520,47 @@ def test_device_call_then_host_call_share_a_workspace(vdb):
         side.synchronize()
         assert np.array_equal(ids.cpu().numpy(), want1[0]) and np.array_equal(dd.cpu().numpy(), want1[1])
         assert np.array_equal(got2[0], want2[0]) and np.array_equal(got2[1], want2[1])
+
+
+@pytest.mark.parametrize("k,nq", [(10, 1), (10, 2), (100, 1), (100, 2), (128, 1), (300, 1), (10, 3)])
+def test_single_query_scan_merges_in_kernel(vdb, k, nq):
+    """One or two queries over enough rows for a full grid: the scan kernel's last CTAs merge the per-CTA lists (one
+    level at k = 10, groups + a final level at k = 100 / 128); k = 300 and three queries keep the merge kernel.  Same
+    answers either way, and one launch per search when the merge is fused."""
+    n, dim = 60_000, 512
+    ix = vdb.Index("l2", dim)
+    ix.init_index(n)
+    ix.add_synthetic(R.SEED_DB, 0, n)
+    ix.mark_deleted([11, 40_000])
+    stored = R.synth_rows(R.SEED_DB, 0, n, dim)
+    q = R.synth_rows(R.SEED_QUERY, 3, nq, dim)
+    l0 = vdb.launch_count()
+    got_l, got_d, cnt = ix.knn_query_padded(q, k)
+    launches = vdb.launch_count() - l0
+    assert launches == (1 if (nq <= 2 and k <= 128) else 2)
+    for i in range(nq):
+        assert cnt[i] == k
+        msg = R.check_topk(got_l[i], got_d[i], q[i], stored, np.arange(n), k, "l2", deleted=[11, 40_000], rtol=RTOL)
+        assert msg is None, f"query {i}: {msg}"
+    again = ix.knn_query_padded(q, k)                              # the arrival counters were left at zero
+    assert np.array_equal(again[0], got_l) and np.array_equal(again[1], got_d)
+
+
+def test_device_side_fallback_with_arbitrary_labels(vdb):
+    """A flood of near-duplicates fails the tensor path's certificates: the flagged queries are re-searched exactly by
+    a kernel of the same enqueue (no host round trip); labels that are not base + row go through the label array."""
+    dim, n = 512, 3000
+    base = R.synth_rows(R.SEED_DB, 0, 1, dim)[0]
+    dup = np.tile(base, (n, 1)) + np.random.default_rng(1).normal(0, 1e-6, (n, dim)).astype(np.float32)
+    labels = np.arange(n)[::-1].copy() * 3 + 7
+    ix = vdb.Index("cosine", dim)
+    ix.init_index(n)
+    ix.add_items(dup, labels)
+    ix.set_option("path", 2)
+    q = R.synth_rows(R.SEED_QUERY, 0, 12, dim)
+    got_l, got_d, cnt = ix.knn_query_padded(q, 10)
+    stored = R.prepare_rows(dup, "cosine")
+    for i in range(len(q)):
+        msg = R.check_topk(got_l[i], got_d[i], q[i], stored, labels, 10, "cosine", rtol=RTOL)
+        assert msg is None, f"query {i}: {msg}"
+    assert ix.get_stat("fallback_queries") > 0 and ix.get_stat("tensor_batches") == 1
