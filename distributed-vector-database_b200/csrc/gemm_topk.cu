@@ -1383,6 +1383,7 @@ static cudaError_t launch_rerank_window(int kp, const RerankParams& rp, size_t n
         if (e != cudaSuccess) return e;
         configured[slot] = smem;
     }
+    // (64 / 96 / 128 threads per query measured alike at 8192 queries)
     cudaError_t le = kp <= 64 ? launch_pdl(rerank_window_kernel<T, 2>, dim3((unsigned)nq), dim3(128), smem, st, rp, kp)
                               : launch_pdl(rerank_window_kernel<T, 4>, dim3((unsigned)nq), dim3(RW_MAX_THREADS), smem, st, rp, kp);
     count_launch();

@@ -28,13 +28,32 @@ __global__ void prepare_queries_kernel(const float* __restrict__ q, size_t nq, i
         scale = 1.0f / (sqrtf(s) + 1e-30f);
     }
     float a = 0.0f;
-    for (int c = lane * 4; c < ld; c += 128) {
+    // 128-bit path (dim a multiple of 4, 16-byte aligned batch: every CLIP-shaped query block); same arithmetic, same
+    // order as the scalar path below
+    const bool vec = (dim & 3) == 0 && (ld16 & 3) == 0 && ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(out) |
+                                                         reinterpret_cast<uintptr_t>(out16)) & 15) == 0;
+    if (vec) {
+        for (int c = lane * 4; c < ld; c += 128) {
+            float4 x = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (c < dim) x = *reinterpret_cast<const float4*>(src + c);
+            const float v[4] = {x.x * scale, x.y * scale, x.z * scale, x.w * scale};
+            *reinterpret_cast<float4*>(out + w * (size_t)ld + c) = make_float4(v[0], v[1], v[2], v[3]);
+            if (out16 && c < ld16) {
+                __half2 h[2] = {__floats2half2_rn(v[0], v[1]), __floats2half2_rn(v[2], v[3])};
+                *reinterpret_cast<uint2*>(out16 + w * (size_t)ld16 + c) = *reinterpret_cast<uint2*>(h);
+            }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float v = (c + e < dim) ? src[c + e] * scale : 0.0f;
-            out[w * (size_t)ld + c + e] = v;
-            if (out16 && c + e < ld16) out16[w * (size_t)ld16 + c + e] = __float2half_rn(v);   // fp16 operand copy
-            a = fmaf(v, v, a);
+            for (int e = 0; e < 4; ++e) a = fmaf(v[e], v[e], a);
+        }
+    } else {
+        for (int c = lane * 4; c < ld; c += 128) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float v = (c + e < dim) ? src[c + e] * scale : 0.0f;
+                out[w * (size_t)ld + c + e] = v;
+                if (out16 && c + e < ld16) out16[w * (size_t)ld16 + c + e] = __float2half_rn(v);   // fp16 operand copy
+                a = fmaf(v, v, a);
+            }
         }
     }
     a = warp_sum_butterfly(a);

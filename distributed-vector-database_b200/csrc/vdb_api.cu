@@ -304,7 +304,7 @@ static void prof_end_cb(void* ctx, cudaStream_t) { static_cast<ProfScope*>(ctx)-
 // Queries one scan pass takes: up to 8, fewer when the rows are so long that 8 query vectors + k-lists no longer fit
 // beside the copy ring in shared memory (dim > 1152 fp32 / 1792 fp16).  0: k does not fit even for one query.
 int scan_group(const vdb* db, int k, size_t nq) {
-    int g = nq >= 8 ? 8 : nq >= 4 ? 4 : nq >= 2 ? 2 : 1;
+    int g = nq > 4 ? 8 : nq > 2 ? 4 : nq > 1 ? 2 : 1;      // one pass when the batch fits a kernel variant
     while (g > 1 && scan_max_k(g, db->ld, (uint32_t)db->row_bytes()) < k) g >>= 1;
     return scan_max_k(g, db->ld, (uint32_t)db->row_bytes()) >= k ? g : 0;
 }
