@@ -17,6 +17,7 @@ batch is 1024 x N, so the contraction work per GPU (batch x rows/N) is fixed as 
 Beside the headline the same line holds
   "sustained"  the headline step repeated back to back for >= 2 s (power-capped steady state), against the
                sustained tensor peak, with its own clock samples
+  "two_streams" (N=1) the same step with two batches in flight on two streams, as two server threads produce them
   "check"      results of sampled queries against the CPU oracle over the WHOLE database at every N (rows
                regenerated from the counter RNG), ordered ids + distances, and at N > 1 one step of the fused
                NVLink exchange against the NCCL exchange (bitwise) -- all outside the timed regions
@@ -592,6 +593,38 @@ class Arm:
                          "step_level_tflops": ach_s, "frac_of_burst_peak": ach_s / peak,
                          "frac_of_sustained_peak": ach_s / peak_s, "sustained_peak": peak_s, "clocks": sclk.summary()}
 
+        # two searches in flight on two streams (what two server threads produce): the short launches of one search
+        # -- probe, selects, re-rank -- fill the ramps and tails of the other's tensor launches.  Reported beside the
+        # headline, which stays one search at a time on one stream.
+        two_streams = None
+        if headline and world == 1 and a.sustain_s > 0:
+            qs = [self.make_queries(wl, B, start=i * B) for i in range(2)]
+            outs = [(torch.empty((B, k), dtype=torch.int64, device=dev), torch.empty((B, k), dtype=torch.float32, device=dev),
+                     torch.empty((B,), dtype=torch.int32, device=dev)) for _ in range(2)]
+            streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+
+            def run(nsteps):
+                for i in range(nsteps):
+                    j = i & 1
+                    ix.search_device(qs[j].data_ptr(), B, k, outs[j][0].data_ptr(), outs[j][1].data_ptr(), outs[j][2].data_ptr(),
+                                     streams[j].cuda_stream)
+            run(2 * warmup)
+            torch.cuda.synchronize()
+            n2 = 2 * max(steps, 20)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for st_ in streams:
+                st_.wait_event(e0)
+            run(n2)
+            for st_ in streams:
+                torch.cuda.current_stream().wait_stream(st_)
+            e1.record()
+            torch.cuda.synchronize()
+            ms2 = e0.elapsed_time(e1)
+            two_streams = {"value": B * n2 / (ms2 * 1e-3), "unit": "queries/s", "steps": n2, "ms_per_step": ms2 / n2,
+                           "step_level_frac": flops / (ms2 * 1e-3 / n2) / 1e12 / peak,
+                           "note": "two independent batches in flight (one stream + workspace each)"}
+
         # ---- checks (outside every timed region) -----------------------------------------------
         check = None
         if not a.no_check:
@@ -621,6 +654,7 @@ class Arm:
             "e2e": {"value": B * steps / e2e_sec, "unit": "queries/s", "h2d_bytes_per_step": B * wl.dim * 4,
                     "d2h_bytes_per_step": B * k * 12 + (B * 4 if world == 1 else 0)},
             "gpu_launches": main["launches"], "roofline": roof, "single_query": single, "sustained": sustained,
+            "two_streams": two_streams,
             "check": check, "cpu_baseline": cpu, "clocks": clk.summary(),
             "fallback_queries": ix.get_stat("fallback_queries"), "steps": main["steps"],
         }
@@ -748,6 +782,7 @@ def run_ours(a):
                        "l2": "inputs larger than L2 (no flush needed)", "path": head["path"]},
             "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "roofline": head["roofline"],
             "cpu_baseline": head["cpu_baseline"], "single_query": head["single_query"], "sustained": head["sustained"],
+            "two_streams": head["two_streams"],
             "clocks": head["clocks"], "recall_at_k": recall, "check": head["check"],
             "fallback_queries": head["fallback_queries"],
         }

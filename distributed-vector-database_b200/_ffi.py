@@ -43,6 +43,8 @@ SIGNATURES = {
     "vdb_get_rows": (C.c_int, [_vp, _i64p, C.c_size_t, _f32p]),
     "vdb_save": (C.c_int, [_vp, C.c_char_p]),
     "vdb_load": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(_vp)]),
+    "vdb_save_image": (C.c_int, [_vp, C.c_char_p, C.c_char_p]),
+    "vdb_load_image": (C.c_int, [C.c_char_p, C.c_char_p, C.c_size_t, C.c_int, C.POINTER(_vp)]),
     "vdb_merge_topk": (C.c_int, [_vp, _vp, C.c_int, C.c_size_t, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp]),
     "vdb_xchg_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, C.POINTER(_vp), _vp]),
     "vdb_xchg_connect": (C.c_int, [_vp, _vp]),

@@ -364,10 +364,16 @@ class ShardedIndex:
     # ---- pipelined client calls: upload of batch i+1 overlaps the search of batch i ---------------------------
     def submit_host(self, q, k: int):
         """Asynchronous `search_host` for even batches (every rank passes ITS rows of the batch, page-locked): the
-        upload + NVLink all-gather of the queries runs on a copy stream into one of two query buffers, the search,
-        the exchange + merge and the download of the results are enqueued on the current stream behind it.  Returns
-        a ticket for `collect`.  With two batches in flight the host<->device copies and the all-gather of one batch
-        hide behind the search of the other (a server's steady state); at most two tickets may be outstanding."""
+        upload of the queries runs on a copy stream (DMA) into one of two query buffers; the NVLink all-gather of the
+        slices, the search, the exchange + merge and the download of the results are enqueued on the current stream
+        behind it.  Returns a ticket for `collect`.  With two batches in flight the host<->device copies of one batch
+        (and the host's launch work) hide behind the search of the other; at most two tickets may be outstanding.
+
+        The all-gather stays on the SEARCH stream on purpose: it is a kernel that waits for its peers, and so is the
+        fused exchange + merge.  Two such kernels in flight at once on one GPU can deadlock a box (rank A: the
+        all-gather is resident and keeps the cooperative exchange kernel from being placed; rank B: the exchange kernel
+        is resident, spins for A, and its registers keep B's all-gather from being placed -- seen on 8 GPUs, caught by
+        the exchange's bounded wait).  One stream per rank makes them alternate."""
         torch, dist = self._torch, self._dist
         if not torch.is_tensor(q):
             q = torch.from_numpy(q)
@@ -386,14 +392,14 @@ class ShardedIndex:
         up = P["stream"]
         up.wait_event(P["free"][slot])                     # the search that last read this query buffer has finished
         d_q = P["q"][slot][:n * self.world]
+        mine = d_q[self.rank * n:(self.rank + 1) * n]
         with torch.cuda.stream(up):
-            mine = d_q[self.rank * n:(self.rank + 1) * n]
             mine.copy_(q, non_blocking=True)
-            if self.world > 1:
-                dist.all_gather_into_tensor(d_q, mine, group=self.group)
             ready = torch.cuda.Event()
             ready.record(up)
         cur.wait_event(ready)
+        if self.world > 1:
+            dist.all_gather_into_tensor(d_q, mine, group=self.group)     # on the search stream: see above
         dd, ids = self.search_device(d_q, k)
         P["free"][slot].record(cur)
         out = P["out"][slot]

@@ -4,6 +4,10 @@
 // a pool of per-call workspaces (stream + scratch) and dispatches a search to the scan kernel
 // (K1) or the tensor-core kernel (K2) followed by the merge (K5).  No CPU compute path exists:
 // if CUDA is unavailable every entry point fails with VDB_ECUDA.
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
@@ -53,7 +57,8 @@ constexpr int MAX_WORKSPACES = 8;
 struct Workspace {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
-    bool used = false;
+    bool used = false;                // a device-pointer call left work in flight on `last_stream` (see `done`)
+    cudaStream_t last_stream = nullptr;
     // device scratch (grow only)
     float* d_q_in = nullptr;  size_t q_in_cap = 0;     // raw queries (host path)
     float* d_q = nullptr;     size_t q_cap = 0;        // prepared queries [nq][ld]
@@ -112,6 +117,7 @@ struct vdb {
     size_t va_rows = 0;               // rows the address reservations hold
     GrowBuf b_rows, b_shadow, b_sqnorm, b_labels, b_tomb;
     size_t tomb_words_zeroed = 0;
+    size_t image_saved = 0;           // rows of this shard known to be in its on-disk image (vdb_save_image)
     void* rows = nullptr;             // == b_rows.ptr() etc.: stable while `mu` is held shared
     void* shadow = nullptr;           // fp16 copy of fp32 rows [capacity][ld16]: operand plane of the tensor path
     int ld16 = 0;
@@ -248,20 +254,40 @@ void free_workspace(Workspace* w) {
     if (w->stream) cudaStreamDestroy(w->stream);
 }
 
-Workspace* acquire_ws(vdb* db) {
+// `st`: the stream a device-pointer call will enqueue on (null for host-buffer calls, which run on the workspace's
+// own stream and hold it until they return).  Order of preference: the workspace this stream used last (stream
+// order already protects its scratch, and a caller looping on one stream keeps one warm workspace); one whose last
+// device-side user has finished; a new one; any (the caller then waits for its event on the GPU).  A caller that
+// enqueues on several streams gets its searches side by side instead of chained through one scratch buffer.
+Workspace* acquire_ws(vdb* db, cudaStream_t st = nullptr, bool dev_call = false) {
     std::unique_lock<std::mutex> lk(db->ws_mu);
     for (;;) {
-        if (!db->ws_free.empty()) {
-            Workspace* w = db->ws_free.back();
-            db->ws_free.pop_back();
-            return w;
+        if (dev_call)
+            for (size_t i = db->ws_free.size(); i-- > 0;)
+                if (db->ws_free[i]->used && db->ws_free[i]->last_stream == st) {
+                    Workspace* w = db->ws_free[i];
+                    db->ws_free.erase(db->ws_free.begin() + (long)i);
+                    return w;
+                }
+        for (size_t i = db->ws_free.size(); i-- > 0;) {
+            Workspace* w = db->ws_free[i];
+            if (!w->used || cudaEventQuery(w->done) == cudaSuccess) {
+                db->ws_free.erase(db->ws_free.begin() + (long)i);
+                return w;
+            }
         }
+        cudaGetLastError();                                   // cudaErrorNotReady from the queries above is not an error
         if ((int)db->ws_all.size() < MAX_WORKSPACES) {
             auto w = std::make_unique<Workspace>();
             if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
             if (cudaEventCreateWithFlags(&w->done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
             db->ws_all.push_back(std::move(w));
             return db->ws_all.back().get();
+        }
+        if (!db->ws_free.empty()) {                           // all busy and the pool is full: queue behind one
+            Workspace* w = db->ws_free.back();
+            db->ws_free.pop_back();
+            return w;
         }
         db->ws_cv.wait(lk);
     }
@@ -776,15 +802,16 @@ int vdb_search_dev(vdb_t* db, const float* d_queries, size_t nq, int k, int64_t*
     std::shared_lock<std::shared_mutex> lk(db->mu);
     CU_TRY(cudaSetDevice(db->device));
     const size_t n = db->count.load(std::memory_order_acquire);
-    Workspace* ws = acquire_ws(db);
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace* ws = acquire_ws(db, st, true);
     if (!ws) return fail(VDB_ECUDA, "cannot create a search workspace (stream)");
     WsGuard guard{db, ws};
-    cudaStream_t st = (cudaStream_t)stream;
-    // the scratch may still be in use by the previous call's stream: order after it on the GPU
-    if (ws->used) CU_TRY(cudaStreamWaitEvent(st, ws->done, 0));
+    // the scratch may still be in use by a call on ANOTHER stream: order after it on the GPU (the same stream orders itself)
+    if (ws->used && ws->last_stream != st) CU_TRY(cudaStreamWaitEvent(st, ws->done, 0));
     rc = search_core(db, ws, d_queries, nq, k, d_labels, d_dist, d_counts, st, n);
     CU_TRY(cudaEventRecord(ws->done, st));
     ws->used = true;
+    ws->last_stream = st;
     return rc;
 }
 
@@ -939,6 +966,165 @@ int vdb_load(const char* path, size_t capacity, int device, vdb_t** out) {
     db->label_base = h.label_base;
     db->live.store(h.live);
     db->count.store(n);
+    *out = db;
+    return VDB_OK;
+}
+
+// ---- append-only shard image -----------------------------------------------------------------------------------
+// rows / norms / labels of an appended row never change, so the on-disk form of a shard can be append-only too:
+//   <image_dir>/rows.bin  sqnorm.bin  labels.bin     grow by the rows added since the last save
+//   <meta_path>                                       header + tombstone words of THIS moment (small; tmp + rename)
+// A checkpoint costs O(new rows) instead of rewriting the shard (2 GB per million rows with vdb_save); loading reads
+// the prefix [0, count) that the meta names.  Rows the image holds beyond `image_saved` (a save that crashed before
+// its meta was renamed, or a restart from an older meta) are cut off before the next append.
+namespace {
+struct Fd {
+    int fd = -1;
+    ~Fd() { if (fd >= 0) ::close(fd); }
+};
+bool write_all(int fd, const void* p, size_t n, off_t off) {
+    const char* c = static_cast<const char*>(p);
+    while (n) {
+        ssize_t w = ::pwrite(fd, c, n, off);
+        if (w <= 0) return false;
+        c += w; n -= (size_t)w; off += w;
+    }
+    return true;
+}
+bool read_all(int fd, void* p, size_t n, off_t off) {
+    char* c = static_cast<char*>(p);
+    while (n) {
+        ssize_t r = ::pread(fd, c, n, off);
+        if (r <= 0) return false;
+        c += r; n -= (size_t)r; off += r;
+    }
+    return true;
+}
+}  // namespace
+
+int vdb_save_image(vdb_t* db, const char* image_dir, const char* meta_path) {
+    if (!db || !image_dir || !meta_path) return fail(VDB_EINVAL, "null argument");
+    std::lock_guard<std::mutex> wlk(db->wmu);
+    std::shared_lock<std::shared_mutex> lk(db->mu);
+    CU_TRY(cudaSetDevice(db->device));
+    CU_TRY(cudaStreamSynchronize(db->wstream));
+    const size_t n = db->count.load();
+    ::mkdir(image_dir, 0755);
+    const std::string dir(image_dir);
+    struct Part { const char* name; const uint8_t* dev; size_t bytes_per_row; };
+    const Part parts[3] = {{"rows.bin", (const uint8_t*)db->rows, db->row_bytes()},
+                           {"sqnorm.bin", (const uint8_t*)db->sqnorm, sizeof(float)},
+                           {"labels.bin", (const uint8_t*)db->labels, sizeof(uint32_t)}};
+    size_t have = db->image_saved;
+    for (const Part& pt : parts) {                 // what the files really hold (a foreign or shorter image: start over)
+        struct stat sb;
+        const std::string f = dir + "/" + pt.name;
+        if (::stat(f.c_str(), &sb) != 0) { have = 0; break; }
+        have = std::min(have, (size_t)sb.st_size / pt.bytes_per_row);
+    }
+    have = std::min(have, n);
+    std::vector<uint8_t> buf;
+    for (const Part& pt : parts) {
+        Fd f;
+        f.fd = ::open((dir + "/" + pt.name).c_str(), O_RDWR | O_CREAT, 0644);
+        if (f.fd < 0) return fail(VDB_EIO, std::string("cannot open ") + dir + "/" + pt.name);
+        if (::ftruncate(f.fd, (off_t)(have * pt.bytes_per_row)) != 0) return fail(VDB_EIO, "ftruncate failed");
+        const size_t chunk_rows = std::max<size_t>(1, (64u << 20) / pt.bytes_per_row);
+        buf.resize(std::min(chunk_rows, n - have + 1) * pt.bytes_per_row);
+        for (size_t r = have; r < n; r += chunk_rows) {
+            const size_t m = std::min(chunk_rows, n - r);
+            CU_TRY(cudaMemcpy(buf.data(), pt.dev + r * pt.bytes_per_row, m * pt.bytes_per_row, cudaMemcpyDeviceToHost));
+            if (!write_all(f.fd, buf.data(), m * pt.bytes_per_row, (off_t)(r * pt.bytes_per_row)))
+                return fail(VDB_EIO, std::string("write failed: ") + pt.name);
+        }
+        if (::fsync(f.fd) != 0) return fail(VDB_EIO, "fsync failed");
+    }
+    // the meta names how many rows count, with this moment's tombstones: written last, atomically
+    SnapHeader h{};
+    memcpy(h.magic, "VDBIMG2\0", 8);
+    h.version = 2; h.dim = db->dim; h.ld = db->ld; h.metric = db->metric; h.dtype = db->dtype; h.affine = db->affine.load();
+    h.count = n; h.live = db->live.load(); h.label_base = db->label_base;
+    CU_TRY(cudaMemcpy(&h.max_sqnorm_bits, db->d_max_sqnorm, 4, cudaMemcpyDeviceToHost));
+    const std::string tmp = std::string(meta_path) + ".tmp";
+    {
+        Fd f;
+        f.fd = ::open(tmp.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        if (f.fd < 0) return fail(VDB_EIO, std::string("cannot open ") + tmp);
+        const size_t w = (n + 63) / 64;
+        if (!write_all(f.fd, &h, sizeof(h), 0) || (w && !write_all(f.fd, db->h_dead.data(), w * 8, sizeof(h))) || ::fsync(f.fd) != 0)
+            return fail(VDB_EIO, std::string("write failed: ") + tmp);
+    }
+    if (::rename(tmp.c_str(), meta_path) != 0) return fail(VDB_EIO, std::string("rename failed: ") + meta_path);
+    db->image_saved = n;
+    return VDB_OK;
+}
+
+int vdb_load_image(const char* image_dir, const char* meta_path, size_t capacity, int device, vdb_t** out) {
+    if (!image_dir || !meta_path || !out) return fail(VDB_EINVAL, "null argument");
+    *out = nullptr;
+    Fd mf;
+    mf.fd = ::open(meta_path, O_RDONLY);
+    if (mf.fd < 0) return fail(VDB_EIO, std::string("cannot open ") + meta_path);
+    SnapHeader h{};
+    if (!read_all(mf.fd, &h, sizeof(h), 0) || memcmp(h.magic, "VDBIMG2\0", 8) != 0 || h.version != 2)
+        return fail(VDB_EIO, "not a vdb_b200 image meta file");
+    const size_t n = h.count;
+    if (capacity < n) capacity = n;
+    vdb_t* db = nullptr;
+    int rc = vdb_create((int)h.dim, (int)h.metric, (int)h.dtype, capacity, device, &db);
+    if (rc) return rc;
+    auto bail = [&](const std::string& msg) { cudaGetLastError(); vdb_destroy(db); return fail(VDB_EIO, msg); };
+    if ((uint32_t)db->ld != h.ld) return bail("image row stride mismatch");
+    const std::string dir(image_dir);
+    struct Part { const char* name; uint8_t* dev; size_t bytes_per_row; };
+    const Part parts[3] = {{"rows.bin", (uint8_t*)db->rows, db->row_bytes()},
+                           {"sqnorm.bin", (uint8_t*)db->sqnorm, sizeof(float)},
+                           {"labels.bin", (uint8_t*)db->labels, sizeof(uint32_t)}};
+    std::vector<uint8_t> buf;
+    std::vector<uint32_t> labels32;
+    for (const Part& pt : parts) {
+        Fd f;
+        f.fd = ::open((dir + "/" + pt.name).c_str(), O_RDONLY);
+        if (f.fd < 0) return bail(std::string("cannot open ") + dir + "/" + pt.name);
+        const size_t chunk_rows = std::max<size_t>(1, (64u << 20) / pt.bytes_per_row);
+        buf.resize(std::min(chunk_rows, n + 1) * pt.bytes_per_row);
+        for (size_t r = 0; r < n; r += chunk_rows) {
+            const size_t m = std::min(chunk_rows, n - r);
+            if (!read_all(f.fd, buf.data(), m * pt.bytes_per_row, (off_t)(r * pt.bytes_per_row)))
+                return bail(std::string("image shorter than its meta says: ") + pt.name);
+            if (cudaMemcpy(pt.dev + r * pt.bytes_per_row, buf.data(), m * pt.bytes_per_row, cudaMemcpyHostToDevice) != cudaSuccess)
+                return bail("copy to the device failed");
+            if (!h.affine && pt.dev == (uint8_t*)db->labels) {
+                const uint32_t* l = reinterpret_cast<const uint32_t*>(buf.data());
+                labels32.insert(labels32.end(), l, l + m);
+            }
+        }
+    }
+    if (!h.affine) {
+        db->affine.store(false);
+        db->map.reserve(n * 2);
+        for (size_t r = 0; r < n; ++r) db->map[(int64_t)labels32[r]] = (uint32_t)r;   // later rows win
+    }
+    const size_t w = (n + 63) / 64;
+    if (w && !read_all(mf.fd, db->h_dead.data(), w * 8, sizeof(h))) return bail("meta file truncated");
+    {
+        std::vector<uint32_t> words((n + 31) / 32 + 1, 0);
+        bool any = false;
+        for (size_t r = 0; r < n; ++r)
+            if (db->dead(r)) { words[r >> 5] |= 1u << (r & 31); any = true; }
+        db->any_dead.store(any);
+        if (n && cudaMemcpy(db->tomb, words.data(), ((n + 31) / 32) * 4, cudaMemcpyHostToDevice) != cudaSuccess) return bail("copy failed");
+    }
+    cudaMemcpy(db->d_max_sqnorm, &h.max_sqnorm_bits, 4, cudaMemcpyHostToDevice);
+    if (db->shadow && n) {   // derived data: rebuilt from the fp32 rows
+        if (launch_shadow_rows((const float*)db->rows, db->ld, db->shadow, db->ld16, 0, n, db->wstream) != cudaSuccess ||
+            cudaStreamSynchronize(db->wstream) != cudaSuccess)
+            return bail("rebuilding the fp16 shadow plane failed");
+    }
+    db->label_base = h.label_base;
+    db->live.store(h.live);
+    db->count.store(n);
+    db->image_saved = n;
     *out = db;
     return VDB_OK;
 }

@@ -180,7 +180,12 @@ class GpuVectorNodeHandler:
                 path = os.path.join(self.checkpoint_dir, f"checkpoint_{ts}")
             tmp = path + ".tmp"
             os.makedirs(tmp)
-            self.hnsw_index.save_index(os.path.join(tmp, "index.bin"))
+            if hasattr(self.hnsw_index, "save_image"):
+                # the shard's append-only image under hnsw_index/ grows by the rows added since the last checkpoint;
+                # index.bin is the small meta of this moment (count + tombstones): O(new rows), not O(shard)
+                self.hnsw_index.save_image(self.hnsw_index_dir, os.path.join(tmp, "index.bin"))
+            else:
+                self.hnsw_index.save_index(os.path.join(tmp, "index.bin"))
             self.store.flush()
             kv_dir = os.path.join(tmp, "leveldb_data")
             os.makedirs(kv_dir, exist_ok=True)
@@ -208,7 +213,10 @@ class GpuVectorNodeHandler:
         path = os.path.join(self.checkpoint_dir, dirs[-1])
         index_path = os.path.join(path, "index.bin")
         if os.path.exists(index_path):
-            self.hnsw_index.load_index(index_path, max_elements=self.max_elements)     # handler.py:195
+            if hasattr(self.hnsw_index, "load_image") and self.hnsw_index.is_image_meta(index_path):
+                self.hnsw_index.load_image(self.hnsw_index_dir, index_path, max_elements=self.max_elements)
+            else:
+                self.hnsw_index.load_index(index_path, max_elements=self.max_elements)     # handler.py:195
             self.next_hnsw_id = self.hnsw_index.get_current_count()
         pos_path = os.path.join(path, "leveldb_data", "kv_pos.json")
         if os.path.exists(pos_path):

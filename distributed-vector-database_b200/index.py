@@ -181,6 +181,32 @@ class Index:
         self._h = h.value
         self._auto_label = self.get_current_count()
 
+    def save_image(self, image_dir: str, meta_path: str) -> None:
+        """Incremental form of save_index for frequent checkpoints: the shard's append-only image under `image_dir`
+        grows by the rows added since the last call; `meta_path` gets the small header + tombstone bitmap of this
+        moment (what a checkpoint stores as its index.bin)."""
+        _ffi.check(_ffi.lib().vdb_save_image(self._handle(), str(image_dir).encode(), str(meta_path).encode()), "save_image")
+
+    def load_image(self, image_dir: str, meta_path: str, max_elements: int = 0) -> None:
+        h = C.c_void_p()
+        _ffi.check(_ffi.lib().vdb_load_image(str(image_dir).encode(), str(meta_path).encode(), int(max_elements), self.device,
+                                             C.byref(h)), "load_image")
+        got_dim = int(_ffi.lib().vdb_dim(h.value))
+        if got_dim != self.dim:
+            _ffi.lib().vdb_destroy(h.value)
+            raise RuntimeError(f"image dim {got_dim} does not match index dim {self.dim}")
+        self.close()
+        self._h = h.value
+        self._auto_label = self.get_current_count()
+
+    @staticmethod
+    def is_image_meta(path: str) -> bool:
+        try:
+            with open(path, "rb") as f:
+                return f.read(8) == b"VDBIMG2\0"
+        except OSError:
+            return False
+
     # ---- extensions used by benches / the sharded path ----------------------------------
     def add_synthetic(self, seed: int, row_start: int, n: int, label_start: Optional[int] = None) -> None:
         """Append rows of the synthetic unit-norm set generated on the device (bench utility)."""

@@ -99,6 +99,14 @@ int vdb_get_rows(vdb_t *db, const int64_t *labels, size_t n, float *out);
 int vdb_save(vdb_t *db, const char *path);
 int vdb_load(const char *path, size_t capacity, int device, vdb_t **out);
 
+/* The same for checkpoints that come often (every 2000 puts in the reference, handler.py:316-317): rows, norms and
+ * labels of an appended row never change, so the shard keeps an APPEND-ONLY image on disk -- <image_dir>/rows.bin,
+ * sqnorm.bin, labels.bin grow by the rows added since the last save -- and a checkpoint is a small meta file (header
+ * + the tombstone bitmap of that moment, written to meta_path by tmp + rename).  O(new rows) instead of rewriting the
+ * shard.  vdb_load_image reads the prefix the meta names; older metas stay loadable (their prefix never changes). */
+int vdb_save_image(vdb_t *db, const char *image_dir, const char *meta_path);
+int vdb_load_image(const char *image_dir, const char *meta_path, size_t capacity, int device, vdb_t **out);
+
 /* CoordinatorHandler.search merge: sorted(range(n), key=score)[:top_k]
  *                                                              src/coordinator/handler.py:212-216
  * dist/ids [G, nq, k_in] (id < 0 = padding) -> ascending (distance, id) top k_out per query.
@@ -117,7 +125,10 @@ int vdb_merge_topk(const float *dist, const int64_t *ids, int G, size_t nq, int 
  *            slice = ceil(nq/G) (rank r owns queries [r*slice, min(nq,(r+1)*slice)); rows beyond what it owns
  *            are left untouched), enqueued on `stream`.  Collective: every rank must call it once per step with the same nq and k; one step in
  *            flight per rank.  The kernel is launched cooperatively (its whole grid is placed at once), so other work
- *            on the same GPU -- searches on other streams -- can delay but not deadlock it. */
+ *            on the same GPU -- searches on other streams -- can delay but not deadlock it.  The one thing that may
+ *            NOT run beside it is another kernel that waits for the same peers (a collective of a communication
+ *            library on another stream): two ranks can then each hold the resources the other's waiting kernel needs.
+ *            Enqueue collectives on the stream that carries this call. */
 typedef struct vdb_xchg vdb_xchg_t;
 int vdb_xchg_create(int device, int rank, int world, size_t max_slice, int max_k, vdb_xchg_t **out,
                     unsigned char *handle64);

@@ -269,3 +269,76 @@ def test_handler_bulk_load_and_recovery(vdb, tmp_path):
     g = h2.get("b7")
     assert g.vector_data.metadata == {"i": "7"} and np.allclose(g.vector_data.vector, rows[7])
     assert np.allclose(h2.get("b5").vector_data.vector, extra[1]) and len(h2.store) == 4001
+
+
+def test_append_only_shard_image(vdb, tmp_path):
+    """vdb_save_image / vdb_load_image: the on-disk image grows by the rows added since the last save, every meta
+    file stays loadable (its prefix never changes), a crashed save (files longer than the newest meta) and a restart
+    from an older meta are cut back before the next append."""
+    img = str(tmp_path / "img")
+    n1, n2 = 3000, 5000
+    raw = vecs(n2)
+    ix = vdb.Index("cosine", DIM)
+    ix.init_index(n2)
+    ix.add_items(raw[:n1], np.arange(n1))
+    ix.mark_deleted([5, 7])
+    ix.save_image(img, str(tmp_path / "meta1.bin"))
+    size1 = (tmp_path / "img" / "rows.bin").stat().st_size
+    ix.add_items(raw[n1:], np.arange(n1, n2))
+    ix.mark_deleted([4000])
+    ix.save_image(img, str(tmp_path / "meta2.bin"))
+    assert (tmp_path / "img" / "rows.bin").stat().st_size == size1 * n2 // n1        # appended, not rewritten
+    assert (tmp_path / "meta2.bin").stat().st_size < 4096                            # a checkpoint is a few hundred bytes
+    q = R.synth_rows(R.SEED_QUERY, 0, 20, DIM)
+    want2 = ix.knn_query_padded(q, 10)
+    stored = R.prepare_rows(raw, "cosine")
+    # newest meta: the whole shard
+    b = vdb.Index("cosine", DIM)
+    b.load_image(img, str(tmp_path / "meta2.bin"), max_elements=n2 + 100)
+    got = b.knn_query_padded(q, 10)
+    assert b.get_current_count() == n2 and np.array_equal(got[0], want2[0]) and np.array_equal(got[1], want2[1])
+    # older meta: the prefix, with the tombstones of that moment
+    a = vdb.Index("cosine", DIM)
+    a.load_image(img, str(tmp_path / "meta1.bin"), max_elements=n2)
+    assert a.get_current_count() == n1 and a.get_live_count() == n1 - 2
+    l, d, c = a.knn_query_padded(q[:4], 10)
+    for i in range(4):
+        msg = R.check_topk(l[i], d[i], q[i], stored[:n1], np.arange(n1), 10, "cosine", deleted=[5, 7], rtol=1e-5)
+        assert msg is None, msg
+    # continue from the OLDER state with different rows: the stale tail of the image is cut off first
+    other = vecs(500, start=900_000)
+    a.add_items(other, np.arange(n1, n1 + 500))
+    a.save_image(img, str(tmp_path / "meta3.bin"))
+    assert (tmp_path / "img" / "rows.bin").stat().st_size == size1 * (n1 + 500) // n1
+    c3 = vdb.Index("cosine", DIM)
+    c3.load_image(img, str(tmp_path / "meta3.bin"))
+    l, d, c = c3.knn_query_padded(other[:3], 1)
+    assert l[:, 0].tolist() == [n1, n1 + 1, n1 + 2] and np.all(np.abs(d[:, 0]) < 1e-6)
+    with pytest.raises(RuntimeError):
+        vdb.Index("cosine", DIM).load_image(img, str(tmp_path / "meta2.bin"))       # names rows the image no longer has
+    assert vdb.Index.is_image_meta(str(tmp_path / "meta3.bin")) and not vdb.Index.is_image_meta(str(tmp_path / "img" / "rows.bin"))
+
+
+def test_handler_checkpoints_are_incremental(vdb, tmp_path):
+    """checkpoint_every = 1000 with 1000-row batches: every batch takes a checkpoint (the reference's cadence,
+    handler.py:316-317); with the append-only image each costs the new rows only, and a restart from the newest one
+    (plus the WAL tail) restores the state."""
+    h = vdb.GpuVectorNodeHandler("inc", storage_root=str(tmp_path), space="l2", dim=DIM, max_elements=2000,
+                                 checkpoint_every=1000, fsync=False)
+    rows = vecs(6500)
+    for lo in range(0, 6000, 1000):
+        assert h.put_arrays([f"k{i}" for i in range(lo, lo + 1000)], rows[lo:lo + 1000]).success
+    assert h.put_arrays([f"k{i}" for i in range(6000, 6500)], rows[6000:]).success   # WAL tail, no checkpoint
+    h.delete("k10")
+    cps = sorted(d for d in (tmp_path / "inc" / "checkpoint").iterdir())
+    assert len(cps) == 2 and all((c / "index.bin").stat().st_size < 4096 for c in cps)
+    assert (tmp_path / "inc" / "hnsw_index" / "rows.bin").stat().st_size == 6000 * DIM * 4
+    qs = rows[[10, 3333, 6400]]
+    want = h.search_batch(qs, 3)
+    h.store.close()
+    h2 = vdb.GpuVectorNodeHandler("inc", storage_root=str(tmp_path), space="l2", dim=DIM, max_elements=2000,
+                                  checkpoint_every=1000, fsync=False)
+    got = h2.search_batch(qs, 3)
+    assert got[0] == want[0] and "k10" not in got[0][0] and got[0][1][0] == "k3333" and got[0][2][0] == "k6400"
+    np.testing.assert_allclose(np.array(got[1]), np.array(want[1]), rtol=1e-6, atol=1e-7)
+    assert len(h2.store) == 6499
