@@ -682,6 +682,35 @@ class Arm:
             dist.all_reduce(same, op=dist.ReduceOp.MIN)
             out["p2p_equals_nccl"] = bool(same.item())
             other.close()
+            # the fused NVLink exchange + merge kernel (K5x) alone: this rank's [B, k] lists out by query slice, its
+            # slice's G lists merged; (G-1)/G of the packed keys cross NVLink
+            px = sx.px if a.exchange == "p2p" else None
+            if px is not None:
+              try:
+                ids_l = torch.arange(B * k, dtype=torch.int64, device=dev).view(B, k)
+                dd_l = torch.rand((B, k), device=dev).sort(dim=1).values
+                sl = (B + world - 1) // world
+                o_i = torch.empty((sl, k), dtype=torch.int64, device=dev)
+                o_d = torch.empty((sl, k), dtype=torch.float32, device=dev)
+                reps = 20
+                for _ in range(3):
+                    px.merge(dd_l.data_ptr(), ids_l.data_ptr(), B, k, o_d.data_ptr(), o_i.data_ptr(), stream)
+                self.barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    px.merge(dd_l.data_ptr(), ids_l.data_ptr(), B, k, o_d.data_ptr(), o_i.data_ptr(), stream)
+                e1.record()
+                torch.cuda.synchronize()
+                px.status()
+                us = torch.tensor([e0.elapsed_time(e1) * 1e3 / reps], device=dev)
+                dist.all_reduce(us, op=dist.ReduceOp.MAX)
+                nv_bytes = B * k * 8 * (world - 1) // world
+                out["exchange_merge_kernel"] = {"us_per_step": float(us.item()), "nvlink_bytes_out_per_rank": nv_bytes,
+                                                "nvlink_gbs_per_rank": nv_bytes / (float(us.item()) * 1e-6) / 1e9,
+                                                "note": "K5x alone, back to back, max over ranks (CUDA events)"}
+              except Exception as e:          # an optional figure must not cost the line
+                out["exchange_merge_kernel"] = {"error": repr(e)}
         # (2) sampled queries of rank 0's slice against the CPU oracle over the whole database
         n_mine = len(main["ids"])
         nsamp = min(a.check_queries, n_mine)
