@@ -20,6 +20,7 @@ cap() {  # name, kernel regex, skip, count, env..., -- bench args
   env "${envs[@]}" $NCU --kernel-name regex:$re --launch-skip $skip --launch-count $count -o $O/${R}_$name \
       python bench.py $Q "$@" > $O/ncu_$name.log 2>&1
   ncu -i $O/${R}_$name.ncu-rep --page raw --csv > $O/${R}_${name}_ncu_raw.csv 2>> $O/ncu_$name.log
+  rm -f $O/${R}_$name.ncu-rep        # the raw page is what is kept: gpurun brings back at most 64 MiB
 }
 # steady state: skip the first 2 searches (probe + levels launches each)
 cap gemm_f16shadow_cos_k10_b1024 gemm_filter 8 4 X=1 -- --no-single --steps 3 --warmup 1
