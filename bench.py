@@ -652,7 +652,8 @@ class Arm:
             "dtype": ("f16 operands (shadow plane of f32 rows) / f32 accumulate, exact f32 re-rank" if shadow else
                       "tf32 operands / f32 accumulate, exact f32 re-rank" if tf32_path else "f16-stored / f32 accumulate"),
             "e2e": {"value": B * steps / e2e_sec, "unit": "queries/s", "h2d_bytes_per_step": B * wl.dim * 4,
-                    "d2h_bytes_per_step": B * k * 12 + (B * 4 if world == 1 else 0)},
+                    "d2h_bytes_per_step": B * k * 12 + (B * 4 if world == 1 else 0),
+                    "in_flight": 1 if world == 1 else 2},
             "gpu_launches": main["launches"], "roofline": roof, "single_query": single, "sustained": sustained,
             "two_streams": two_streams,
             "check": check, "cpu_baseline": cpu, "clocks": clk.summary(),
