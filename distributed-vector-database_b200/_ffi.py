@@ -48,6 +48,10 @@ SIGNATURES = {
     "vdb_merge_topk": (C.c_int, [_vp, _vp, C.c_int, C.c_size_t, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp]),
     "vdb_xchg_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, C.POINTER(_vp), _vp]),
     "vdb_xchg_connect": (C.c_int, [_vp, _vp]),
+    "vdb_xchg_create_q": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_size_t, C.POINTER(_vp), _vp]),
+    "vdb_xchg_query_slot": (_vp, [_vp, C.c_int]),
+    "vdb_xchg_gather_queries": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int, C.c_uint32, _vp]),
+    "vdb_xchg_wait_queries": (C.c_int, [_vp, C.c_int, C.c_uint32, _vp]),
     "vdb_xchg_merge_dev": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_int, _vp, _vp, _vp]),
     "vdb_xchg_status": (C.c_int, [_vp]),
     "vdb_xchg_destroy": (None, [_vp]),

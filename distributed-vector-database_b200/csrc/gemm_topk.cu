@@ -63,25 +63,50 @@ constexpr int GT_STAGE_BYTES = GT_A_BYTES + GT_B_BYTES;
 #ifndef VDB_GT_RING
 #define VDB_GT_RING 40
 #endif
+#ifndef VDB_GT_STAGES_ARES
+#define VDB_GT_STAGES_ARES 4  // query-resident variant: stages of 16 KB (shard rows only)
+#endif
+#ifndef VDB_GT_RING_ARES
+#define VDB_GT_RING_ARES 13
+#endif
 constexpr int GT_STAGES = VDB_GT_STAGES;
 constexpr int GT_THREADS = 384;                      // 12 warps: TMA, MMA, 2 movers, 8 epilogue
-constexpr int GT_RING = VDB_GT_RING;                  // keys per ring (one ring per epilogue thread)
-constexpr int GT_RING_STRIDE = GT_RING + 1;                   // padded: same-slot appends of a warp spread over banks
+constexpr int GT_RING = VDB_GT_RING;                  // keys per ring, streaming variant
 constexpr int GT_EPI_THREADS = 256;                  // 2 threads per query (TMEM lane): columns 0-127 / 128-255
 constexpr int GT_EPI_WARPS = GT_EPI_THREADS / 32;
 constexpr int GT_TMEM_COLS = 512;
 constexpr int GT_LEVEL_GROWTH = 8;                   // each level sees 8x the rows seen so far
 constexpr int GT_PROBE_TILES = 16;                   // probe level: 16 tiles = 4096 rows, 128 chunk minima per query
+constexpr int GT_CTL_BYTES = GT_EPI_THREADS * 8 + 64;  // EpiCtl, checked below
 
-// dynamic shared memory map (base aligned to 1024)
-constexpr int GT_OFF_RING = GT_STAGES * GT_STAGE_BYTES;                           // 163840
-constexpr int GT_OFF_NORM = GT_OFF_RING + GT_EPI_THREADS * GT_RING_STRIDE * 8;    // + 50176
-constexpr int GT_OFF_BAR = GT_OFF_NORM + 2 * GT_BN * 4;                           // + 2048
-constexpr int GT_OFF_CTL = GT_OFF_BAR + 128;
-constexpr int GT_CTL_BYTES = GT_EPI_THREADS * 8 + 64;                             // EpiCtl, checked below
-constexpr int GT_SMEM_BYTES_FILTER = GT_OFF_CTL + GT_CTL_BYTES + 1024;            // + slack for the 1024-byte alignment
-static_assert(GT_SMEM_BYTES_FILTER <= 232448, "shared memory budget");
-
+// dynamic shared memory map (base aligned to 1024), two variants of the kernel:
+//   streaming (ARES = false): every stage of the ring holds one k-block of the query block (A, 16 KB) and of this
+//     CTA's half of the shard tile (B, 16 KB); A is fetched again for every tile (from L2).
+//   query-resident (ARES = true, rows of at most 1024 bytes = 8 k-blocks): the CTA's 128 query rows stay in shared
+//     memory (128 KB) for as long as the pair works on the same query block, the ring holds shard rows only.  Per
+//     tile a CTA then pulls 128 KB instead of 256 KB through the L2 -> SM path, which at the f16 MMA rate was running
+//     at ~11 TB/s chip-wide, ~0.9 of what the L2 slices deliver (profiles/README.md); the key rings shrink to pay
+//     for it (survivors are ~1 score in 3000 on the levels that matter).
+template <bool ARES>
+struct GtSmem {
+    static constexpr int A_RES_KB = 8;                                        // resident k-blocks (ARES)
+    static constexpr int A_RES_BYTES = ARES ? A_RES_KB * GT_A_BYTES : 0;      // 128 KB
+    static constexpr int STAGES = ARES ? VDB_GT_STAGES_ARES : GT_STAGES;
+    static constexpr int STAGE_BYTES = ARES ? GT_B_BYTES : GT_STAGE_BYTES;
+    static constexpr int B_OFF = ARES ? 0 : GT_A_BYTES;                       // B inside a stage
+    static constexpr int RING = ARES ? VDB_GT_RING_ARES : GT_RING;           // keys per ring (one ring per epilogue thread)
+    static constexpr int RING_STRIDE = RING | 1;                              // odd: same-slot appends of a warp spread over banks
+    static constexpr int OFF_STAGE = A_RES_BYTES;
+    static constexpr int OFF_RING = OFF_STAGE + STAGES * STAGE_BYTES;
+    static constexpr int OFF_NORM = OFF_RING + GT_EPI_THREADS * RING_STRIDE * 8;
+    static constexpr int OFF_BAR = OFF_NORM + 2 * GT_BN * 4;                  // + 2048
+    static constexpr int BAR_BYTES = 256;                                     // full/empty per stage, 2+2 TMEM, 2 A, TMEM pointer
+    static constexpr int OFF_CTL = OFF_BAR + BAR_BYTES;
+    static constexpr int BYTES = OFF_CTL + GT_CTL_BYTES + 1024;               // + slack for the 1024-byte alignment
+    static_assert((2 * STAGES + 6) * 8 + 4 <= BAR_BYTES, "barrier block");
+    static_assert(RING >= 8, "the epilogue reserves room for 4 appends at a time");
+    static_assert(BYTES <= 232448, "shared memory budget");
+};
 struct GemmParams {
     uint32_t n_rows, nq;
     int num_kb;              // k-blocks per row (row bytes / 128)
@@ -110,6 +135,12 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
+}
+// true in exactly one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -242,27 +273,32 @@ __device__ __forceinline__ ItemRange item_range(const GemmParams& p, int item) {
 // ------------------------------------------------------------------------------------------
 // K2
 // ------------------------------------------------------------------------------------------
-template <bool F16, bool L2>
+template <bool F16, bool L2, bool ARES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GT_THREADS, 1)
 gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     pdl_prologue();
+    using SM = GtSmem<ARES>;
+    constexpr int NST = SM::STAGES, RING = SM::RING, RING_STRIDE = SM::RING_STRIDE;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* ring_all = reinterpret_cast<uint64_t*>(smem + GT_OFF_RING);
-    float* norm_s = reinterpret_cast<float*>(smem + GT_OFF_NORM);   // [2][256]
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + GT_OFF_BAR);
-    uint64_t* empty = full + GT_STAGES;
-    uint64_t* tmem_full = empty + GT_STAGES;
+    uint8_t* stage_base = smem + SM::OFF_STAGE;                     // ring of operand stages (ARES: after the resident queries)
+    uint64_t* ring_all = reinterpret_cast<uint64_t*>(smem + SM::OFF_RING);
+    float* norm_s = reinterpret_cast<float*>(smem + SM::OFF_NORM);   // [2][256]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
+    uint64_t* empty = full + NST;
+    uint64_t* tmem_full = empty + NST;
     uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    EpiCtl* ctl = reinterpret_cast<EpiCtl*>(smem + GT_OFF_CTL);
+    uint64_t* a_full = tmem_empty + 2;       // ARES: the pair's query block has landed (leader's barrier counts both CTAs' bytes)
+    uint64_t* a_empty = a_full + 1;          // ARES: every MMA that reads the resident block has retired
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_empty + 1);
+    EpiCtl* ctl = reinterpret_cast<EpiCtl*>(smem + SM::OFF_CTL);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta_rank = cluster_ctarank();     // 0 = pair leader (issues the MMAs), 1 = peer
     const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < GT_STAGES; ++s) {
+        for (int s = 0; s < NST; ++s) {
             mbar_init(&full[s], 1);      // leader's arrive.expect_tx; bytes of BOTH CTAs' copies land on the leader's barrier
             mbar_init(&empty[s], 1);     // one multicast tcgen05.commit per use
         }
@@ -270,6 +306,8 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             mbar_init(&tmem_full[a], 1);
             mbar_init(&tmem_empty[a], 2 * GT_EPI_WARPS);   // 8 epilogue warps x 2 CTAs arrive on the LEADER's barrier
         }
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
         fence_barrier_init();
     }
     if (threadIdx.x < GT_EPI_THREADS) {
@@ -293,34 +331,61 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             uint64_t pol_stream;
             asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_stream));
             const uint64_t pol_keep = l2_policy_evict_last();
-            uint32_t it = 0;
+            uint32_t it = 0, a_loads = 0;
+            int cur_mb = -1;
             for (int item = pair; item < p.n_items; item += num_pairs) {
                 const ItemRange ir = item_range(p, item);
                 const int arow = ir.mb * (2 * GT_BM) + (int)cta_rank * GT_BM;
+                if (ARES && ir.mb != cur_mb) {
+                    // (re)load the resident query block: all k-blocks at once, after the MMAs on the previous block
+                    if (a_loads) mbar_wait(a_empty, (a_loads - 1) & 1);
+                    if (cta_rank == 0) mbar_arrive_expect_tx(a_full, 2u * (uint32_t)p.num_kb * GT_A_BYTES);
+                    const uint32_t abar = map_to_cta(smem_u32(a_full), 0);
+                    for (int kb = 0; kb < p.num_kb; ++kb) tma_load_2d(smem + kb * GT_A_BYTES, &tmA, kb * p.kb_elems, arow, abar, pol_keep);
+                    cur_mb = ir.mb;
+                    ++a_loads;
+                }
                 for (int pos = ir.p0; pos < ir.p1; ++pos) {
                     const int tile = (int)bitrev((uint32_t)pos, p.bits);
                     if (tile >= p.n_tiles) continue;
                     const int brow = tile * GT_BN + (int)cta_rank * GT_BN_HALF;
                     for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
-                        const int s = it % GT_STAGES;
-                        const uint32_t ph = (it / GT_STAGES) & 1;
+                        const int s = it % NST;
+                        const uint32_t ph = (it / NST) & 1;
                         mbar_wait(&empty[s], ph ^ 1);
-                        if (cta_rank == 0) mbar_arrive_expect_tx(&full[s], 2 * GT_STAGE_BYTES);
+                        if (cta_rank == 0) mbar_arrive_expect_tx(&full[s], 2 * SM::STAGE_BYTES);
                         const uint32_t bar = map_to_cta(smem_u32(&full[s]), 0);
-                        uint8_t* sa = smem + s * GT_STAGE_BYTES;
-                        tma_load_2d(sa, &tmA, kb * p.kb_elems, arow, bar, pol_keep);
-                        tma_load_2d(sa + GT_A_BYTES, &tmB, kb * p.kb_elems, brow, bar, pol_stream);
+                        uint8_t* sa = stage_base + s * SM::STAGE_BYTES;
+                        if (!ARES) tma_load_2d(sa, &tmA, kb * p.kb_elems, arow, bar, pol_keep);
+                        tma_load_2d(sa + SM::B_OFF, &tmB, kb * p.kb_elems, brow, bar, pol_stream);
                     }
                 }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer (pair leader only): M = 256 (2 x 128 queries) x N = 256 =================
-        if (lane == 0 && cta_rank == 0) {
+        // The WHOLE warp walks the loops and waits on the barriers; one elected lane issues.  Everything the
+        // tcgen05 instructions take (descriptors, TMEM address, barrier address) is then warp-uniform by
+        // construction and lives in uniform registers.  With a single lane inside `if (lane == 0)` the compiler
+        // cannot know that and wraps every MMA in an elect / R2UR loop: ~106 dependent instructions per k-block,
+        // ~156 cycles per MMA against the 128 the tensor pipe needs -- the issuer, not the data, paced the
+        // kernel (ncu source page: no samples on the full / tmem_empty waits, all on the issue loop).
+        if (cta_rank == 0) {
             constexpr uint32_t idesc = make_idesc(F16 ? 0u : 2u, 2 * GT_BM, GT_BN);
-            uint32_t it = 0, tcount = 0;
+            const uint32_t stage0 = smem_u32(stage_base), a_res0 = smem_u32(smem);
+            const uint64_t desc_hi = make_smem_desc(0);              // everything but the 14-bit start address
+            uint32_t it = 0, tcount = 0, a_loads = 0;
+            int cur_mb = -1;
             for (int item = pair; item < p.n_items; item += num_pairs) {
                 const ItemRange ir = item_range(p, item);
+                if (ARES && ir.mb != cur_mb) {
+                    if (a_loads && elect_one()) umma_commit_pair(a_empty);   // both producers may overwrite the block once these MMAs retire
+                    __syncwarp();
+                    mbar_wait(a_full, a_loads & 1);
+                    tc_fence_after();
+                    cur_mb = ir.mb;
+                    ++a_loads;
+                }
                 for (int pos = ir.p0; pos < ir.p1; ++pos) {
                     if ((int)bitrev((uint32_t)pos, p.bits) >= p.n_tiles) continue;
                     const uint32_t acc = tcount & 1;
@@ -328,18 +393,22 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * GT_BN;
                     for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
-                        const int s = it % GT_STAGES;
-                        const uint32_t ph = (it / GT_STAGES) & 1;
+                        const uint32_t s = it % NST;
+                        const uint32_t ph = (it / NST) & 1;
                         mbar_wait(&full[s], ph);
                         tc_fence_after();
-                        const uint32_t sa = smem_u32(smem + s * GT_STAGE_BYTES);
-                        const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + GT_A_BYTES);
+                        const uint32_t sa = stage0 + s * SM::STAGE_BYTES;
+                        const uint64_t adesc = desc_hi | (uint64_t)(((ARES ? a_res0 + (uint32_t)kb * GT_A_BYTES : sa) & 0x3FFFFu) >> 4);
+                        const uint64_t bdesc = desc_hi | (uint64_t)(((sa + SM::B_OFF) & 0x3FFFFu) >> 4);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4)   // 4 x 32 bytes of K per 128-byte swizzle atom
-                            umma<F16>(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
-                        umma_commit_pair(&empty[s]);           // both CTAs may refill this stage once the MMAs retire
+                            for (int k4 = 0; k4 < 4; ++k4)   // 4 x 32 bytes of K per 128-byte swizzle atom
+                                umma<F16>(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
+                            umma_commit_pair(&empty[s]);           // both CTAs may refill this stage once the MMAs retire
+                            if (kb == p.num_kb - 1) umma_commit_pair(&tmem_full[acc]);   // accumulators ready in both CTAs' TMEM
+                        }
+                        __syncwarp();
                     }
-                    umma_commit_pair(&tmem_full[acc]);         // accumulators ready in both CTAs' TMEM
                     ++tcount;
                 }
             }
@@ -382,10 +451,10 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 for (int h = 0; h < RPL; ++h) {
                     if (n[h]) {
                         const int ri = base + h * 32 + lane;
-                        const uint64_t* ring = ring_all + (size_t)ri * GT_RING_STRIDE;
+                        const uint64_t* ring = ring_all + (size_t)ri * RING_STRIDE;
                         uint64_t* dst = p.buf + (size_t)q[h] * p.cap;
                         for (uint32_t i = 0; i < n[h]; ++i) {
-                            const uint64_t key = *reinterpret_cast<const volatile uint64_t*>(ring + ((t[h] + i) % GT_RING));
+                            const uint64_t key = *reinterpret_cast<const volatile uint64_t*>(ring + ((t[h] + i) % RING));
                             if (slot[h] + (int)i < p.cap) dst[slot[h] + i] = key;     // beyond cap: counted, flagged by K2s
                         }
                     }
@@ -411,9 +480,9 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int half = ew >> 2;                          // which 128 columns
         const int ql = quad * 32 + lane;                   // TMEM lane == query within this CTA's block
         const int col0 = half * (GT_BN / 2);
-        const uint32_t my_ring_s = smem_u32(ring_all + (size_t)et * GT_RING_STRIDE);
+        const uint32_t my_ring_s = smem_u32(ring_all + (size_t)et * RING_STRIDE);
         volatile uint32_t* my_tail = &ctl->tail[et];
-        uint32_t head = 0, slot = 0;      // keys appended so far; slot == head % GT_RING
+        uint32_t head = 0, slot = 0;      // keys appended so far; slot == head % RING
         uint32_t tail_seen = 0;           // last value read from the movers' tail counter
         bool dirty = false;               // keys appended since head was last published
         uint32_t tcount = 0;
@@ -547,9 +616,9 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                                 if (g[gi] > nthr) {
                                     // up to 4 appends: make room first (tail_seen is a stale copy: the ring can only
                                     // be emptier than it says); publish what is pending before waiting for the movers
-                                    if (head - tail_seen > (uint32_t)(GT_RING - 4)) {
+                                    if (head - tail_seen > (uint32_t)(RING - 4)) {
                                         if (dirty) { __threadfence_block(); ctl->head_pub[et] = head; dirty = false; }
-                                        while (head - (tail_seen = *my_tail) > (uint32_t)(GT_RING - 4)) __nanosleep(32);
+                                        while (head - (tail_seen = *my_tail) > (uint32_t)(RING - 4)) __nanosleep(32);
                                     }
 #pragma unroll
                                     for (int e = 0; e < 4; ++e) {
@@ -557,7 +626,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                                             st_shared_u64(my_ring_s + slot * 8,
                                                           make_key(-s[4 * gi + e], row0 + col0 + c * 32 + 4 * gi + e));
                                             ++head;
-                                            if (++slot == GT_RING) slot = 0;
+                                            if (++slot == RING) slot = 0;
                                         }
                                     }
                                     dirty = true;
@@ -1358,16 +1427,17 @@ static int current_device_slot() {
     return dev & (MAX_DEVICES - 1);
 }
 
-template <bool F16, bool L2>
+template <bool F16, bool L2, bool ARES>
 static cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& gp, int grid, cudaStream_t st) {
     static bool configured[MAX_DEVICES] = {};
     const int slot = current_device_slot();
+    constexpr int smem_bytes = GtSmem<ARES>::BYTES;
     if (!configured[slot]) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_filter_kernel<F16, L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES_FILTER);
+        cudaError_t e = cudaFuncSetAttribute(gemm_filter_kernel<F16, L2, ARES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e != cudaSuccess) return e;
         configured[slot] = true;
     }
-    cudaError_t e = launch_pdl(gemm_filter_kernel<F16, L2>, dim3(grid), dim3(GT_THREADS), GT_SMEM_BYTES_FILTER, st, tmA, tmB, gp);
+    cudaError_t e = launch_pdl(gemm_filter_kernel<F16, L2, ARES>, dim3(grid), dim3(GT_THREADS), smem_bytes, st, tmA, tmB, gp);
     count_launch();
     return e != cudaSuccess ? e : cudaGetLastError();
 }
@@ -1554,6 +1624,8 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
     sp.np2 = sel_np;
     const size_t sel_smem = ((size_t)sel_np + kp) * 8;
 
+    // query-resident kernel variant for rows of at most 8 k-blocks (VDB_ARES: bit 0 = probe, bit 1 = levels; A/B runs)
+    static const int ares_mode = env_int("VDB_ARES", 3);
     auto run_level = [&](int p0, int p1, bool probe) -> cudaError_t {
         gp.pos_begin = p0; gp.pos_end = p1; gp.probe = probe ? 1 : 0;
         gp.S = choose_slices(MB, p1 - p0, num_pairs_max);
@@ -1561,8 +1633,14 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
         const int grid = 2 * std::min(gp.n_items, num_pairs_max);   // whole CTA pairs
         cudaError_t le;
         if (a.prof_begin) a.prof_begin(a.prof_ctx, st);
-        if (g16) le = l2 ? launch_gemm<true, true>(tmA, tmB, gp, grid, st) : launch_gemm<true, false>(tmA, tmB, gp, grid, st);
-        else       le = l2 ? launch_gemm<false, true>(tmA, tmB, gp, grid, st) : launch_gemm<false, false>(tmA, tmB, gp, grid, st);
+        const bool ares = gp.num_kb <= GtSmem<true>::A_RES_KB && (probe ? (ares_mode & 1) : (ares_mode & 2)) != 0;
+        if (g16) {
+            if (ares) le = l2 ? launch_gemm<true, true, true>(tmA, tmB, gp, grid, st) : launch_gemm<true, false, true>(tmA, tmB, gp, grid, st);
+            else      le = l2 ? launch_gemm<true, true, false>(tmA, tmB, gp, grid, st) : launch_gemm<true, false, false>(tmA, tmB, gp, grid, st);
+        } else {
+            if (ares) le = l2 ? launch_gemm<false, true, true>(tmA, tmB, gp, grid, st) : launch_gemm<false, false, true>(tmA, tmB, gp, grid, st);
+            else      le = l2 ? launch_gemm<false, true, false>(tmA, tmB, gp, grid, st) : launch_gemm<false, false, false>(tmA, tmB, gp, grid, st);
+        }
         if (a.prof_end) a.prof_end(a.prof_ctx, st);
         return le;
     };

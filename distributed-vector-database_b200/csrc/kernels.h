@@ -78,6 +78,11 @@ struct XchgParams {
     unsigned int* done_counter;    // local, zeroed by the launcher
 };
 cudaError_t launch_exchange_merge(const XchgParams& x, const MergeParams& mp, int num_sms, cudaStream_t st);
+// arrival signal / wait of the copy-engine query all-gather (vdb_xchg_gather_queries / vdb_xchg_wait_queries)
+struct XchgSignal { int world; uint32_t value; uint32_t* flag[XCHG_MAX_WORLD]; };   // this rank's word in every rank's array
+struct XchgWait { int world; uint32_t value; const uint32_t* flag; unsigned long long timeout_ns; uint32_t* err; };
+cudaError_t launch_xchg_signal(const XchgSignal& s, cudaStream_t st);
+cudaError_t launch_xchg_wait(const XchgWait& w, cudaStream_t st);
 
 // ---- K0 / K3 / utilities (insert.cu) ------------------------------------------------------
 // queries [nq][dim] fp32 -> prepared [nq][ld] fp32 (normalised when cosine, zero padded),

@@ -296,6 +296,48 @@ cudaError_t launch_exchange_merge(const XchgParams& x, const MergeParams& mp, in
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------
+// Query all-gather over the copy engines: every rank DMAs its slice of the batch into every peer's query slot
+// (cudaMemcpyAsync over NVLink, no SM), then this one-warp kernel publishes "slice of batch `value` has landed" in
+// every rank's arrival array; the consumer's one-warp wait kernel sits in front of its search.  Neither kernel needs
+// more than a warp slot, and the signal waits for nothing: unlike a collective kernel on a second stream it cannot be
+// kept off the SMs by -- or keep off the SMs -- the cooperative exchange kernel.
+// ------------------------------------------------------------------------------------------
+__global__ void xchg_signal_kernel(const XchgSignal s) {
+    __threadfence_system();
+    if (threadIdx.x < s.world) *reinterpret_cast<volatile uint32_t*>(s.flag[threadIdx.x]) = s.value;
+}
+
+__global__ void xchg_wait_kernel(const XchgWait w) {
+    if (threadIdx.x < w.world) {
+        const volatile uint32_t* f = w.flag + threadIdx.x;
+        const uint64_t t0 = global_timer_ns();
+        while (*f < w.value) {
+            __nanosleep(200);
+            if (global_timer_ns() - t0 > w.timeout_ns) {
+                if (atomicCAS(reinterpret_cast<unsigned int*>(w.err), 0u, (unsigned int)XCHG_ERR_TIMEOUT) == 0u) {
+                    w.err[1] = w.value;
+                    w.err[2] = (uint32_t)threadIdx.x;
+                    __threadfence_system();
+                }
+                break;
+            }
+        }
+    }
+    __threadfence_system();
+}
+
+cudaError_t launch_xchg_signal(const XchgSignal& s, cudaStream_t st) {
+    xchg_signal_kernel<<<1, 32, 0, st>>>(s);
+    count_launch();
+    return cudaGetLastError();
+}
+cudaError_t launch_xchg_wait(const XchgWait& w, cudaStream_t st) {
+    xchg_wait_kernel<<<1, 32, 0, st>>>(w);
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t launch_merge_topk(const MergeParams& p, cudaStream_t st) {
     if (p.nq == 0) return cudaSuccess;
     if (p.k_out < 1 || p.k_out > MERGE_BUF / 2) return cudaErrorInvalidValue;

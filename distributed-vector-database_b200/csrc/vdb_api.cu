@@ -1178,6 +1178,8 @@ struct vdb_xchg {
     uint8_t* peer_base[XCHG_MAX_WORLD] = {};       // peer mappings ([rank] == base)
     bool connected = false;
     unsigned int* done_counter = nullptr;
+    // query all-gather over the copy engines (vdb_xchg_gather_queries): [2 slots][world] arrival words, then 2 query slots
+    size_t q_flag_off = 0, q_buf_off = 0, q_slot_bytes = 0;
     uint32_t* h_err = nullptr;                     // pinned, mapped: [code, step, peer, -] written by the kernel
     uint32_t* d_err = nullptr;                     // device alias of h_err
     unsigned long long timeout_ns = 30ull * 1000000000ull;
@@ -1196,6 +1198,11 @@ static int xchg_error(vdb_xchg* x) {
 }
 
 int vdb_xchg_create(int device, int rank, int world, size_t max_slice, int max_k, vdb_xchg_t** out, unsigned char* handle64) {
+    return vdb_xchg_create_q(device, rank, world, max_slice, max_k, 0, out, handle64);
+}
+
+int vdb_xchg_create_q(int device, int rank, int world, size_t max_slice, int max_k, size_t query_slot_bytes, vdb_xchg_t** out,
+                      unsigned char* handle64) {
     if (!out || !handle64) return fail(VDB_EINVAL, "null argument");
     *out = nullptr;
     if (world < 1 || world > XCHG_MAX_WORLD || rank < 0 || rank >= world) return fail(VDB_EINVAL, "bad rank/world (at most 16 ranks)");
@@ -1216,8 +1223,15 @@ int vdb_xchg_create(int device, int rank, int world, size_t max_slice, int max_k
     x->stride_src = max_slice * (size_t)max_k;                       // keys per source rank
     x->stride_parity = x->stride_src * world;
     x->total_bytes = x->flag_bytes + 2 * x->stride_parity * sizeof(uint64_t);
+    if (query_slot_bytes) {                                          // [arrival words 256 B][slot 0][slot 1], 256-byte aligned
+        x->q_flag_off = (x->total_bytes + 255) / 256 * 256;
+        x->q_slot_bytes = (query_slot_bytes + 255) / 256 * 256;
+        x->q_buf_off = x->q_flag_off + 256;
+        x->total_bytes = x->q_buf_off + 2 * x->q_slot_bytes;
+    }
     CU_TRY(cudaMalloc((void**)&x->base, x->total_bytes));
     CU_TRY(cudaMemset(x->base, 0, x->flag_bytes));
+    if (query_slot_bytes) CU_TRY(cudaMemset(x->base + x->q_flag_off, 0, 256));
     CU_TRY(cudaMalloc((void**)&x->done_counter, sizeof(unsigned int)));
     CU_TRY(cudaHostAlloc((void**)&x->h_err, 4 * sizeof(uint32_t), cudaHostAllocMapped));
     memset(x->h_err, 0, 4 * sizeof(uint32_t));
@@ -1283,6 +1297,50 @@ int vdb_xchg_merge_dev(vdb_xchg_t* x, const float* d_dist, const int64_t* d_ids,
     mp.nq = xp.owned; mp.n_in = x->world * k; mp.k_out = k;
     mp.out_ids = o_ids; mp.out_dist = o_dist;
     CU_TRY(launch_exchange_merge(xp, mp, x->num_sms, (cudaStream_t)stream));
+    return VDB_OK;
+}
+
+// ---- query all-gather over the copy engines ---------------------------------------------------------------------
+void* vdb_xchg_query_slot(vdb_xchg_t* x, int slot) {
+    if (!x || !x->q_slot_bytes || slot < 0 || slot > 1) return nullptr;
+    return x->base + x->q_buf_off + (size_t)slot * x->q_slot_bytes;
+}
+
+int vdb_xchg_gather_queries(vdb_xchg_t* x, const void* slice, size_t slice_bytes, int slot, uint32_t batch_no, void* stream) {
+    if (!x || !slice) return fail(VDB_EINVAL, "null argument");
+    if (!x->q_slot_bytes) return fail(VDB_EINVAL, "the exchange was created without query slots (vdb_xchg_create_q)");
+    if (!x->connected && x->world > 1) return fail(VDB_EINVAL, "vdb_xchg_connect has not been called");
+    if (slot < 0 || slot > 1 || slice_bytes * (size_t)x->world > x->q_slot_bytes || batch_no == 0)
+        return fail(VDB_EINVAL, "bad slot / slice size / batch number");
+    if (int rc = xchg_error(x)) return rc;
+    CU_TRY(cudaSetDevice(x->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t off = x->q_buf_off + (size_t)slot * x->q_slot_bytes + (size_t)x->rank * slice_bytes;
+    // own slot first (host or device source), then the same bytes into every peer's slot: DMA over NVLink, no SM
+    CU_TRY(cudaMemcpyAsync(x->base + off, slice, slice_bytes, cudaMemcpyDefault, st));
+    for (int r = 0; r < x->world; ++r)
+        if (r != x->rank) CU_TRY(cudaMemcpyAsync(x->peer_base[r] + off, x->base + off, slice_bytes, cudaMemcpyDeviceToDevice, st));
+    XchgSignal sg{};
+    sg.world = x->world;
+    for (int r = 0; r < x->world; ++r)
+        sg.flag[r] = reinterpret_cast<uint32_t*>(x->peer_base[r] + x->q_flag_off) + slot * XCHG_MAX_WORLD + x->rank;
+    sg.value = batch_no;
+    CU_TRY(launch_xchg_signal(sg, st));
+    return VDB_OK;
+}
+
+int vdb_xchg_wait_queries(vdb_xchg_t* x, int slot, uint32_t batch_no, void* stream) {
+    if (!x) return fail(VDB_EINVAL, "null argument");
+    if (!x->q_slot_bytes || slot < 0 || slot > 1) return fail(VDB_EINVAL, "bad slot, or no query slots");
+    if (int rc = xchg_error(x)) return rc;
+    CU_TRY(cudaSetDevice(x->device));
+    XchgWait w{};
+    w.world = x->world;
+    w.flag = reinterpret_cast<const uint32_t*>(x->base + x->q_flag_off) + slot * XCHG_MAX_WORLD;
+    w.value = batch_no;
+    w.timeout_ns = x->timeout_ns;
+    w.err = x->d_err;
+    CU_TRY(launch_xchg_wait(w, (cudaStream_t)stream));
     return VDB_OK;
 }
 

@@ -133,6 +133,20 @@ typedef struct vdb_xchg vdb_xchg_t;
 int vdb_xchg_create(int device, int rank, int world, size_t max_slice, int max_k, vdb_xchg_t **out,
                     unsigned char *handle64);
 int vdb_xchg_connect(vdb_xchg_t *x, const unsigned char *handles /* world * 64 bytes */);
+/* The broadcast of the queries (coordinator/handler.py:186-197: the same SearchRequest to every node) for ranks that
+ * each hold a slice of the batch, over the COPY ENGINES: create_q reserves two query slots of query_slot_bytes in the
+ * exported buffer; gather_queries copies this rank's slice (host or device pointer) into its place of slot `slot`
+ * here and -- by DMA over NVLink -- on every peer, then publishes batch_no (1, 2, 3, ...; slot = batch_no & 1 by
+ * convention) in every rank's arrival array, all enqueued on `stream` (a copy stream); wait_queries enqueues, on the
+ * stream that will search, a one-warp kernel that waits until every rank's slice of batch_no has landed in the local
+ * slot (bounded like the merge; errors through vdb_xchg_status).  No collective-library kernel is involved, so it
+ * may overlap the previous batch's search and exchange.  The caller must not gather batch i into a slot before its
+ * own merge of batch i-2 has completed (then every peer has finished searching that slot). */
+int vdb_xchg_create_q(int device, int rank, int world, size_t max_slice, int max_k, size_t query_slot_bytes,
+                      vdb_xchg_t **out, unsigned char *handle64);
+void *vdb_xchg_query_slot(vdb_xchg_t *x, int slot);   /* device pointer of the local slot: [world][slice] rows */
+int vdb_xchg_gather_queries(vdb_xchg_t *x, const void *slice, size_t slice_bytes, int slot, uint32_t batch_no, void *stream);
+int vdb_xchg_wait_queries(vdb_xchg_t *x, int slot, uint32_t batch_no, void *stream);
 int vdb_xchg_merge_dev(vdb_xchg_t *x, const float *d_dist, const int64_t *d_ids, size_t nq, int k,
                        float *o_dist, int64_t *o_ids, void *stream);
 /* 0, or VDB_ECUDA once a step has failed: a peer did not arrive within the timeout (30 s; VDB_XCHG_TIMEOUT_MS),
