@@ -471,16 +471,37 @@ class Arm:
             return {"sec": float(ms.item()) * 1e-3, "steps": total_steps, "kern_ns": kern_ns, "nprof": nprof,
                     "launches": launches, "ids": got[0], "dist": got[1]}
 
-        def e2e_leg(nq, nsteps, nwarm):
+        def e2e_leg(nq, nsteps, nwarm, in_flight=1):
             """through the public host-buffer API: H2D of the queries and D2H of the results inside the timed region"""
             qh = vdb.pinned_empty((nq, wl.dim), np.float32)   # page-locked host buffers, filled outside the timed region
             qh[:] = self.make_queries(wl, nq).cpu().numpy()
-            if sx is None:
+            if sx is None and in_flight <= 1:
                 outs = (vdb.pinned_empty((nq, k), np.int64), vdb.pinned_empty((nq, k), np.float32),
                         vdb.pinned_empty((nq,), np.int32))
 
                 def step():
                     return ix.knn_query_padded(qh, k, out=outs)
+
+                def drain():
+                    pass
+            elif sx is None:
+                # the serving steady state of one GPU: two batches in flight through vdb_search_submit / _collect --
+                # the upload of batch i+1 is behind the kernels of batch i; every step still uploads its queries
+                # from page-locked host memory and has its results in host memory when it is collected
+                outs2 = [(vdb.pinned_empty((nq, k), np.int64), vdb.pinned_empty((nq, k), np.float32),
+                          vdb.pinned_empty((nq,), np.int32)) for _ in range(in_flight)]
+                pending, n_sub, out = [], [0], [None]
+
+                def step():
+                    pending.append(ix.submit_query(qh, k, out=outs2[n_sub[0] % in_flight]))
+                    n_sub[0] += 1
+                    if len(pending) == in_flight:
+                        out[0] = ix.collect_query(pending.pop(0))
+                    return out[0]
+
+                def drain():
+                    while pending:
+                        out[0] = ix.collect_query(pending.pop(0))
             else:
                 # the batch arrives split over the ranks' hosts: each rank passes ITS slice and gets that slice's
                 # results; a batch that does not divide by N (the single query) is passed whole by every rank
@@ -513,14 +534,12 @@ class Arm:
 
             for _ in range(nwarm):
                 step()
-            if sx is not None:
-                drain()
+            drain()
             self.barrier()
             t0 = time.perf_counter()
             for _ in range(nsteps):
                 step()
-            if sx is not None:
-                drain()                                     # the last results are on the host before the clock stops
+            drain()                                         # the last results are on the host before the clock stops
             torch.cuda.synchronize()
             dt = torch.tensor([time.perf_counter() - t0], device=dev)
             if world > 1:
@@ -534,7 +553,8 @@ class Arm:
 
         with ClockSampler(self.local) as clk:
             main = device_leg(B, steps, warmup)
-            e2e_sec = e2e_leg(B, steps, warmup)
+            e2e_sec = e2e_leg(B, steps, warmup, in_flight=2)
+            e2e_serial_sec = e2e_leg(B, steps, warmup) if world == 1 else None
             single = None
             if not a.no_single:
                 ss = a.single_steps or max(5 * steps, 50)
@@ -653,7 +673,12 @@ class Arm:
                       "tf32 operands / f32 accumulate, exact f32 re-rank" if tf32_path else "f16-stored / f32 accumulate"),
             "e2e": {"value": B * steps / e2e_sec, "unit": "queries/s", "h2d_bytes_per_step": B * wl.dim * 4,
                     "d2h_bytes_per_step": B * k * 12 + (B * 4 if world == 1 else 0),
-                    "in_flight": 1 if world == 1 else 2},
+                    "in_flight": 2,
+                    "one_at_a_time": B * steps / e2e_serial_sec if e2e_serial_sec else None,
+                    "note": "two batches in flight (" + ("vdb_search_submit / vdb_search_collect" if world == 1 else
+                                                         "ShardedIndex.submit_host / collect") +
+                            "): every step uploads its queries from page-locked host memory and has its results in host "
+                            "memory when collected; one_at_a_time = the blocking call, one batch after the other"},
             "gpu_launches": main["launches"], "roofline": roof, "single_query": single, "sustained": sustained,
             "two_streams": two_streams,
             "check": check, "cpu_baseline": cpu, "clocks": clk.summary(),

@@ -32,6 +32,8 @@ SIGNATURES = {
     "vdb_mark_deleted": (C.c_int, [_vp, _i64p, C.c_size_t]),
     "vdb_unmark_deleted": (C.c_int, [_vp, _i64p, C.c_size_t]),
     "vdb_search": (C.c_int, [_vp, _f32p, C.c_size_t, C.c_int, _i64p, _f32p, _i32p]),
+    "vdb_search_submit": (C.c_int, [_vp, _f32p, C.c_size_t, C.c_int, _i64p, _f32p, _i32p, C.POINTER(_vp)]),
+    "vdb_search_collect": (C.c_int, [_vp]),
     "vdb_host_alloc": (_vp, [C.c_size_t]),
     "vdb_host_free": (None, [_vp]),
     "vdb_search_dev": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int, _vp, _vp, _vp, _vp]),

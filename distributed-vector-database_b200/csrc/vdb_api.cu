@@ -728,9 +728,23 @@ static int mark_impl(vdb* db, const int64_t* labels, size_t n, bool set) {
 int vdb_mark_deleted(vdb_t* db, const int64_t* labels, size_t n) { return mark_impl(db, labels, n, true); }
 int vdb_unmark_deleted(vdb_t* db, const int64_t* labels, size_t n) { return mark_impl(db, labels, n, false); }
 
-int vdb_search(vdb_t* db, const float* queries, size_t nq, int k, int64_t* out_labels, float* out_dist, int* out_counts) {
+// A host-buffer search in two halves: submit enqueues upload + search + download on a workspace's own stream and
+// returns; collect waits for it.  vdb_search is submit + collect; a caller that keeps two tickets open has the upload
+// of batch i+1 (and, on the SMs, the short launches of its search) behind the kernels of batch i.
+struct vdb_ticket {
+    vdb* db = nullptr;
+    Workspace* ws = nullptr;
+    size_t nq = 0, nout = 0;
+    bool out_pinned = false;
+    int64_t* out_labels = nullptr; float* out_dist = nullptr; int* out_counts = nullptr;
+};
+
+int vdb_search_submit(vdb_t* db, const float* queries, size_t nq, int k, int64_t* out_labels, float* out_dist, int* out_counts,
+                      vdb_ticket_t** ticket) {
+    if (!ticket) return fail(VDB_EINVAL, "ticket is null");
+    *ticket = nullptr;
     if (!db) return fail(VDB_EINVAL, "db is null");
-    if (nq == 0) return VDB_OK;
+    if (nq == 0) { *ticket = new vdb_ticket(); return VDB_OK; }
     if (!queries || !out_labels || !out_dist) return fail(VDB_EINVAL, "null buffer");
     int rc = check_k(db, k, nq);
     if (rc) return rc;
@@ -745,7 +759,7 @@ int vdb_search(vdb_t* db, const float* queries, size_t nq, int k, int64_t* out_l
     // the CALLER's stream: order this call's use of the scratch after them on the GPU
     if (ws->used) {
         CU_TRY(cudaStreamWaitEvent(st, ws->done, 0));
-        ws->used = false;          // this call synchronises `st` before it returns: nothing stays in flight
+        ws->used = false;          // the ticket holds the workspace until collect has synchronised `st`
     }
     const size_t qelems = nq * (size_t)db->dim, nout = nq * (size_t)k;
     CU_TRY(grow(ws->d_q_in, ws->q_in_cap, qelems));
@@ -767,16 +781,40 @@ int vdb_search(vdb_t* db, const float* queries, size_t nq, int k, int64_t* out_l
     float* h_dist = reinterpret_cast<float*>(ws->h_out + nout * sizeof(int64_t));
     int* h_cnt = reinterpret_cast<int*>(ws->h_out + nout * (sizeof(int64_t) + sizeof(float)));
     if (out_pinned) { h_ids = out_labels; h_dist = out_dist; h_cnt = out_counts; }
-    CU_TRY(cudaMemcpyAsync(h_ids, ws->d_ids, nout * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaMemcpyAsync(h_dist, ws->d_dist, nout * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (h_cnt) CU_TRY(cudaMemcpyAsync(h_cnt, ws->d_cnt, nq * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaStreamSynchronize(st));
-    if (!out_pinned) {
-        memcpy(out_labels, h_ids, nout * sizeof(int64_t));
-        memcpy(out_dist, h_dist, nout * sizeof(float));
-        if (out_counts) memcpy(out_counts, h_cnt, nq * sizeof(int));
+    cudaError_t ce = cudaMemcpyAsync(h_ids, ws->d_ids, nout * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_dist, ws->d_dist, nout * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess && h_cnt) ce = cudaMemcpyAsync(h_cnt, ws->d_cnt, nq * sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (ce != cudaSuccess) { cudaStreamSynchronize(st); return fail(VDB_ECUDA, cudaGetErrorString(ce)); }
+    auto* t = new vdb_ticket();
+    t->db = db; t->ws = ws; t->nq = nq; t->nout = nout; t->out_pinned = out_pinned;
+    t->out_labels = out_labels; t->out_dist = out_dist; t->out_counts = out_counts;
+    guard.w = nullptr;             // the ticket owns the workspace now
+    *ticket = t;
+    return VDB_OK;
+}
+
+int vdb_search_collect(vdb_ticket_t* t) {
+    if (!t) return fail(VDB_EINVAL, "ticket is null");
+    std::unique_ptr<vdb_ticket> own(t);
+    if (!t->ws) return VDB_OK;     // empty batch
+    WsGuard guard{t->db, t->ws};
+    cudaSetDevice(t->db->device);
+    CU_TRY(cudaStreamSynchronize(t->ws->stream));
+    if (!t->out_pinned) {
+        const uint8_t* h = t->ws->h_out;
+        memcpy(t->out_labels, h, t->nout * sizeof(int64_t));
+        memcpy(t->out_dist, h + t->nout * sizeof(int64_t), t->nout * sizeof(float));
+        if (t->out_counts) memcpy(t->out_counts, h + t->nout * (sizeof(int64_t) + sizeof(float)), t->nq * sizeof(int));
     }
     return VDB_OK;
+}
+
+int vdb_search(vdb_t* db, const float* queries, size_t nq, int k, int64_t* out_labels, float* out_dist, int* out_counts) {
+    if (!db) return fail(VDB_EINVAL, "db is null");
+    if (nq == 0) return VDB_OK;
+    vdb_ticket_t* t = nullptr;
+    int rc = vdb_search_submit(db, queries, nq, k, out_labels, out_dist, out_counts, &t);
+    return rc ? rc : vdb_search_collect(t);
 }
 
 void* vdb_host_alloc(size_t bytes) {

@@ -144,6 +144,36 @@ class Index:
                    "knn_query")
         return labels, dist, counts
 
+    def submit_query(self, data, k: int, out=None):
+        """First half of `knn_query_padded`: enqueue upload + search + download and return a ticket for
+        `collect_query`.  A caller that keeps two tickets open overlaps the upload of one batch with the search
+        of the other (vdb_search_submit / vdb_search_collect).  `data` and `out` must stay untouched until
+        the ticket has been collected."""
+        h = self._handle()
+        q = _as_f32_2d(data, self.dim, "query")
+        nq = q.shape[0]
+        k = int(k)
+        if out is not None:
+            labels, dist, counts = out
+            if (labels.shape != (nq, k) or dist.shape != (nq, k) or counts.shape != (nq,) or labels.dtype != np.int64
+                    or dist.dtype != np.float32 or counts.dtype != np.int32
+                    or not (labels.flags.c_contiguous and dist.flags.c_contiguous and counts.flags.c_contiguous)):
+                raise RuntimeError("out must be C-contiguous (int64 [nq,k], float32 [nq,k], int32 [nq])")
+        else:
+            labels = np.empty((nq, k), dtype=np.int64)
+            dist = np.empty((nq, k), dtype=np.float32)
+            counts = np.empty((nq,), dtype=np.int32)
+        t = _ffi.C.c_void_p()
+        _ffi.check(_ffi.lib().vdb_search_submit(h, q.ctypes.data_as(_ffi._f32p), nq, k, labels.ctypes.data_as(_ffi._i64p),
+                                                dist.ctypes.data_as(_ffi._f32p), counts.ctypes.data_as(_ffi._i32p),
+                                                _ffi.C.byref(t)), "submit_query")
+        return (t, q, labels, dist, counts)          # keeps the buffers alive
+
+    def collect_query(self, ticket) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        t, _q, labels, dist, counts = ticket
+        _ffi.check(_ffi.lib().vdb_search_collect(t), "collect_query")
+        return labels, dist, counts
+
     def mark_deleted(self, label) -> None:
         """hnswlib.Index.mark_deleted; replaces the handler's python-side filter (handler.py:378)."""
         ids = np.ascontiguousarray(np.asarray(label, dtype=np.int64).reshape(-1))

@@ -74,6 +74,15 @@ int vdb_unmark_deleted(vdb_t *db, const int64_t *labels, size_t n);
  * fp32 re-rank. */
 int vdb_search(vdb_t *db, const float *queries, size_t nq, int k, int64_t *out_labels,
                float *out_dist, int *out_counts);
+/* The same call in two halves, for a server that keeps more than one batch in flight (the reference's Thrift
+ * server runs one handler call per client thread: datanode/server.py; here one thread can overlap them):
+ * submit enqueues upload + search + download on a stream of its own and returns a ticket; collect waits until the
+ * results are in the caller's buffers and frees the ticket (always call it once per successful submit).  The
+ * buffers must stay valid and untouched in between.  vdb_search == submit + collect. */
+typedef struct vdb_ticket vdb_ticket_t;
+int vdb_search_submit(vdb_t *db, const float *queries, size_t nq, int k, int64_t *out_labels, float *out_dist,
+                      int *out_counts, vdb_ticket_t **ticket);
+int vdb_search_collect(vdb_ticket_t *ticket);
 /* Page-locked host buffers for queries / results: vdb_search moves them by DMA without the staging copy it
  * needs for pageable memory (any page-locked buffer is recognised, these two are a convenience). */
 void *vdb_host_alloc(size_t bytes);

@@ -564,3 +564,29 @@ def test_device_side_fallback_with_arbitrary_labels(vdb):
         msg = R.check_topk(got_l[i], got_d[i], q[i], stored, labels, 10, "cosine", rtol=RTOL)
         assert msg is None, f"query {i}: {msg}"
     assert ix.get_stat("fallback_queries") > 0 and ix.get_stat("tensor_batches") == 1
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+def test_submit_collect_two_batches_in_flight(vdb, pinned):
+    """vdb_search_submit / vdb_search_collect: several tickets open at once (tensor path and scan path mixed),
+    collected in order, return exactly what the blocking call returns; an empty batch gives an empty ticket."""
+    ix, raw = build(vdb, "cosine", 30_000)
+    k = 10
+    batches = [R.synth_rows(R.SEED_QUERY, 1000 * i, nq, 512) for i, nq in enumerate((64, 1, 300, 2, 64))]
+    want = [tuple(a.copy() for a in ix.knn_query_padded(q, k)) for q in batches]
+    alloc = vdb.pinned_empty if pinned else (lambda shape, dt: np.empty(shape, dtype=dt))
+    for depth in (2, 3):
+        pending, got = [], []
+        for q in batches:
+            qh = alloc(q.shape, np.float32)
+            qh[:] = q
+            out = (alloc((len(q), k), np.int64), alloc((len(q), k), np.float32), alloc((len(q),), np.int32))
+            pending.append(ix.submit_query(qh, k, out=out))
+            if len(pending) == depth:
+                got.append(tuple(a.copy() for a in ix.collect_query(pending.pop(0))))
+        while pending:
+            got.append(tuple(a.copy() for a in ix.collect_query(pending.pop(0))))
+        for (wl, wd, wc), (gl, gd, gc) in zip(want, got):
+            assert (wl == gl).all() and (wd == gd).all() and (wc == gc).all()
+    l, d, c = ix.collect_query(ix.submit_query(np.zeros((0, 512), np.float32), k))
+    assert l.shape == (0, k) and c.shape == (0,)
