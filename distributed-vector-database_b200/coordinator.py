@@ -4,6 +4,8 @@
 torch.distributed job (`ShardedSearcher`)."""
 from __future__ import annotations
 
+import os
+
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -224,14 +226,17 @@ class PeerExchange:
     `exchange_handles(my_handle: bytes) -> list[bytes]` must return every rank's 64-byte handle in rank order
     (e.g. an all-gather over the job's process group)."""
 
-    def __init__(self, device: int, rank: int, world: int, max_slice: int, max_k: int, exchange_handles: Callable):
+    def __init__(self, device: int, rank: int, world: int, max_slice: int, max_k: int, exchange_handles: Callable,
+                 query_slot_bytes: int = 0):
         import ctypes as C
         from . import _ffi
         self._ffi, self._C = _ffi, C
         self.rank, self.world = rank, world
+        self.query_slot_bytes = int(query_slot_bytes)
         h = C.c_void_p()
         buf = (C.c_ubyte * 64)()
-        _ffi.check(_ffi.lib().vdb_xchg_create(device, rank, world, max_slice, max_k, C.byref(h), buf), "xchg_create")
+        _ffi.check(_ffi.lib().vdb_xchg_create_q(device, rank, world, max_slice, max_k, self.query_slot_bytes, C.byref(h), buf),
+                   "xchg_create")
         self._h = h.value
         handles = exchange_handles(bytes(buf))
         if len(handles) != world or any(len(x) != 64 for x in handles):
@@ -243,6 +248,22 @@ class PeerExchange:
         """Enqueue on `stream`: this rank's lists [nq,k] (device pointers) -> its slice's results [nq/world,k]."""
         self._ffi.check(self._ffi.lib().vdb_xchg_merge_dev(self._h, d_dist_ptr, d_ids_ptr, nq, int(k), o_dist_ptr,
                                                            o_ids_ptr, stream or None), "xchg_merge")
+
+    # ---- query all-gather over the copy engines (needs query_slot_bytes > 0) -----------------------------------
+    def query_slot(self, slot: int) -> int:
+        """device pointer of local query slot 0 / 1: the whole batch, [world][slice] rows in rank order"""
+        return int(self._ffi.lib().vdb_xchg_query_slot(self._h, int(slot)) or 0)
+
+    def gather_queries(self, slice_ptr: int, slice_bytes: int, slot: int, batch_no: int, stream: int) -> None:
+        """Enqueue on `stream` (a copy stream): this rank's slice (host or device pointer) -> its place in slot `slot`
+        here and, by DMA over NVLink, on every peer; then the arrival word `batch_no` in every rank's array."""
+        self._ffi.check(self._ffi.lib().vdb_xchg_gather_queries(self._h, slice_ptr, slice_bytes, int(slot), int(batch_no),
+                                                                stream or None), "xchg_gather_queries")
+
+    def wait_queries(self, slot: int, batch_no: int, stream: int) -> None:
+        """Enqueue on `stream` (the search stream): wait until every rank's slice of `batch_no` is in the local slot."""
+        self._ffi.check(self._ffi.lib().vdb_xchg_wait_queries(self._h, int(slot), int(batch_no), stream or None),
+                        "xchg_wait_queries")
 
     def status(self) -> None:
         """Raises RuntimeError if a step failed (a peer never arrived, or arrived with another batch size / k).
@@ -288,7 +309,8 @@ class ShardedIndex:
         self.px = None
         if exchange == "p2p" and self.world > 1:
             self.px = PeerExchange(index.device, self.rank, self.world, max_slice=sl, max_k=self.max_k,
-                                   exchange_handles=self._gather_handles)
+                                   exchange_handles=self._gather_handles,
+                                   query_slot_bytes=sl * self.world * index.dim * 4)
         elif exchange not in ("p2p", "nccl"):
             raise ValueError("exchange must be 'p2p' or 'nccl'")
         e = lambda *shape, dtype: torch.empty(shape, dtype=dtype, device=self.dev)          # noqa: E731
@@ -300,6 +322,7 @@ class ShardedIndex:
         self._o_ids = e(self.max_batch * self.max_k, dtype=torch.int64)
         self._o_dd = e(self.max_batch * self.max_k, dtype=torch.float32)
         self._views = {}
+        self._ce_gather = os.environ.get("VDB_CE_GATHER", "1") != "0"      # A/B switch of the copy-engine query gather
 
     def close(self) -> None:
         """Releases the peer-memory exchange (collective: every rank closes before the process group goes away)."""
@@ -324,8 +347,10 @@ class ShardedIndex:
         """`d_queries` [nq, dim] fp32 on this rank's GPU, the WHOLE batch -> (dist [n, k], ids [n, k]) device tensors
         of this rank's slice (`slice_of(nq)`; views of internal buffers, valid until the next call; enqueued on the
         current stream)."""
+        return self._search_ptr(d_queries.data_ptr(), int(d_queries.shape[0]), k)
+
+    def _search_ptr(self, q_ptr: int, nq: int, k: int):
         torch, dist = self._torch, self._dist
-        nq = int(d_queries.shape[0])
         if nq > self.max_batch or k > self.max_k:
             raise ValueError("batch or k beyond what this ShardedIndex was sized for")
         stream = torch.cuda.current_stream().cuda_stream
@@ -337,7 +362,7 @@ class ShardedIndex:
                                         self._o_ids[:s * k].view(s, k), self._o_dd[:s * k].view(s, k),
                                         self._o_ids[:s * k].view(s, k)[:hi - lo], self._o_dd[:s * k].view(s, k)[:hi - lo])
         ids, dd, lo, hi, s, o_ids, o_dd, r_ids, r_dd = v
-        self.ix.search_device(d_queries.data_ptr(), nq, k, ids.data_ptr(), dd.data_ptr(), 0, stream)
+        self.ix.search_device(q_ptr, nq, k, ids.data_ptr(), dd.data_ptr(), 0, stream)
         if self.world == 1:
             return dd, ids
         if self.px is not None:       # one kernel: peer stores over NVLink, flags, merge of the owned slice (ragged too)
@@ -369,11 +394,16 @@ class ShardedIndex:
         behind it.  Returns a ticket for `collect`.  With two batches in flight the host<->device copies of one batch
         (and the host's launch work) hide behind the search of the other; at most two tickets may be outstanding.
 
-        The all-gather stays on the SEARCH stream on purpose: it is a kernel that waits for its peers, and so is the
-        fused exchange + merge.  Two such kernels in flight at once on one GPU can deadlock a box (rank A: the
-        all-gather is resident and keeps the cooperative exchange kernel from being placed; rank B: the exchange kernel
-        is resident, spins for A, and its registers keep B's all-gather from being placed -- seen on 8 GPUs, caught by
-        the exchange's bounded wait).  One stream per rank makes them alternate."""
+        With the peer-memory exchange (`exchange="p2p"`) the all-gather of the slices runs on the COPY ENGINES too
+        (`PeerExchange.gather_queries`: the upload, then one DMA per peer over NVLink into the peers' query slots, then a
+        one-warp kernel that publishes the batch number; the search stream only waits for the arrival words), so it is
+        hidden behind the previous batch as well.  With `exchange="nccl"` the all-gather is an NCCL kernel and stays on
+        the SEARCH stream on purpose: it is a kernel that waits for its peers, and so is the fused exchange + merge.
+        Two such kernels in flight at once on one GPU can deadlock a box (rank A: the all-gather is resident and keeps
+        the cooperative exchange kernel from being placed; rank B: the exchange kernel is resident, spins for A, and
+        its registers keep B's all-gather from being placed -- seen on 8 GPUs, caught by the exchange's bounded wait).
+        The copy-engine form has no such kernel: the signal waits for nothing, the wait is one warp in front of the
+        search on the same stream."""
         torch, dist = self._torch, self._dist
         if not torch.is_tensor(q):
             q = torch.from_numpy(q)
@@ -386,10 +416,22 @@ class ShardedIndex:
                           "q": [self._q, e(self.max_batch, self.ix.dim, dtype=torch.float32)],
                           "free": [torch.cuda.Event(), torch.cuda.Event()], "out": [None, None]}
         P = self._pipe
-        slot = P["slot"]
-        P["slot"] ^= 1
         cur = torch.cuda.current_stream()
         up = P["stream"]
+        if self.px is not None and self.px.query_slot_bytes and self._ce_gather:
+            if not (q.is_pinned() and q.is_contiguous() and q.dtype == torch.float32):
+                raise ValueError("submit_host needs a contiguous float32 tensor in page-locked host memory")
+            batch_no = P["batch_no"] = P.get("batch_no", 0) + 1
+            slot = batch_no & 1
+            # this rank's merge of batch_no - 2 has completed => every peer has finished searching that batch, i.e.
+            # reading this slot: the DMA into the peers' slots may start
+            up.wait_event(P["free"][slot])
+            self.px.gather_queries(q.data_ptr(), n * self.ix.dim * 4, slot, batch_no, up.cuda_stream)
+            self.px.wait_queries(slot, batch_no, cur.cuda_stream)
+            dd, ids = self._search_ptr(self.px.query_slot(slot), n * self.world, k)
+            return self._finish_submit(P, slot, cur, dd, ids, q)
+        slot = P["slot"]
+        P["slot"] ^= 1
         up.wait_event(P["free"][slot])                     # the search that last read this query buffer has finished
         d_q = P["q"][slot][:n * self.world]
         mine = d_q[self.rank * n:(self.rank + 1) * n]
@@ -401,7 +443,12 @@ class ShardedIndex:
         if self.world > 1:
             dist.all_gather_into_tensor(d_q, mine, group=self.group)     # on the search stream: see above
         dd, ids = self.search_device(d_q, k)
+        return self._finish_submit(P, slot, cur, dd, ids, None)
+
+    def _finish_submit(self, P, slot, cur, dd, ids, keep):
+        torch = self._torch
         P["free"][slot].record(cur)
+        P["keep"] = (P.get("keep", (None, None))[1], keep)      # the host queries of the two batches in flight stay alive
         out = P["out"][slot]
         if out is None or tuple(out[0].shape) != tuple(ids.shape):
             out = P["out"][slot] = (torch.empty(tuple(ids.shape), dtype=torch.int64).pin_memory(),

@@ -202,9 +202,10 @@ def _worker_sharded_index(rank, world, port, n, dim, k, exchange, out):
             res[nq] = (lo_hi, ids.numpy().copy(), dd.numpy().copy())
         # pipelined form (submit_host / collect, two batches in flight) == one batch at a time
         batches = []
-        for b in range(5):
-            q = R.synth_rows(R.SEED_QUERY, 500 + 64 * b, 64, dim)
-            sl = 64 // world
+        for b in range(9):             # both query slots are reused several times, with two batch sizes
+            nqb = 64 if b % 3 else 32
+            q = R.synth_rows(R.SEED_QUERY, 500 + 64 * b, nqb, dim)
+            sl = nqb // world
             batches.append(torch.from_numpy(q[rank * sl:(rank + 1) * sl].copy()).pin_memory())
         want = []
         for qb in batches:
