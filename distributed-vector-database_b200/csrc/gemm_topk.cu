@@ -676,11 +676,14 @@ struct EpsModel {
     float eps_rel;            // bound on |approx dot - exact dot| / (||q|| ||d||)
     float eps_abs;            // + eps_abs * (||q|| + ||d||max): fp16 subnormal rounding of single elements
     int metric;               // 0 = L2, 1 = ip / cosine
+    float eps_dd;             // L2 in direct form over rounded rows (candidates of the shadow-plane scan): + eps_dd * ||d||^2max
+    float eps_sum;            //   ... + eps_sum * (||q||^2 + ||d||^2max): fp32 accumulation of the dim squared differences
 };
 // `at` = the value (offset included) whose magnitude scales the fp32 slack
 __device__ __forceinline__ float approx_eps(const EpsModel& m, float qn2, float dmax2, float at) {
     const float eb = m.eps_rel * sqrtf(qn2) * sqrtf(dmax2) + m.eps_abs * (sqrtf(qn2) + sqrtf(dmax2));
-    return m.metric == 0 ? 2.0f * eb + 4e-7f * (qn2 + dmax2 + fabsf(at)) : eb + 4e-7f * (1.0f + fabsf(at));
+    return m.metric == 0 ? 2.0f * eb + m.eps_dd * dmax2 + (m.eps_sum + 4e-7f) * (qn2 + dmax2) + 4e-7f * fabsf(at)
+                         : eb + 4e-7f * (1.0f + fabsf(at));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -948,6 +951,7 @@ struct RerankParams {
     const int* cnt;           // [nq] keys in the buffer (may exceed cap: overflow)
     int cap;
     const uint32_t* tomb; uint32_t n_rows;
+    int approx_is_dist;       // the keys and tau carry approximate DISTANCES (offset included), not contraction values
 };
 
 // Exact fp32 distances of (query, row) in the scan kernel's summation order -> sortable keys; whole warp, NR rows
@@ -1162,7 +1166,7 @@ __global__ void __launch_bounds__(RW_MAX_THREADS) rerank_window_kernel(const Rer
     n = min(n, p.cap);
     const float qn2 = p.qn2[q];
     const float dmax2 = __uint_as_float(*p.max_sqnorm_bits);
-    const float off = p.metric == 0 ? qn2 : 1.0f;
+    const float off = p.approx_is_dist ? 0.0f : (p.metric == 0 ? qn2 : 1.0f);
     const float INF = __int_as_float(0x7f800000);
     // value bits of a_x + 2 eps (with a margin for the rounding of the sum); non-finite: keep everything.
     // eps(at) = s_eps0 + 4e-7 |at|: the part with the square roots is computed once per query, not per thread
@@ -1687,6 +1691,51 @@ cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearch
     const unsigned xgrid = (unsigned)std::min<size_t>(a.nq, (size_t)a.num_sms * 2);
     e = a.f16 ? launch_pdl(exact_fallback_kernel<__half>, dim3(xgrid), dim3(XF_THREADS), 0, st, rp, (int)a.nq)
               : launch_pdl(exact_fallback_kernel<float>, dim3(xgrid), dim3(XF_THREADS), 0, st, rp, (int)a.nq);
+    count_launch();
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+int gemm_topk_candidate_kp(int k) { return k >= 1 && k <= 32 ? kp_for_k(k) : 0; }
+
+cudaError_t gemm_topk_candidate_buffers(GemmWorkspace& ws, size_t nq, int kp, CandidateBuffers* out) {
+    cudaError_t e = ensure_ws(ws);
+    if (e != cudaSuccess) return e;
+    auto* w = static_cast<GemmWsImpl*>(ws.impl);
+    if ((e = grow_dev(w->buf, w->buf_cap, nq * (size_t)kp)) != cudaSuccess) return e;
+    if ((e = grow_dev(w->cnt, w->cnt_cap, nq)) != cudaSuccess) return e;
+    if ((e = grow_dev(w->thr, w->thr_cap, nq)) != cudaSuccess) return e;
+    out->keys = w->buf; out->stride = (size_t)kp; out->cnt = w->cnt; out->tau = w->thr;
+    return cudaSuccess;
+}
+
+cudaError_t gemm_topk_rerank_candidates(GemmWorkspace& ws, const GemmSearchArgs& a, int kp, cudaStream_t st) {
+    cudaError_t e = ensure_ws(ws);
+    if (e != cudaSuccess) return e;
+    auto* w = static_cast<GemmWsImpl*>(ws.impl);
+    if ((e = grow_dev(w->flags, w->flags_cap, a.nq)) != cudaSuccess) return e;
+    // the candidates' distances were computed in fp32 from fp16-ROUNDED rows and the fp32 query: one operand rounded
+    // (u = 2^-11), fp32 accumulation of `dim` terms.  L2 was taken in direct form sum (q - d16)^2, whose error also has
+    // the term 2 d.(d16 - d) <= 2u ||d||^2 (eps_dd, with u^2 and slack)
+    EpsModel em{};
+    em.eps_rel = 4.9e-4f + (float)a.dim * 1.1920929e-7f + 1.0e-4f;
+    em.eps_abs = 3.0e-8f * sqrtf((float)a.dim);
+    em.metric = a.metric;
+    em.eps_dd = a.metric == 0 ? 1.1e-3f : 0.0f;
+    em.eps_sum = a.metric == 0 ? 2.0f * (float)a.dim * 1.1920929e-7f : 0.0f;       // sum <= 2 (||q||^2 + ||d||^2), dim * 2^-23 of it
+    RerankParams rp{};
+    rp.approx = w->buf; rp.stride = (size_t)kp; rp.overflow = w->overflow; rp.tau = w->thr;
+    rp.rows = a.rows; rp.row_bytes = (uint32_t)((size_t)a.ld * 4); rp.ld = a.ld;
+    rp.labels = a.labels; rp.q = a.q; rp.qn2 = a.qn2; rp.max_sqnorm_bits = a.d_max_sqnorm_bits;
+    rp.k = a.k; rp.metric = a.metric;
+    rp.em = em;
+    rp.f16_range = 1;
+    rp.out_ids = a.out_ids; rp.out_dist = a.out_dist; rp.out_counts = a.out_counts;
+    rp.flags = w->flags; rp.n_flagged = w->n_flagged; rp.n_fallback = w->n_fallback;
+    rp.cnt = w->cnt; rp.cap = kp; rp.tomb = a.tomb; rp.n_rows = a.n_rows;
+    rp.approx_is_dist = 1;
+    if ((e = launch_rerank_window<float>(kp, rp, a.nq, st)) != cudaSuccess) return e;
+    const unsigned xgrid = (unsigned)std::min<size_t>(a.nq, (size_t)a.num_sms * 2);
+    e = launch_pdl(exact_fallback_kernel<float>, dim3(xgrid), dim3(XF_THREADS), 0, st, rp, (int)a.nq);
     count_launch();
     return e != cudaSuccess ? e : cudaGetLastError();
 }

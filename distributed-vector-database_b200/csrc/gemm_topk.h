@@ -49,6 +49,17 @@ struct LevelPlan {
 };
 LevelPlan gemm_topk_level_plan(size_t nq, size_t n_rows, int k);
 
+// Exact re-rank of candidates that another kernel collected (the scan over the fp16 shadow plane, vdb_api.cu): per
+// query up to kp keys (approximate DISTANCE, row), their count and tau = a bound from below on the approximate
+// distance of every row that is not a candidate.  candidate_buffers hands out the workspace's arrays to fill;
+// rerank_candidates enqueues K4w (window re-rank + certificate) and K4x (exact re-search of queries whose
+// certificate failed).  a.q / a.qn2 are the prepared queries, a.rows the exact rows; the per-query overflow flags
+// and the flagged-query counter must have been cleared (gemm_topk_prep_targets + the prepare kernel).
+struct CandidateBuffers { uint64_t* keys = nullptr; size_t stride = 0; int* cnt = nullptr; float* tau = nullptr; };
+int gemm_topk_candidate_kp(int k);       // candidates to collect for a top-k (0: k too large for this route)
+cudaError_t gemm_topk_candidate_buffers(GemmWorkspace& ws, size_t nq, int kp, CandidateBuffers* out);
+cudaError_t gemm_topk_rerank_candidates(GemmWorkspace& ws, const GemmSearchArgs& a, int kp, cudaStream_t st);
+
 bool gemm_topk_supported(int dim, int ld, bool f16, int k, size_t n_rows);
 cudaError_t gemm_topk_search(GemmPlan& plan, GemmWorkspace& ws, const GemmSearchArgs& a, cudaStream_t st, std::string& err);
 // queries this workspace has re-searched exactly on the device so far (certificate failed / buffer overflowed);

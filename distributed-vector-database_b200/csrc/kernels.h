@@ -32,6 +32,11 @@ struct ScanParams {
     int64_t* out_ids;        // [nq][k] final results (-1 / +inf padded), out_counts optional
     float* out_dist;
     int* out_counts;
+    // Candidate mode (in-kernel merge only; the scan ran over an APPROXIMATE plane of the rows, e.g. the fp16 shadow):
+    // instead of final results the k best keys (distance, label) go to cand_keys[q][0..k), their number to cand_cnt[q]
+    // and cand_tau[q] = the k-th distance (+inf with fewer than k live rows): every row that is not a candidate lies
+    // at or above it.  The exact re-rank (K4w) takes it from there.
+    uint64_t* cand_keys; size_t cand_stride; int* cand_cnt; float* cand_tau;
 };
 struct ScanPlan { int grid, ctas_per_sm, stages; size_t smem; int merge_group, merge_groups; };   // grid == 0: does not fit
 constexpr int SCAN_MERGE_KEYS = 4096;    // keys one in-kernel merge step holds in shared memory

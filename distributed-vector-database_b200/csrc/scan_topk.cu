@@ -86,12 +86,20 @@ struct ScanCtl {            // shared-memory control block of the candidate ring
     uint32_t pad;
 };
 
-template <typename T, int NQ>
+// METRIC (0 = squared L2 in direct form, 1 = 1 - dot) and QREG (the query in registers, see below) are template
+// parameters: as run-time branches inside the 16-stage unrolled accumulation loop they quadrupled the code (13k SASS
+// instructions) and a fifth of the warp samples sat in instruction-cache misses (stall_no_inst).
+template <typename T, int NQ, int METRIC, bool QREG>
 __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_topk_kernel(const ScanParams p) {
     pdl_prologue();
     constexpr int PER16 = Elem<T>::PER16;
     constexpr int VS = SCAN_R * NQ;   // (row, query) values a warp produces per stage
-    constexpr int G = 32 / VS;        // stages whose partial sums are reduced together
+    // (row, query) values reduced together.  32 amortises the threshold test and the ballot best, but unrolls the
+    // accumulation over 32 / VS stages; the register-query variant (short rows: the code per stage is the cost) takes
+    // 8: the unrolled loop is a quarter as long and stays in the instruction cache, at 9 shuffles per 8 values
+    // instead of 31 per 32.
+    constexpr int NV = QREG ? 8 : 32;
+    constexpr int G = NV / VS;        // stages whose partial sums are reduced together
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t row_bytes = p.row_bytes;
     const uint32_t stage_bytes = row_bytes * SCAN_STAGE_ROWS;
@@ -207,20 +215,58 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_topk_kernel(const ScanPa
         // Per-lane partial sums of G consecutive stages (32 (row, query) values) stay in registers and are
         // reduced together: 31 shuffles + one threshold test + one ballot per 32 values instead of per stage.
         const int nld16 = row_bytes / 512;  // 16-byte lane loads per row
+        // One query against 1 KB rows (512 fp16 -- the shadow plane of a 512-d fp32 shard -- or 256 fp32): a lane meets
+        // the same 2 x PER16 query elements in every row, so they live in registers.  Read from shared memory they cost
+        // as many bytes as the rows themselves (fp32 query against fp16 rows, shared by SCAN_R = 2 rows): bulk-copy
+        // writes + row reads + query reads then run the shared-memory pipe at ~0.75 of its bandwidth and the scan at
+        // 4.9 TB/s instead of the HBM rate.
+        static_assert(!QREG || NQ == 1, "register-resident query: one query");     // launched only when nld16 == 2
+        float qreg[QREG ? 2 : 1][PER16];
+        if constexpr (QREG) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int e = 0; e < PER16; ++e) qreg[c][e] = qs[(size_t)(c * 32 + lane) * PER16 + e];
+        }
         const uint32_t my_iters = nchunks > blockIdx.x ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
         volatile ScanCtl* vctl = ctl;
         int s = 0;
         uint32_t ph = 0;
         for (uint32_t it0 = 0; it0 < my_iters; it0 += G) {
-            float acc[32];
+            float acc[NV];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) acc[i] = 0.0f;
+            for (int i = 0; i < NV; ++i) acc[i] = 0.0f;
 #pragma unroll
             for (int g = 0; g < G; ++g) {
                 if (it0 + g < my_iters) {   // warp-uniform
                     mbar_wait(&full[s], ph);
                     const uint8_t* sbase = stage_base + (size_t)s * stage_bytes + (size_t)(warp * SCAN_R) * row_bytes;
-                    if (!(p.dbg & 1)) {
+                    if constexpr (QREG) {
+                        {
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {
+                                float dv[SCAN_R][PER16];
+#pragma unroll
+                                for (int r = 0; r < SCAN_R; ++r)
+                                    Elem<T>::load(sbase + (size_t)r * row_bytes + (size_t)(c * 32 + lane) * 16, dv[r]);
+#pragma unroll
+                                for (int r = 0; r < SCAN_R; ++r) {
+                                    float a = acc[g * VS + r];
+                                    if constexpr (METRIC == 0) {
+#pragma unroll
+                                        for (int e = 0; e < PER16; ++e) {
+                                            const float t = dv[r][e] - qreg[c][e];
+                                            a = fmaf(t, t, a);
+                                        }
+                                    } else {
+#pragma unroll
+                                        for (int e = 0; e < PER16; ++e) a = fmaf(dv[r][e], qreg[c][e], a);
+                                    }
+                                    acc[g * VS + r] = a;
+                                }
+                            }
+                        }
+                    } else if (!(p.dbg & 1)) {   // (dbg & 1: no accumulation, experiments)
 #pragma unroll 2
                         for (int c = 0; c < nld16; ++c) {
                             float dv[SCAN_R][PER16];
@@ -239,7 +285,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_topk_kernel(const ScanPa
 #pragma unroll
                                 for (int r = 0; r < SCAN_R; ++r) {
                                     float a = acc[g * VS + r * NQ + qi];
-                                    if (p.metric == 0) {
+                                    if constexpr (METRIC == 0) {
 #pragma unroll
                                         for (int e = 0; e < PER16; ++e) {
                                             const float t = dv[r][e] - qv[e];
@@ -263,14 +309,14 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_topk_kernel(const ScanPa
                 if (acc[0] == 123.456f) lists[0] = 0;
                 continue;
             }
-            warp_sum_multi<32>(acc);        // lane L now holds the total of value index vi
-            const int vi = value_index_of_lane<32>(lane);
+            warp_sum_multi<NV>(acc);        // lane L now holds the total of value index vi (NV < 32: 32 / NV lanes do)
+            const int vi = value_index_of_lane<NV>(lane);
             const int g = vi / VS, rem = vi - g * VS;
             const int r = rem / NQ, qi = rem - r * NQ;
             const uint32_t it = it0 + g;
             const uint32_t row = (blockIdx.x + it * gridDim.x) * SCAN_STAGE_ROWS + warp * SCAN_R + r;
-            const float dist = (p.metric == 0) ? acc[0] : 1.0f - acc[0];
-            const bool valid = it < my_iters && row < p.n_rows && qi < p.nq;
+            const float dist = (METRIC == 0) ? acc[0] : 1.0f - acc[0];
+            const bool valid = it < my_iters && row < p.n_rows && qi < p.nq && (NV == 32 || lane == lane_of_value_index<NV>(vi));
             // high word (distance bits) of the list tail = current threshold of query qi
             const uint32_t tail_hi = reinterpret_cast<volatile uint32_t*>(lists + (size_t)qi * k + (k - 1))[1];
             bool pass = valid && float_to_ordered(dist) <= tail_hi;
@@ -332,6 +378,14 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_topk_kernel(const ScanPa
     if (!s_last) return;
     __threadfence();
     auto emit = [&](int qi, int cnt) {      // m_out[0..k) -> final outputs of query qi
+        if (p.cand_keys) {
+            for (int j = threadIdx.x; j < k; j += SCAN_THREADS) p.cand_keys[(size_t)qi * p.cand_stride + j] = m_out[j];
+            if (threadIdx.x == 0) {
+                p.cand_cnt[qi] = cnt;
+                p.cand_tau[qi] = cnt == k ? key_dist(m_out[k - 1]) : __int_as_float(0x7f800000);
+            }
+            return;
+        }
         for (int j = threadIdx.x; j < k; j += SCAN_THREADS) {
             const uint64_t key = m_out[j];
             const bool real = key != KEY_SENTINEL;
@@ -377,24 +431,33 @@ static size_t scan_fixed_smem(int nq_t, int ld, int k, int stages) {
     return (size_t)nq_t * ld * 4 + (size_t)nq_t * k * 8 + (size_t)scan_ring_slots(k) * 9 + (size_t)stages * 16 + 64 + 128;
 }
 
-template <typename T, int NQ>
-static cudaError_t launch_t(const ScanParams& p, int grid, size_t smem, cudaStream_t st) {
+template <typename T, int NQ, int METRIC, bool QREG>
+static cudaError_t launch_v(const ScanParams& p, int grid, size_t smem, cudaStream_t st) {
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured[dev & 63]) {
         cudaFuncAttributes fa{};
-        cudaError_t e = cudaFuncGetAttributes(&fa, scan_topk_kernel<T, NQ>);
+        cudaError_t e = cudaFuncGetAttributes(&fa, scan_topk_kernel<T, NQ, METRIC, QREG>);
         if (e != cudaSuccess) return e;
         // static + dynamic shared memory of a block may not exceed 227 KB
-        e = cudaFuncSetAttribute(scan_topk_kernel<T, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        e = cudaFuncSetAttribute(scan_topk_kernel<T, NQ, METRIC, QREG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  227 * 1024 - (int)fa.sharedSizeBytes);
         if (e != cudaSuccess) return e;
         configured[dev & 63] = true;
     }
-    cudaError_t e = launch_pdl(scan_topk_kernel<T, NQ>, dim3(grid), dim3(SCAN_THREADS), smem, st, p);
+    cudaError_t e = launch_pdl(scan_topk_kernel<T, NQ, METRIC, QREG>, dim3(grid), dim3(SCAN_THREADS), smem, st, p);
     count_launch();
     return e != cudaSuccess ? e : cudaGetLastError();
+}
+template <typename T, int NQ>
+static cudaError_t launch_t(const ScanParams& p, int grid, size_t smem, cudaStream_t st) {
+    if constexpr (NQ == 1) {
+        static const bool qreg_on = [] { const char* e = getenv("VDB_SCAN_QREG"); return !(e && e[0] == '0'); }();
+        if (qreg_on && p.row_bytes == 1024 && !(p.dbg & 1))
+            return p.metric == 0 ? launch_v<T, 1, 0, true>(p, grid, smem, st) : launch_v<T, 1, 1, true>(p, grid, smem, st);
+    }
+    return p.metric == 0 ? launch_v<T, NQ, 0, false>(p, grid, smem, st) : launch_v<T, NQ, 1, false>(p, grid, smem, st);
 }
 
 int scan_max_k(int nq_t, int ld, uint32_t row_bytes) {
@@ -443,7 +506,16 @@ ScanPlan scan_plan(int nq, uint32_t ld, uint32_t row_bytes, int k, uint32_t n_ro
     const size_t merge_bytes = 2 * (size_t)SCAN_MERGE_KEYS * sizeof(uint64_t);
     if (fuse && nq_t <= 2 && k <= SCAN_MERGE_KEYS && (size_t)stages * stage_bytes >= merge_bytes &&
         (size_t)scan_ring_slots(k) * 8 >= 256 * 4 + 32 + (size_t)k * 8) {
-        const int per_group = std::max(1, SCAN_MERGE_KEYS / k);
+        // one level while the lists together are a small merge; otherwise ~sqrt(grid) CTAs per group: both levels then
+        // rank a few hundred keys (a merge step costs about as much as it holds keys, and the last one is a serial
+        // tail behind the scan: 296 lists of 32 keys as 3 groups of 128 cost ~25 us more than as 18 groups of 17)
+        int per_group = std::max(1, SCAN_MERGE_KEYS / k);
+        if ((size_t)pl.grid * k > 1024) {
+            int r = 1;
+            while (r * r < pl.grid) ++r;
+            per_group = std::min(per_group, std::max(2, r));
+        }
+        if (const char* e = getenv("VDB_SCAN_MERGE_GROUP")) per_group = std::max(1, std::min(atoi(e), std::max(1, SCAN_MERGE_KEYS / k)));
         const int groups = (pl.grid + per_group - 1) / per_group;
         if ((size_t)groups * k <= (size_t)SCAN_MERGE_KEYS) { pl.merge_group = per_group; pl.merge_groups = groups; }
     }

@@ -147,8 +147,11 @@ struct vdb {
     // of 1/2/4/8 fp32 queries costs 297/300/341/570 us (beyond 4 queries the pass is LDS-bound, not HBM-bound),
     // the tensor path ~320 us for any small batch -> 4 for fp32 rows; fp16 rows do twice the work per byte -> 2
     std::atomic<long> opt_scan_batch{4};
+    std::atomic<long> opt_small_batch_tensor_rows{500000};   // 2..scan_batch queries take the tensor path from this many rows on
+    std::atomic<long> opt_shadow_scan_nq{1};          // ... for batches of up to this many queries (at most 2)
+    std::atomic<long> opt_shadow_scan_rows{65536};   // one or two queries scan the fp16 shadow plane from this many rows on
     std::atomic<long> opt_shadow{1};        // 1 = the tensor path contracts the fp16 shadow plane (fp32 shards)
-    std::atomic<long> stat_fallback{0}, stat_tensor_batches{0}, stat_scan_passes{0};
+    std::atomic<long> stat_fallback{0}, stat_tensor_batches{0}, stat_scan_passes{0}, stat_shadow_scans{0};
     GemmPlan gemm_plan;
     // opt-in timing of the dominant kernel (scan or tensor) with CUDA events on the launching stream
     std::atomic<long> opt_profile{0};
@@ -400,6 +403,71 @@ int scan_prepared(vdb* db, Workspace* ws, const float* d_qp, size_t nq, int k, i
     return VDB_OK;
 }
 
+// One or two queries against an fp32 shard that has an fp16 shadow plane: K1 streams the SHADOW (half the bytes of
+// the rows: the search is HBM-bound) and keeps the k' best approximate candidates per query (in-kernel merge), K4w
+// recomputes the few that can still matter from the fp32 rows and certifies that no other row can enter the top-k
+// (same rigorous error bound as the batched path), K4x re-searches exactly the rare query whose certificate fails.
+// Results are bit-identical to the fp32 scan.  VDB_ENOTSUP_INTERNAL: not applicable here, take the fp32 scan.
+constexpr int VDB_ENOTSUP_INTERNAL = -1000;
+int shadow_scan(vdb* db, Workspace* ws, const float* d_q_raw, size_t nq, int k, int64_t* d_ids, float* d_dist,
+                int* d_cnt, cudaStream_t st, size_t n) {
+    if (db->dtype == VDB_F16 || !db->shadow || !db->opt_shadow.load() || nq > (size_t)db->opt_shadow_scan_nq.load()) return VDB_ENOTSUP_INTERNAL;
+    if ((long)n < db->opt_shadow_scan_rows.load()) return VDB_ENOTSUP_INTERNAL;      // small shards: launches dominate
+    const uint32_t row_bytes16 = (uint32_t)db->ld16 * 2;
+    const int kp = gemm_topk_candidate_kp(k);
+    if (kp == 0 || row_bytes16 % 512 != 0 || n <= (size_t)kp) return VDB_ENOTSUP_INTERNAL;
+    const int group = nq > 1 ? 2 : 1;
+    if (scan_max_k(group, db->ld16, row_bytes16) < kp) return VDB_ENOTSUP_INTERNAL;
+    const ScanPlan pl = scan_plan(group, (uint32_t)db->ld16, row_bytes16, kp, (uint32_t)n, db->num_sms);
+    if (pl.grid == 0 || pl.merge_group == 0) return VDB_ENOTSUP_INTERNAL;
+
+    CU_TRY(grow(ws->d_q, ws->q_cap, nq * (size_t)db->ld));
+    CU_TRY(grow(ws->d_qn2, ws->qn2_cap, nq));
+    GemmSearchArgs a{};
+    a.rows = db->rows; a.ld = db->ld; a.dim = db->dim; a.f16 = false; a.n_rows = (uint32_t)n;
+    a.sqnorm = db->sqnorm; a.labels = db->labels; a.tomb = db->any_dead.load() ? db->tomb : nullptr;
+    a.q = ws->d_q; a.qn2 = ws->d_qn2; a.nq = nq; a.k = k;
+    a.metric = db->metric == VDB_L2 ? 0 : 1;
+    a.d_max_sqnorm_bits = db->d_max_sqnorm;
+    a.num_sms = db->num_sms;
+    a.out_ids = d_ids; a.out_dist = d_dist; a.out_counts = d_cnt;
+    GemmPrepTargets pt;
+    CU_TRY(gemm_topk_prep_targets(ws->gemm, a, &pt));                 // no shadow in `a`: no fp16 query plane wanted
+    CandidateBuffers cb;
+    CU_TRY(gemm_topk_candidate_buffers(ws->gemm, nq, kp, &cb));
+    CU_TRY(launch_prepare_queries(d_q_raw, nq, db->dim, db->ld, db->metric == VDB_COSINE, ws->d_q, ws->d_qn2, st, nullptr, 0,
+                                  pt.overflow, pt.n_flagged));
+
+    ScanParams sp{};
+    sp.rows = db->shadow;
+    sp.row_bytes = row_bytes16;
+    sp.ld = (uint32_t)db->ld16;
+    sp.n_rows = (uint32_t)n;
+    sp.labels = nullptr; sp.label_base = 0;                            // candidates carry ROW numbers: K4w maps them to labels
+    sp.tomb = a.tomb;
+    sp.k = kp;
+    sp.metric = a.metric;
+    sp.nq = (int)nq;
+    sp.q_raw = d_q_raw; sp.dim = db->dim; sp.normalize = db->metric == VDB_COSINE ? 1 : 0;
+    CU_TRY(grow(ws->d_keys, ws->keys_cap, nq * (size_t)pl.grid * kp));
+    if (!ws->d_scan_ctr) {
+        CU_TRY(cudaMalloc((void**)&ws->d_scan_ctr, (SCAN_MERGE_KEYS + 1) * sizeof(unsigned int)));
+        CU_TRY(cudaMemsetAsync(ws->d_scan_ctr, 0, (SCAN_MERGE_KEYS + 1) * sizeof(unsigned int), st));
+        CU_TRY(cudaMalloc((void**)&ws->d_group_keys, 2 * (size_t)SCAN_MERGE_KEYS * sizeof(uint64_t)));
+    }
+    sp.out_keys = ws->d_keys;
+    sp.merge_group = pl.merge_group; sp.merge_ctr = ws->d_scan_ctr; sp.group_keys = ws->d_group_keys;
+    sp.cand_keys = cb.keys; sp.cand_stride = cb.stride; sp.cand_cnt = cb.cnt; sp.cand_tau = cb.tau;
+    {
+        ProfScope prof(db, st);
+        CU_TRY(launch_scan_topk(sp, /*f16=*/true, pl, st));
+    }
+    db->stat_scan_passes.fetch_add(1);
+    db->stat_shadow_scans.fetch_add(1);
+    CU_TRY(gemm_topk_rerank_candidates(ws->gemm, a, kp, st));
+    return VDB_OK;
+}
+
 // Enqueue a search of nq device-resident raw queries on `st`.  Outputs are device pointers.  Nothing here waits for
 // the device: a query whose tensor-path certificate fails is re-searched exactly by a kernel of the same enqueue.
 int search_core(vdb* db, Workspace* ws, const float* d_q_raw, size_t nq, int k, int64_t* d_ids, float* d_dist,
@@ -421,10 +489,20 @@ int search_core(vdb* db, Workspace* ws, const float* d_q_raw, size_t nq, int k, 
     const long path = db->opt_path.load();
     bool tensor = false;
     if (path == 2) tensor = true;
-    else if (path == 0) tensor = (long)nq > db->opt_scan_batch.load();
+    else if (path == 0) {
+        tensor = (long)nq > db->opt_scan_batch.load();
+        // two to four queries against a large fp32 shard with a shadow plane: the tensor path streams half the bytes
+        // (1M x 512: 235 us against 300 - 340 us for the fp32 scan; its six launches lose below ~0.5M rows)
+        if (!tensor && nq >= 2 && !f16 && db->shadow && db->opt_shadow.load() && (long)n >= db->opt_small_batch_tensor_rows.load())
+            tensor = true;
+    }
     if (tensor && !gemm_topk_supported(db->dim, db->ld, f16, k, n)) {
         if (path == 2) return fail(VDB_EINVAL, "tensor path forced but unsupported for this shape/k");
         tensor = false;
+    }
+    if (!tensor && path == 0) {
+        const int rc = shadow_scan(db, ws, d_q_raw, nq, k, d_ids, d_dist, d_cnt, st, n);
+        if (rc != VDB_ENOTSUP_INTERNAL) return rc;
     }
     if (!tensor) return scan_prepared(db, ws, d_q_raw, nq, k, d_ids, d_dist, d_cnt, st, n, /*raw=*/true);
 
@@ -1404,6 +1482,9 @@ int vdb_set_option(vdb_t* db, const char* name, long value) {
     if (!strcmp(name, "path")) { db->opt_path.store(value); return VDB_OK; }
     if (!strcmp(name, "scan_batch")) { db->opt_scan_batch.store(value); return VDB_OK; }
     if (!strcmp(name, "shadow")) { db->opt_shadow.store(value); return VDB_OK; }
+    if (!strcmp(name, "small_batch_tensor_rows")) { db->opt_small_batch_tensor_rows.store(value); return VDB_OK; }
+    if (!strcmp(name, "shadow_scan_rows")) { db->opt_shadow_scan_rows.store(value); return VDB_OK; }
+    if (!strcmp(name, "shadow_scan_nq")) { db->opt_shadow_scan_nq.store(value < 0 ? 0 : value > 2 ? 2 : value); return VDB_OK; }
     if (!strcmp(name, "profile")) { db->opt_profile.store(value); return VDB_OK; }
     return fail(VDB_EINVAL, std::string("unknown option ") + name);
 }
@@ -1418,6 +1499,7 @@ long vdb_get_stat(vdb_t* db, const char* name) {
     }
     if (!strcmp(name, "tensor_batches")) return db->stat_tensor_batches.load();
     if (!strcmp(name, "scan_passes")) return db->stat_scan_passes.load();
+    if (!strcmp(name, "shadow_scans")) return db->stat_shadow_scans.load();
     if (!strcmp(name, "num_sms")) return db->num_sms;
     if (!strcmp(name, "profile_ns") || !strcmp(name, "profile_count")) {
         // sum of (stop - start) over the dominant-kernel launches recorded since the last read

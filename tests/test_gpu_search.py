@@ -590,3 +590,73 @@ def test_submit_collect_two_batches_in_flight(vdb, pinned):
             assert (wl == gl).all() and (wd == gd).all() and (wc == gc).all()
     l, d, c = ix.collect_query(ix.submit_query(np.zeros((0, 512), np.float32), k))
     assert l.shape == (0, k) and c.shape == (0,)
+
+
+# ---------------------------------------------------------------------------------------------
+# one or two queries on an fp32 shard with an fp16 shadow plane: K1 over the shadow + exact re-rank
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("metric", ["l2", "ip", "cosine"])
+@pytest.mark.parametrize("nq,k", [(1, 10), (2, 10), (1, 1), (2, 32), (1, 17)])
+def test_shadow_scan_parity_and_bitwise_equal_to_the_fp32_scan(vdb, metric, nq, k):
+    """The shadow-plane scan returns exactly what the fp32 scan returns (ids, distances bit for bit), tombstones and
+    labels that are not base + row included, and matches the oracle."""
+    n, dim = 20_000, 512
+    raw = R.synth_rows(R.SEED_DB, 0, n, dim) * np.float32(1.3)
+    labels = (np.arange(n)[::-1] * 2 + 5).astype(np.int64)
+    ix = vdb.Index(metric, dim)
+    ix.init_index(n)
+    ix.add_items(raw, labels)
+    dead = labels[[3, 500, 7777, 19_999]]
+    ix.mark_deleted(dead)
+    q = R.synth_rows(R.SEED_QUERY, 31, nq, dim) * np.float32(0.8)
+    ix.set_option("shadow_scan_rows", 1 << 40)            # off: the fp32 scan
+    want = tuple(a.copy() for a in ix.knn_query_padded(q, k))
+    assert ix.get_stat("shadow_scans") == 0
+    ix.set_option("shadow_scan_rows", 1000)
+    ix.set_option("shadow_scan_nq", 2)                    # default: single queries only (two are faster on the tensor path)
+    got = ix.knn_query_padded(q, k)
+    assert ix.get_stat("shadow_scans") == 1 and ix.get_stat("fallback_queries") == 0
+    assert (got[0] == want[0]).all() and (got[1] == want[1]).all() and (got[2] == want[2]).all()
+    stored = R.prepare_rows(raw, metric)
+    for i in range(nq):
+        msg = R.check_topk(got[0][i], got[1][i], q[i], stored, labels, k, metric, deleted=list(dead), rtol=RTOL)
+        assert msg is None, f"query {i}: {msg}"
+
+
+def test_shadow_scan_near_duplicates_fall_back_exactly(vdb):
+    """rows that differ below fp16 resolution: the certificate of the shadow scan fails, the flagged query is
+    re-searched exactly on the device; results equal the fp32 scan's."""
+    rng = np.random.default_rng(5)
+    base = R.synth_rows(R.SEED_DB, 0, 1, 512)[0]
+    rows = base[None, :] + rng.normal(0, 1e-5, size=(4000, 512)).astype(np.float32)
+    for metric in ("l2", "cosine"):
+        ix = vdb.Index(metric, 512)
+        ix.init_index(4000)
+        ix.add_items(rows, np.arange(4000))
+        q = (base[None, :] + rng.normal(0, 1e-5, size=(2, 512))).astype(np.float32)
+        ix.set_option("shadow_scan_rows", 1 << 40)
+        want = tuple(a.copy() for a in ix.knn_query_padded(q, 10))
+        ix.set_option("shadow_scan_rows", 1000)
+        ix.set_option("shadow_scan_nq", 2)
+        got = ix.knn_query_padded(q, 10)
+        assert ix.get_stat("shadow_scans") == 1 and ix.get_stat("fallback_queries") > 0
+        assert (got[0] == want[0]).all() and (got[1] == want[1]).all()
+
+
+def test_shadow_scan_short_results_and_wide_norm_spread(vdb):
+    """fewer live rows than k' (everything is a candidate, no certificate needed); rows whose norms differ by 100x
+    with an L2 query far from all of them (the direct-form error terms of the bound)."""
+    dim = 512
+    raw = R.synth_rows(R.SEED_DB, 0, 3000, dim)
+    raw[::7] *= np.float32(100.0)
+    ix = vdb.Index("l2", dim)
+    ix.init_index(3000)
+    ix.add_items(raw, np.arange(3000))
+    ix.set_option("shadow_scan_rows", 1000)
+    ix.set_option("shadow_scan_nq", 2)
+    q = R.synth_rows(R.SEED_QUERY, 3, 2, dim) * np.float32(0.01)
+    assert_parity(ix, raw, "l2", "f32", q, 10)
+    assert_parity(ix, raw, "l2", "f32", q * np.float32(5000.0), 10)
+    assert ix.get_stat("shadow_scans") == 2
+    ix.mark_deleted(np.arange(20, 3000))
+    assert_parity(ix, raw, "l2", "f32", q[:1], 10, deleted=list(range(20, 3000)))     # 20 live rows < k' = 32

@@ -1,4 +1,5 @@
-"""Search time against batch size for both paths (scan passes of <= 8 queries vs the tensor path), 1M x 512."""
+"""Search time against batch size: forced fp32 scan (passes of <= 8 queries), forced tensor path, and what the
+library picks itself (one or two queries: scan of the fp16 shadow plane + exact re-rank), 1M x 512."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -13,7 +14,7 @@ for nq in (1, 2, 3, 4, 5, 6, 8, 12, 16, 32, 64, 128, 256):
     vdb._ffi.check(lib.vdb_synth_dev(0xC0FFEE, 0, nq, 512, q.data_ptr(), st), "synth")
     ids = torch.empty((nq, 10), dtype=torch.int64, device=dev); dd = torch.empty((nq, 10), dtype=torch.float32, device=dev)
     res = {}
-    for path in (1, 2):
+    for path in (1, 2, 0):
         ix.set_option("path", path)
         for _ in range(3):
             ix.search_device(q.data_ptr(), nq, 10, ids.data_ptr(), dd.data_ptr(), 0, st)
@@ -25,4 +26,4 @@ for nq in (1, 2, 3, 4, 5, 6, 8, 12, 16, 32, 64, 128, 256):
             ix.search_device(q.data_ptr(), nq, 10, ids.data_ptr(), dd.data_ptr(), 0, st)
         e1.record(); torch.cuda.synchronize()
         res[path] = e0.elapsed_time(e1) / n * 1e3
-    print(f"nq={nq:4d}  scan {res[1]:9.1f} us   tensor {res[2]:9.1f} us   -> {'tensor' if res[2] < res[1] else 'scan'}", flush=True)
+    print(f"nq={nq:4d}  scan {res[1]:9.1f} us   tensor {res[2]:9.1f} us   auto {res[0]:9.1f} us (shadow scans so far {ix.get_stat('shadow_scans')})", flush=True)
