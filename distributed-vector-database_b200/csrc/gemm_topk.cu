@@ -1535,6 +1535,7 @@ LevelPlan gemm_topk_level_plan(size_t nq, size_t n_rows, int k) {
     const int n_pos = lp.n_pos;
     auto rank_after = [&](int seen) { return 4L * seen <= n_pos ? lp.kq : lp.kp; };
     lp.probe_tiles = std::min(n_pos, std::max(probe_tiles(lp.kq), lp.small_batch ? 64 : 0));
+    lp.probe_tiles = std::max(1, std::min(lp.probe_tiles, lp.cap / 8));      // the probe writes 8 keys per tile into the buffer
     lp.probe_rank = rank_after(lp.probe_tiles);
     int rank = lp.probe_rank, seen = lp.probe_tiles, pos = 0;
     while (pos < n_pos) {

@@ -1516,6 +1516,7 @@ long vdb_get_stat(vdb_t* db, const char* name) {
         return (long)(total_ms * 1e6);
     }
     if (!strcmp(name, "ld")) return db->ld;
+    if (!strcmp(name, "ld16")) return db->shadow ? db->ld16 : 0;
     if (!strcmp(name, "shadow")) return db->shadow ? 1 : 0;
     return -1;
 }

@@ -3,7 +3,7 @@
 #   tools/profile_round.sh r02
 # 1. the bench line and the reference arm (no profiler)   2. ncu launch list of the SAME bench command
 # 3. ncu --set full raw pages: the tensor kernel (fp16 shadow plane; tf32 on the fp32 rows; L2 k=100 batch 4096),
-#    K2s select, K4w window re-rank, the scan kernel (k=10 and k=100)
+#    K2s select, K4w window re-rank, the scan kernel (single query over the fp16 shadow plane; fp32 rows k=10 and k=100)
 set -u
 R=${1:-r02}; O=gpurun_out
 NCU="ncu --set full --clock-control none --import-source on"
@@ -28,7 +28,8 @@ cap gemm_tf32_cos_k10_b1024 gemm_filter 8 4 VDB_SHADOW=0 -- --no-single --steps 
 cap gemm_f16shadow_l2_k100_b4096 gemm_filter 10 5 X=1 -- --no-single --steps 3 --warmup 1 $C3
 cap select_l2_k100_b4096 select_kernel 9 1 X=1 -- --no-single --steps 3 --warmup 1 $C3
 cap rerank_l2_k100_b4096 rerank_window 2 1 X=1 -- --no-single --steps 3 --warmup 1 $C3
-cap scan_f32_k10 scan_topk 3 1 X=1 -- --batch 1 --steps 3 --warmup 3 --no-single
+cap scan_f16shadow_k10 scan_topk 3 1 X=1 -- --batch 1 --steps 3 --warmup 3 --no-single
+cap scan_f32_k10 scan_topk 3 1 X=1 -- --batch 1 --steps 3 --warmup 3 --no-single --no-shadow-scan
 cap scan_f32_l2_k100 scan_topk 3 1 X=1 -- --batch 1 --steps 3 --warmup 3 --no-single --rows 1250000 --metric l2 --k 100
 python tools/show.py $O/${R}_bench_n1.json
 tail -14 $O/${R}_launches_bench_summary.txt

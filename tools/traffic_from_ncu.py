@@ -29,6 +29,7 @@ CAPTURES = {   # raw page -> (traffic key, "sum" of all launches or "each")
     f"{R}_gemm_tf32_cos_k10_b1024_ncu_raw.csv": ("gemm_filter_kernel[tf32, VDB_SHADOW=0]|1000000x512 f32 cosine top-10, batch 1024", "sum"),
     f"{R}_gemm_f16shadow_l2_k100_b4096_ncu_raw.csv": ("gemm_filter_kernel|1250000x512 f32 l2 top-100, batch 4096", "sum"),
     f"{R}_scan_f32_k10_ncu_raw.csv": ("scan_topk_kernel|1000000x512 f32 cosine top-10", "each"),
+    f"{R}_scan_f16shadow_k10_ncu_raw.csv": ("scan_topk_kernel|1000000x512 f32 cosine top-10 shadow", "each"),
     f"{R}_scan_f32_l2_k100_ncu_raw.csv": ("scan_topk_kernel|1250000x512 f32 l2 top-100", "each"),
     f"{R}_select_l2_k100_b4096_ncu_raw.csv": ("select_kernel|1250000x512 f32 l2 top-100, batch 4096", "each"),
     f"{R}_rerank_l2_k100_b4096_ncu_raw.csv": ("rerank_window_kernel|1250000x512 f32 l2 top-100, batch 4096", "each"),
