@@ -149,7 +149,9 @@ struct vdb {
     std::atomic<long> opt_scan_batch{4};
     std::atomic<long> opt_small_batch_tensor_rows{500000};   // 2..scan_batch queries take the tensor path from this many rows on
     std::atomic<long> opt_shadow_scan_nq{1};          // ... for batches of up to this many queries (at most 2)
-    std::atomic<long> opt_shadow_scan_rows{65536};   // one or two queries scan the fp16 shadow plane from this many rows on
+    std::atomic<long> opt_shadow_scan_rows{360000};  // single queries scan the fp16 shadow plane from this many rows on (measured on
+                                                     // 512-d shards: 250k rows 104 vs 85 us for the fp32 scan, 500k 121 vs 154, 1M 181 vs 294:
+                                                     // four launches against one)
     std::atomic<long> opt_shadow{1};        // 1 = the tensor path contracts the fp16 shadow plane (fp32 shards)
     std::atomic<long> stat_fallback{0}, stat_tensor_batches{0}, stat_scan_passes{0}, stat_shadow_scans{0};
     GemmPlan gemm_plan;
