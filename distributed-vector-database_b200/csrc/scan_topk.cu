@@ -15,7 +15,11 @@
 //                 time, pre-filters against the current k-th key, inserts.  Consumers never take a lock or
 //                 wait for an insert (measured: inserts under a lock on the consumer path cost 50 us of a
 //                 335 us scan; with the selector the scan runs at the speed of the bare copy ring).
-// Each CTA leaves a sorted list of k keys per query; merge_topk.cu reduces grid lists to one.
+// Each CTA leaves a sorted list of k keys per query; for one or two queries the kernel reduces the lists itself (last
+// CTA of a group, then last group), wider passes leave them to merge_topk.cu.
+// Candidate mode (ScanParams::cand_keys): the scan ran over an approximate plane of the rows (the fp16 shadow of an
+// fp32 shard: half the bytes); the k best (distance, ROW) keys and the k-th distance go to the exact re-rank (K4w,
+// gemm_topk.cu) instead of the caller -- vdb_api.cu shadow_scan.
 #include <algorithm>
 #include <cstdlib>
 

@@ -71,7 +71,9 @@ int vdb_unmark_deleted(vdb_t *db, const int64_t *labels, size_t n);
  * Exact over all live rows.  Rows with fewer than k live neighbours are padded with label -1
  * and distance +inf; out_counts[q] (optional) is the number of real results.
  * nq <= 4 (2 for fp16 rows) takes the HBM-streaming scan kernel, larger nq the tcgen05 kernel + exact
- * fp32 re-rank. */
+ * fp32 re-rank.  On an fp32 shard with an fp16 shadow plane, a single query over >= 360k rows scans the shadow
+ * (half the bytes) and the candidates that can still matter are recomputed from the fp32 rows, and 2..4 queries
+ * over >= 500k rows take the tcgen05 path: the results are bit-identical to the fp32 scan's either way. */
 int vdb_search(vdb_t *db, const float *queries, size_t nq, int k, int64_t *out_labels,
                float *out_dist, int *out_counts);
 /* The same call in two halves, for a server that keeps more than one batch in flight (the reference's Thrift
@@ -166,6 +168,9 @@ void vdb_xchg_destroy(vdb_xchg_t *x);
 
 /* Introspection for bench.py / tests */
 uint64_t vdb_launch_count(void);              /* kernels this library has launched so far   */
+/* options: "path" (0 auto, 1 scan, 2 tensor), "scan_batch" (largest batch the scan takes in auto mode), "shadow"
+ * (0: tensor path on the stored rows), "shadow_scan_nq" (0..2: batches up to this size may scan the shadow plane;
+ * default 1), "shadow_scan_rows" / "small_batch_tensor_rows" (shard sizes from which those routes apply), "profile" */
 int vdb_set_option(vdb_t *db, const char *name, long value);
 long vdb_get_stat(vdb_t *db, const char *name); /* "fallback_queries", "tensor_batches", ... */
 const char *vdb_last_error(void);
