@@ -66,9 +66,8 @@ struct Workspace {
     uint64_t* d_keys = nullptr; size_t keys_cap = 0;   // per-CTA candidate lists
     unsigned int* d_scan_ctr = nullptr;                // arrival counters of the scan kernel's in-kernel merge (kept zero)
     uint64_t* d_group_keys = nullptr;                  // its group results: 2 queries x SCAN_MERGE_KEYS keys
-    int64_t* d_ids = nullptr; size_t ids_cap = 0;      // [nq*k]
-    float* d_dist = nullptr;  size_t dist_cap = 0;
-    int* d_cnt = nullptr;     size_t cnt_cap = 0;
+    uint8_t* d_out = nullptr; size_t out_cap = 0;      // results of a host-buffer call: ids [nq*k] | dist [nq*k] | counts [nq],
+                                                       // one block, so that small results come back in ONE copy
     // pinned host staging
     float* h_q = nullptr; size_t h_q_cap = 0;
     uint8_t* h_out = nullptr; size_t h_out_cap = 0;
@@ -249,9 +248,7 @@ void free_workspace(Workspace* w) {
     if (w->d_keys) cudaFree(w->d_keys);
     if (w->d_scan_ctr) cudaFree(w->d_scan_ctr);
     if (w->d_group_keys) cudaFree(w->d_group_keys);
-    if (w->d_ids) cudaFree(w->d_ids);
-    if (w->d_dist) cudaFree(w->d_dist);
-    if (w->d_cnt) cudaFree(w->d_cnt);
+    if (w->d_out) cudaFree(w->d_out);
     if (w->h_q) cudaFreeHost(w->h_q);
     if (w->h_out) cudaFreeHost(w->h_out);
     gemm_workspace_free(w->gemm);
@@ -844,26 +841,36 @@ int vdb_search_submit(vdb_t* db, const float* queries, size_t nq, int k, int64_t
     const size_t qelems = nq * (size_t)db->dim, nout = nq * (size_t)k;
     CU_TRY(grow(ws->d_q_in, ws->q_in_cap, qelems));
     CU_TRY(grow_host(ws->h_q, ws->h_q_cap, qelems));
-    CU_TRY(grow(ws->d_ids, ws->ids_cap, nout));
-    CU_TRY(grow(ws->d_dist, ws->dist_cap, nout));
-    CU_TRY(grow(ws->d_cnt, ws->cnt_cap, nq));
     const size_t out_bytes = nout * (sizeof(int64_t) + sizeof(float)) + nq * sizeof(int);
+    CU_TRY(grow(ws->d_out, ws->out_cap, out_bytes));
     CU_TRY(grow_host(ws->h_out, ws->h_out_cap, out_bytes));
+    int64_t* d_ids = reinterpret_cast<int64_t*>(ws->d_out);
+    float* d_dist = reinterpret_cast<float*>(ws->d_out + nout * sizeof(int64_t));
+    int* d_cnt = reinterpret_cast<int*>(ws->d_out + nout * (sizeof(int64_t) + sizeof(float)));
     // caller buffers that are already page-locked (vdb_host_alloc, cudaHostAlloc/Register, torch pin_memory) are
     // DMA'd directly; pageable ones go through the workspace's pinned staging buffers
-    const bool q_pinned = is_pinned_host(queries);
-    const bool out_pinned = is_pinned_host(out_labels) && is_pinned_host(out_dist) && (!out_counts || is_pinned_host(out_counts));
+    const bool q_pinned = qelems * sizeof(float) > 16384 && is_pinned_host(queries);   // a few rows: staged, no attribute query
+    // results: page-locked caller buffers take the DMA directly when they are large; small results (a single query: 124
+    // bytes in three arrays) come back as ONE copy of the contiguous device block into the pinned staging buffer and are
+    // copied out by the CPU in collect -- two enqueues and two copy-engine round trips less per request
+    const bool out_pinned = out_bytes > 16384 && is_pinned_host(out_labels) && is_pinned_host(out_dist) &&
+                            (!out_counts || is_pinned_host(out_counts));
     if (!q_pinned) memcpy(ws->h_q, queries, qelems * sizeof(float));
     CU_TRY(cudaMemcpyAsync(ws->d_q_in, q_pinned ? queries : ws->h_q, qelems * sizeof(float), cudaMemcpyHostToDevice, st));
-    rc = search_core(db, ws, ws->d_q_in, nq, k, ws->d_ids, ws->d_dist, ws->d_cnt, st, n);
+    rc = search_core(db, ws, ws->d_q_in, nq, k, d_ids, d_dist, d_cnt, st, n);
     if (rc) { cudaStreamSynchronize(st); return rc; }
     int64_t* h_ids = reinterpret_cast<int64_t*>(ws->h_out);
     float* h_dist = reinterpret_cast<float*>(ws->h_out + nout * sizeof(int64_t));
     int* h_cnt = reinterpret_cast<int*>(ws->h_out + nout * (sizeof(int64_t) + sizeof(float)));
     if (out_pinned) { h_ids = out_labels; h_dist = out_dist; h_cnt = out_counts; }
-    cudaError_t ce = cudaMemcpyAsync(h_ids, ws->d_ids, nout * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
-    if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_dist, ws->d_dist, nout * sizeof(float), cudaMemcpyDeviceToHost, st);
-    if (ce == cudaSuccess && h_cnt) ce = cudaMemcpyAsync(h_cnt, ws->d_cnt, nq * sizeof(int), cudaMemcpyDeviceToHost, st);
+    cudaError_t ce;
+    if (!out_pinned) {
+        ce = cudaMemcpyAsync(ws->h_out, ws->d_out, out_bytes, cudaMemcpyDeviceToHost, st);
+    } else {
+        ce = cudaMemcpyAsync(h_ids, d_ids, nout * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_dist, d_dist, nout * sizeof(float), cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess && h_cnt) ce = cudaMemcpyAsync(h_cnt, d_cnt, nq * sizeof(int), cudaMemcpyDeviceToHost, st);
+    }
     if (ce != cudaSuccess) { cudaStreamSynchronize(st); return fail(VDB_ECUDA, cudaGetErrorString(ce)); }
     auto* t = new vdb_ticket();
     t->db = db; t->ws = ws; t->nq = nq; t->nout = nout; t->out_pinned = out_pinned;
