@@ -138,6 +138,8 @@ def parse():
     ap.add_argument("--oracle-budget-s", type=float, default=240.0,
                     help="CPU-oracle time allowed per workload; beyond it the check falls back to the GPU cross-check "
                          "+ exact CPU distances of the returned rows")
+    ap.add_argument("--hnsw-rows", type=int, default=100_000,
+                    help="--impl reference: rows of the HNSW-port leg (oracle/hnsw_ref.c; 0 = skip it)")
     ap.add_argument("--configs", default="auto",
                     help="'auto' (configs 3 and 4 at --gpus 8), 'none', or a list like '3,4' (rows per GPU as at 8 GPUs)")
     return ap.parse_args()
@@ -335,7 +337,62 @@ def run_reference(a):
     hn = hnswlib_leg(wl)
     if hn is not None:
         line["hnswlib"] = hn
+    if a.hnsw_rows > 0:
+        line["hnsw_port"] = hnsw_port_leg(wl, rows_cap=a.hnsw_rows)
     print(json.dumps(line), flush=True)
+
+
+def hnsw_port_leg(wl: Workload, rows_cap: int = 100_000, nq: int = 2048):
+    """What the reference's APPROXIMATE walk does per second, and at what recall: oracle/hnsw_ref.c, a restatement of
+    hnswlib v0.8.0's HNSW (the library itself is not installable here) with the reference's parameters -- M=32,
+    ef_construction=128 (src/datanode/handler.py:86), ef=max(50, 2k) and 2k results asked for (:360-364) -- on a bounded
+    prefix of the same database, all host cores.  Informative only: `value` stays the exact scan (the GPU path is exact,
+    recall 1.0), and the synthetic rows are structureless (uniform), the hardest case for a graph index."""
+    try:
+        from oracle import hnsw_port
+        c_ref, cores = cpu_setup()
+        n = min(wl.rows, rows_cap)
+        raw = c_ref.synth_rows(SEED_DB, 0, n, wl.dim)
+        stored = c_ref.normalize(raw) if wl.metric == "cosine" else raw
+        q = c_ref.synth_rows(SEED_QUERY, 0, nq, wl.dim)
+        qn = c_ref.normalize(q) if wl.metric == "cosine" else q
+        t0 = time.perf_counter()
+        h = hnsw_port.HnswPort(stored, wl.metric, M=32, ef_construction=128, nthreads=cores)
+        build_s = time.perf_counter() - t0
+        k2, ef = 2 * wl.k, max(50, 2 * wl.k)                        # the handler asks for 2k and filters (:364,375-402)
+        h.knn_query(qn[:64], k2, ef, cores)
+        t0 = time.perf_counter()
+        hl, _ = h.knn_query(qn, k2, ef, cores)
+        dt = time.perf_counter() - t0
+        el, _, _ = c_ref.knn(q, stored, None, wl.k, wl.metric, nthreads=cores)
+        rec = float(np.mean([len(set(hl[i, :wl.k].tolist()) & set(el[i].tolist())) / wl.k for i in range(nq)]))
+        out = {"kind": "port of the HNSW algorithm of hnswlib v0.8.0 (oracle/hnsw_ref.c), not the library",
+               "rows": n, "queries": nq, "M": 32, "ef_construction": 128, "ef": ef, "k": wl.k, "qps": nq / dt,
+               "recall_at_k_vs_exact": rec, "build_s": build_s, "cores": cores, "max_level": h.max_level,
+               "note": "approximate search over the first %d rows of the same synthetic (uniform, structureless) database; "
+                       "the exact arms scan all %d rows" % (n, wl.rows)}
+        h.close()
+        # the same index parameters on CLUSTERED rows (what embeddings look like): 200 Gaussian clusters, sigma 0.3
+        rng = np.random.default_rng(7)
+        nc = min(n, 50_000)
+        cent = rng.normal(size=(200, wl.dim)).astype(np.float32)
+        rows_c = (cent[rng.integers(0, 200, nc)] + 0.3 * rng.normal(size=(nc, wl.dim))).astype(np.float32)
+        q_c = (cent[rng.integers(0, 200, nq)] + 0.3 * rng.normal(size=(nq, wl.dim))).astype(np.float32)
+        stored_c = c_ref.normalize(rows_c) if wl.metric == "cosine" else rows_c
+        qn_c = c_ref.normalize(q_c) if wl.metric == "cosine" else q_c
+        h = hnsw_port.HnswPort(stored_c, wl.metric, M=32, ef_construction=128, nthreads=cores)
+        h.knn_query(qn_c[:64], k2, ef, cores)
+        t0 = time.perf_counter()
+        hl, _ = h.knn_query(qn_c, k2, ef, cores)
+        dt = time.perf_counter() - t0
+        el, _, _ = c_ref.knn(q_c, stored_c, None, wl.k, wl.metric, nthreads=cores)
+        out["clustered"] = {"rows": nc, "qps": nq / dt,
+                            "recall_at_k_vs_exact": float(np.mean([len(set(hl[i, :wl.k].tolist()) & set(el[i].tolist())) / wl.k
+                                                                   for i in range(nq)]))}
+        h.close()
+        return out
+    except Exception as e:           # never lose the line to an optional leg
+        return {"error": repr(e)}
 
 
 def hnswlib_leg(wl: Workload, rows_cap: int = 100_000, nq: int = 256):

@@ -364,6 +364,11 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert "brute-force" in d["config"]["note"]              # labelled for what it is: not the HNSW walk
     assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    # the approximate walk the reference really does (HNSW restatement), informative, beside the exact value
+    hp = d["hnsw_port"]
+    assert "error" not in hp, hp
+    assert hp["rows"] == 20000 and hp["M"] == 32 and hp["ef_construction"] == 128 and hp["ef"] == 50 and hp["qps"] > 0
+    assert 0.0 <= hp["recall_at_k_vs_exact"] <= 1.0 and hp["clustered"]["recall_at_k_vs_exact"] >= 0.95
     # a rank other than 0 prints nothing and exits 0
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"],

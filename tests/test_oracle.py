@@ -207,3 +207,32 @@ def test_hnswlib_index_with_reference_parameters():
     want, _, _ = R.knn_exact(q, R.prepare_rows(raw, "cosine"), np.arange(n), k, "cosine")
     recall = np.mean([len(set(labels[i].tolist()) & set(want[i].tolist())) / k for i in range(len(q))])
     assert recall >= 0.9
+
+
+def test_hnsw_port_finds_the_neighbours_on_easy_data():
+    """oracle/hnsw_ref.c (the HNSW restatement timed by `bench.py --impl reference`): on low-dimensional and on
+    clustered data the reference's parameters (M=32, ef_construction=128, ef=50) must reach the exact neighbours, and
+    every returned distance is the exact distance of the returned label."""
+    from oracle import c_ref, hnsw_port
+    k = 10
+    raw = c_ref.synth_rows(R.SEED_DB, 0, 6000, 16)
+    q = c_ref.synth_rows(R.SEED_QUERY, 0, 64, 16)
+    h = hnsw_port.HnswPort(raw, "l2", nthreads=1)                      # one thread: a deterministic graph
+    hl, hd = h.knn_query(q, k, 50)
+    el, ed, _ = c_ref.knn(q, raw, None, k, "l2")
+    rec = np.mean([len(set(hl[i].tolist()) & set(el[i].tolist())) / k for i in range(len(q))])
+    assert rec >= 0.97, rec
+    for i in range(4):
+        want = ((raw[hl[i]] - q[i]) ** 2).sum(axis=1)
+        assert np.allclose(hd[i], want, rtol=1e-5) and (np.diff(hd[i]) >= 0).all()
+    assert 1 <= h.max_level <= 6 and 8 <= h.mean_degree0 <= 64
+    h.close()
+    rng = np.random.default_rng(0)
+    cent = rng.normal(size=(50, 128)).astype(np.float32)
+    rows = c_ref.normalize((cent[rng.integers(0, 50, 5000)] + 0.3 * rng.normal(size=(5000, 128))).astype(np.float32))
+    qs = (cent[rng.integers(0, 50, 32)] + 0.3 * rng.normal(size=(32, 128))).astype(np.float32)
+    h = hnsw_port.HnswPort(rows, "cosine", nthreads=2)                 # concurrent inserts
+    hl, _ = h.knn_query(c_ref.normalize(qs), k, 50)
+    el, _, _ = c_ref.knn(qs, rows, None, k, "cosine")
+    assert np.mean([len(set(hl[i].tolist()) & set(el[i].tolist())) / k for i in range(len(qs))]) >= 0.97
+    h.close()
