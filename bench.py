@@ -371,6 +371,17 @@ def hnsw_port_leg(wl: Workload, rows_cap: int = 100_000, nq: int = 2048):
                "recall_at_k_vs_exact": rec, "build_s": build_s, "cores": cores, "max_level": h.max_level,
                "note": "approximate search over the first %d rows of the same synthetic (uniform, structureless) database; "
                        "the exact arms scan all %d rows" % (n, wl.rows)}
+        # what ef the same graph needs for a usable recall on these rows (search only; the reference fixes ef = max(50, 2k))
+        sweep = []
+        for ef2 in (200, 800):
+            m = min(nq, 512)
+            t0 = time.perf_counter()
+            hl2, _ = h.knn_query(qn[:m], k2, ef2, cores)
+            dt2 = time.perf_counter() - t0
+            sweep.append({"ef": ef2, "qps": m / dt2,
+                          "recall_at_k_vs_exact": float(np.mean([len(set(hl2[i, :wl.k].tolist()) & set(el[i].tolist())) / wl.k
+                                                                 for i in range(m)]))})
+        out["ef_sweep"] = sweep
         h.close()
         # the same index parameters on CLUSTERED rows (what embeddings look like): 200 Gaussian clusters, sigma 0.3
         rng = np.random.default_rng(7)
